@@ -1,0 +1,101 @@
+"""ctypes binding of libhdbo_b200.so (the C ABI declared in include/hdbo_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or a call returns non-zero, this
+module raises.  The library is built in-tree by `__graft_entry__.build()` /
+`make -C hdbo_benchmark_b200/csrc` into hdbo_benchmark_b200/lib/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "libhdbo_b200.so"
+
+KERNEL_MATERN52 = 0
+KERNEL_RBF = 1
+ACQ_EI, ACQ_LOGEI, ACQ_UCB, ACQ_MEAN, ACQ_PI, ACQ_NONE = 0, 1, 2, 3, 4, -1
+KR_FULL, KR_LE_N, KR_LE_M, KR_GE_N, KR_GE_M, KR_GE_MN = range(6)
+
+_dp = C.c_void_p  # device pointers travel as integers
+
+
+class HdboGp(C.Structure):
+    """Mirror of `struct hdbo_gp` (include/hdbo_b200.h)."""
+
+    _fields_ = [
+        ("n", C.c_int32), ("d", C.c_int32), ("n_pad", C.c_int32), ("d_pad", C.c_int32),
+        ("kind", C.c_int32), ("batch", C.c_int32),
+        ("X", _dp), ("ldx", C.c_int64), ("y", _dp), ("center", _dp), ("inv_ls", _dp), ("hyp", _dp),
+        ("Xs", _dp), ("xn", _dp), ("R2", _dp), ("Awork", _dp), ("L", _dp), ("Linv", _dp), ("Linvt", _dp),
+        ("w", _dp), ("alpha", _dp), ("scal", _dp), ("info", _dp),
+    ]
+
+
+class HdboError(RuntimeError):
+    pass
+
+
+_SIGNATURES = {
+    "hdbo_version": (C.c_int, []),
+    "hdbo_gp_fit": (C.c_int, [C.POINTER(HdboGp), C.c_int, _dp]),
+    "hdbo_mll_grad": (C.c_int, [C.POINTER(HdboGp), _dp, _dp, _dp, _dp, _dp, _dp]),
+    "hdbo_posterior_workspace_bytes": (C.c_size_t, [C.POINTER(HdboGp), C.c_int64, C.c_int]),
+    "hdbo_posterior_acq": (C.c_int, [C.POINTER(HdboGp), _dp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_double,
+                                     _dp, _dp, _dp, C.c_int64, _dp, C.c_size_t, _dp]),
+    "hdbo_posterior_fwd": (C.c_int, [C.POINTER(HdboGp), _dp, C.c_int64, C.c_int64, C.c_int, _dp, _dp, C.c_int64,
+                                     _dp, C.c_size_t, _dp]),
+    "hdbo_posterior_joint_cov": (C.c_int, [C.POINTER(HdboGp), _dp, C.c_int64, C.c_int64, C.c_int, C.c_int, _dp,
+                                           C.c_int64, _dp, C.c_size_t, _dp]),
+    "hdbo_posterior_bwd": (C.c_int, [C.POINTER(HdboGp), _dp, C.c_int64, C.c_int64, C.c_int, _dp, _dp, _dp, C.c_int64,
+                                     C.c_int64, _dp, C.c_int64, _dp, C.c_size_t, _dp]),
+    "hdbo_acq_elementwise": (C.c_int, [_dp, _dp, C.c_int64, C.c_int, C.c_double, _dp, _dp, _dp, _dp]),
+    "hdbo_qei": (C.c_int, [_dp, _dp, _dp, C.c_int64, C.c_int, C.c_int64, C.c_double, C.c_double, _dp, _dp, _dp, _dp,
+                           _dp]),
+    "hdbo_argmax": (C.c_int, [_dp, C.c_int64, _dp, _dp, _dp, _dp]),
+    "hdbo_dgemm_nt": (C.c_int, [_dp, C.c_int64, _dp, C.c_int64, _dp, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                C.c_double, C.c_double, C.c_int, C.c_int, _dp]),
+    "hdbo_cdist": (C.c_int, [_dp, C.c_int64, C.c_int, C.c_int, _dp, _dp, _dp, _dp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Raises HdboError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = Path(os.environ.get("HDBO_B200_LIB", LIB_PATH))
+    if not path.exists():
+        raise HdboError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the CUDA hot path)"
+        )
+    lib = C.CDLL(str(path))
+    for name, (res, args) in _SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            if os.environ.get("HDBO_B200_DEV_PARTIAL"):  # developer builds of a subset of the ABI only
+                continue
+            raise HdboError(f"{path} does not export {name}; rebuild it")
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    if rc > 0:
+        raise HdboError(f"{what}: CUDA error {rc}")
+    raise HdboError(f"{what}: invalid argument #{-rc}")
+
+
+def ptr(t) -> int:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return 0 if t is None else t.data_ptr()

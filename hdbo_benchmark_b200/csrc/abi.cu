@@ -1,0 +1,163 @@
+// extern "C" entry points of libhdbo_b200.so (declared in include/hdbo_b200.h).  Host-side orchestration only:
+// argument checks, workspace carving, launch sequences on the caller's stream.  No allocation, no synchronisation.
+#include "gemm_core.cuh"
+#include "kernels.cuh"
+#include "elem.cuh"
+#include "grad.cuh"
+
+using namespace hdbo;
+
+#define TRY_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return (int)_e; } while (0)
+
+static inline int64_t rup(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+static int check_gp(const hdbo_gp* gp) {
+    if (!gp) return -1;
+    if (gp->n <= 0 || gp->d <= 0 || gp->batch <= 0) return -1;
+    if (gp->n_pad != rup(gp->n, 128) || gp->d_pad != rup(gp->d, 16)) return -1;
+    if (gp->kind != HDBO_KERNEL_MATERN52 && gp->kind != HDBO_KERNEL_RBF) return -1;
+    return 0;
+}
+
+extern "C" int hdbo_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int hdbo_gp_fit(const hdbo_gp* gp, int need_r2, void* stream_) {
+    if (int e = check_gp(gp)) return e;
+    if (need_r2 && !gp->R2) return -2;
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int np = gp->n_pad, dp = gp->d_pad, B = gp->batch;
+    const long long nn = (long long)np * np;
+    TRY_CUDA(cudaMemsetAsync(gp->info, 0, sizeof(int32_t) * B, st));
+    TRY_CUDA(launch_scale_inputs(gp->X, (int)gp->ldx, 0, gp->n, gp->d, gp->center, gp->inv_ls, gp->d, gp->Xs, dp, np,
+                                 (long long)np * dp, gp->xn, np, B, st));
+    SymBuildParams sb{};
+    sb.Xs = gp->Xs; sb.xn = gp->xn; sb.hyp = gp->hyp; sb.Khat = gp->Awork; sb.R2 = need_r2 ? gp->R2 : nullptr;
+    sb.ldx = dp; sb.ldk = np; sb.bsX = (long long)np * dp; sb.bsxn = np; sb.bsK = nn;
+    sb.n = gp->n; sb.tiles = np / 128; sb.kblocks = dp / BK; sb.kind = gp->kind;
+    TRY_CUDA(launch_sym_build(sb, B, st));
+    TRY_CUDA(chol_inverse(gp->Awork, gp->L, gp->Linv, gp->Linvt, np, nn, np / 128, gp->n, gp->info, B, st));
+    // w = Linv (y - m);  alpha = Linv^T w
+    TRY_CUDA(launch_tri_matvec(gp->Linv, np, nn, np, 0, nullptr, 0, gp->y, gp->n, gp->hyp, gp->w, np, B, st));
+    TRY_CUDA(launch_tri_matvec(gp->Linvt, np, nn, np, 1, gp->w, np, nullptr, gp->n, gp->hyp, gp->alpha, np, B, st));
+    TRY_CUDA(launch_fit_scalars(gp->L, np, nn, gp->w, gp->alpha, np, gp->n, np, gp->scal, B, st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+struct PostWs {
+    double *Zs, *zn, *Kstar, *meanpart, *varpart, *DK, *V, *T;
+    size_t bytes;
+};
+PostWs carve(const hdbo_gp* gp, int64_t rows, int keep, void* base) {
+    const size_t B = gp->batch, np = gp->n_pad, dp = gp->d_pad, nt = np / 128;
+    size_t off = 0;
+    auto take = [&](size_t n) { size_t o = off; off += rup((int64_t)n, 16); return (double*)base + o; };
+    PostWs w{};
+    w.Zs = take(B * rows * dp);
+    w.zn = take(B * rows);
+    w.Kstar = take(B * rows * np);
+    w.meanpart = take(B * nt * rows);
+    w.varpart = take(B * nt * rows);
+    if (keep) {
+        w.DK = take(B * rows * np);
+        w.V = take(B * rows * np);
+        w.T = take(B * rows * np);
+    }
+    w.bytes = off * sizeof(double);
+    return w;
+}
+
+// scale -> cross -> var for `mc` candidates starting at Z (rows_alloc = row capacity of the workspace arrays)
+cudaError_t posterior_chunk(const hdbo_gp* gp, const PostWs& w, int64_t rows_alloc, const double* Z, int64_t ldz,
+                            int64_t mc, int keep, cudaStream_t st) {
+    const int np = gp->n_pad, dp = gp->d_pad, B = gp->batch;
+    const int rp = (int)rup(mc, 128), mt = rp / 128, nt = np / 128;
+    cudaError_t e;
+    e = launch_scale_inputs(Z, (int)ldz, 0, (int)mc, gp->d, gp->center, gp->inv_ls, gp->d, w.Zs, dp, rp,
+                            (long long)rows_alloc * dp, w.zn, rows_alloc, B, st);
+    if (e != cudaSuccess) return e;
+    CrossParams c{};
+    c.Zs = w.Zs; c.Xs = gp->Xs; c.zn = w.zn; c.xn = gp->xn; c.alpha = gp->alpha; c.hyp = gp->hyp;
+    c.Kstar = w.Kstar; c.DK = keep ? w.DK : nullptr; c.meanpart = w.meanpart;
+    c.ldz = dp; c.ldx = dp; c.ldk = np;
+    c.bsZ = (long long)rows_alloc * dp; c.bsX = (long long)np * dp; c.bszn = rows_alloc; c.bsxn = np; c.bsalpha = np;
+    c.bsK = (long long)rows_alloc * np; c.bsmp = (long long)nt * rows_alloc;
+    c.m = (int)mc; c.n = gp->n; c.mtiles = mt; c.ntiles = nt; c.kblocks = dp / BK; c.kind = gp->kind;
+    e = launch_cross(c, B, st);
+    if (e != cudaSuccess) return e;
+    VarParams v{};
+    v.Kstar = w.Kstar; v.Linv = gp->Linv; v.V = keep ? w.V : nullptr; v.varpart = w.varpart;
+    v.ldk = np; v.ldl = np; v.ldv = np;
+    v.bsK = (long long)rows_alloc * np; v.bsL = (long long)np * np; v.bsV = (long long)rows_alloc * np;
+    v.bsvp = (long long)nt * rows_alloc; v.mtiles = mt; v.ntiles = nt;
+    return launch_var(v, B, st);
+}
+}  // namespace
+
+extern "C" size_t hdbo_posterior_workspace_bytes(const hdbo_gp* gp, int64_t rows, int keep_grad_state) {
+    if (check_gp(gp) || rows <= 0 || rows % 128) return 0;
+    return carve(gp, rows, keep_grad_state, nullptr).bytes;
+}
+
+extern "C" int hdbo_posterior_acq(const hdbo_gp* gp, const double* Z, int64_t ldz, int64_t m, int observation_noise,
+                                  int acq_kind, double acq_param, double* mean, double* var, double* acq, int64_t bso,
+                                  void* workspace, size_t workspace_bytes, void* stream_) {
+    if (int e = check_gp(gp)) return e;
+    if (!Z || ldz < gp->d) return -2;
+    if (m < 0) return -4;
+    if (m == 0) return 0;
+    if (!workspace) return -12;
+    cudaStream_t st = (cudaStream_t)stream_;
+    // largest multiple of 128 rows that fits the workspace
+    int64_t rows = rup(m, 128);
+    const size_t per128 = carve(gp, 128, 0, nullptr).bytes;
+    if (per128 > workspace_bytes) return -13;
+    while (rows > 128 && carve(gp, rows, 0, nullptr).bytes > workspace_bytes) {
+        int64_t guess = (int64_t)(workspace_bytes / per128) * 128;
+        rows = (guess < rows) ? guess : rows - 128;
+        if (rows < 128) rows = 128;
+    }
+    PostWs w = carve(gp, rows, 0, workspace);
+    const int nt = gp->n_pad / 128, B = gp->batch;
+    for (int64_t off = 0; off < m; off += rows) {
+        const int64_t mc = (m - off < rows) ? (m - off) : rows;
+        TRY_CUDA(posterior_chunk(gp, w, rows, Z + off * ldz, ldz, mc, 0, st));
+        TRY_CUDA(launch_finalize_acq(w.meanpart, w.varpart, (long long)nt * rows, nt, (int)rup(mc, 128), (int)mc, gp->hyp,
+                                     observation_noise, acq_kind, acq_param, mean ? mean + off : nullptr,
+                                     var ? var + off : nullptr, (acq && acq_kind >= 0) ? acq + off : nullptr, bso, B, st));
+    }
+    return 0;
+}
+
+extern "C" int hdbo_acq_elementwise(const double* mean, const double* var, int64_t m, int acq_kind, double acq_param,
+                                    double* acq, double* dmean, double* dvar, void* stream_) {
+    if (!mean || !var) return -1;
+    if (m < 0) return -3;
+    if (acq_kind < 0 || acq_kind > 4) return -4;
+    TRY_CUDA(launch_acq_elem(mean, var, m, acq_kind, acq_param, acq, dmean, dvar, (cudaStream_t)stream_));
+    return 0;
+}
+
+extern "C" int hdbo_argmax(const double* v, int64_t m, void* work, double* out_val, int64_t* out_idx, void* stream_) {
+    if (!v || m <= 0) return -1;
+    if (!work) return -3;
+    TRY_CUDA(launch_argmax(v, m, work, out_val, (long long*)out_idx, (cudaStream_t)stream_));
+    return 0;
+}
+
+extern "C" int hdbo_dgemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                             int64_t m_pad, int64_t n_pad, int64_t k_pad, double alpha, double beta, int krange,
+                             int lower_only, void* stream_) {
+    if (!A || !B || !C) return -1;
+    if (m_pad % 128 || n_pad % 128 || k_pad % 16 || lda % 2 || ldb % 2 || ldc % 2) return -7;
+    if (krange < 0 || krange > KR_GE_MN) return -12;
+    GemmParams g{};
+    g.A = A; g.B = B; g.C = C; g.Ct = nullptr;
+    g.lda = (int)lda; g.ldb = (int)ldb; g.ldc = (int)ldc; g.ldct = 0;
+    g.mtiles = (int)(m_pad / 128); g.ntiles = (int)(n_pad / 128); g.kblocks = (int)(k_pad / 16);
+    g.krange = krange; g.lower_only = lower_only; g.alpha = alpha; g.beta = beta;
+    TRY_CUDA(launch_gemm_nt(g, 1, (cudaStream_t)stream_));
+    return 0;
+}

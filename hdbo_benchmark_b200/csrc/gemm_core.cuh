@@ -1,0 +1,167 @@
+// FP64 "NT" GEMM tile mainloop for sm_100a:  acc[128x128] += A[128 x K] * B[128 x K]^T
+//
+// Both operands are row-major with the contraction index contiguous, which is how every
+// contraction on the GP hot path is laid out in HBM (scaled inputs [rows x d], K* [m x n],
+// L^-1 [n x n], L^-T [n x n]); see DESIGN.md "Data layout".
+//
+// Hardware mapping (measured, profiles/r01_fp64_peak.json): tcgen05 has no f64 kind, the FP64
+// tensor instruction on sm_100a is DMMA.8x8x4 (every mma.sync f64 shape lowers to it), peak
+// 37.0 TFLOP/s = 64 FMA/clk/SM.  One CTA = 256 threads = 8 warps in a 2 (M) x 4 (N) grid, each warp
+// owns a 64x32 sub-tile = 8x4 DMMA tiles = 64 accumulator doubles per thread.  Operands are staged
+// with cp.async (LDGSTS, 16 B) through a 3-stage ring of [128 x 16] slabs; the smem row stride is
+// 20 doubles so that the 8 rows x 4 k fragment read of a warp hits 16 distinct 8-byte banks per
+// half-warp (conflict-free).  Per k4 step a warp issues 12 LDS.64 and 32 DMMA, so the DMMA pipe is
+// the only saturated resource (smem traffic is 24 B/clk/SM of 128).
+//
+// All operand matrices handed to the mainloop are padded: row counts to multiples of 128, the
+// contraction length to a multiple of 16, leading dimensions to multiples of 16 doubles (128 B), so
+// the mainloop has no bounds checks and every cp.async is a full aligned 16-byte copy.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hdbo {
+
+constexpr int BM = 128;
+constexpr int BN = 128;
+constexpr int BK = 16;
+constexpr int STAGES = 3;
+constexpr int SLD = BK + 4;                  // smem row stride (doubles)
+constexpr int NTHREADS = 256;
+constexpr int TILE_ELEMS = BM * SLD;         // doubles per operand per stage
+constexpr int GEMM_SMEM_BYTES = STAGES * 2 * TILE_ELEMS * 8;   // 122880
+constexpr int KB_PER_TILE = BM / BK;         // k-blocks per 128-wide tile (8)
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// accumulator fragment of one thread: acc[mt][nt][e] = C[wm*64 + mt*8 + (lane>>2)][wn*32 + nt*8 + (lane&3)*2 + e]
+struct Frag {
+    double v[8][4][2];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) { v[i][j][0] = 0.0; v[i][j][1] = 0.0; }
+    }
+};
+
+__device__ __forceinline__ int frag_row(int mt) { return ((threadIdx.x >> 5) >> 2) * 64 + mt * 8 + ((threadIdx.x & 31) >> 2); }
+__device__ __forceinline__ int frag_col(int nt) { return ((threadIdx.x >> 5) & 3) * 32 + nt * 8 + ((threadIdx.x & 3) << 1); }
+
+__device__ __forceinline__ void load_slab(double* s, const double* __restrict__ g, int ld, int kb, int tid) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int c = tid + i * NTHREADS;
+        int row = c >> 3, ch = c & 7;
+        cp_async16(s + row * SLD + ch * 2, g + (size_t)row * ld + (size_t)kb * BK + ch * 2);
+    }
+}
+
+// gA / gB point at the first row of the 128-row operand slabs (column 0).  k-blocks [kb_begin, kb_end).
+__device__ __forceinline__ void gemm_nt_mainloop(const double* __restrict__ gA, int lda, const double* __restrict__ gB,
+                                                 int ldb, int kb_begin, int kb_end, double* smem, Frag& acc) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+    double* sA = smem;
+    double* sB = smem + STAGES * TILE_ELEMS;
+    const int nkb = kb_end - kb_begin;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < nkb) {
+            load_slab(sA + s * TILE_ELEMS, gA, lda, kb_begin + s, tid);
+            load_slab(sB + s * TILE_ELEMS, gB, ldb, kb_begin + s, tid);
+        }
+        cp_async_commit();
+    }
+    const int frag_off_a = (wm * 64 + (lane >> 2)) * SLD + (lane & 3);
+    const int frag_off_b = (wn * 32 + (lane >> 2)) * SLD + (lane & 3);
+    int slot = 0;
+    for (int it = 0; it < nkb; it++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nx = it + STAGES - 1;
+            int nslot = slot + STAGES - 1; if (nslot >= STAGES) nslot -= STAGES;
+            if (nx < nkb) {
+                load_slab(sA + nslot * TILE_ELEMS, gA, lda, kb_begin + nx, tid);
+                load_slab(sB + nslot * TILE_ELEMS, gB, ldb, kb_begin + nx, tid);
+            }
+            cp_async_commit();
+        }
+        const double* a_s = sA + slot * TILE_ELEMS + frag_off_a;
+        const double* b_s = sB + slot * TILE_ELEMS + frag_off_b;
+#pragma unroll
+        for (int k4 = 0; k4 < BK / 4; k4++) {
+            double a[8], b[4];
+#pragma unroll
+            for (int mt = 0; mt < 8; mt++) a[mt] = a_s[mt * 8 * SLD + k4 * 4];
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) b[nt] = b_s[nt * 8 * SLD + k4 * 4];
+#pragma unroll
+            for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) dmma884(acc.v[mt][nt][0], acc.v[mt][nt][1], a[mt], b[nt]);
+        }
+        slot = (slot + 1 == STAGES) ? 0 : slot + 1;
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+}
+
+// Deterministic per-row reduction of a per-thread value rowval[mt] (already summed over the thread's 8 columns):
+// lanes sharing a row (lane&3) via shuffles, then the 4 N-warps through smem in fixed order.
+// Result: out[r] for r in [0,128) valid in thread r (threads 0..127) after the call.
+__device__ __forceinline__ double tile_row_reduce(double (&rowval)[8], double* red /* >= 4*128 doubles */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+#pragma unroll
+    for (int mt = 0; mt < 8; mt++) {
+        double x = rowval[mt];
+        x += __shfl_xor_sync(0xffffffffu, x, 1);
+        x += __shfl_xor_sync(0xffffffffu, x, 2);
+        if ((lane & 3) == 0) red[wn * 128 + wm * 64 + mt * 8 + (lane >> 2)] = x;
+    }
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x < 128) r = ((red[threadIdx.x] + red[128 + threadIdx.x]) + red[256 + threadIdx.x]) + red[384 + threadIdx.x];
+    __syncthreads();
+    return r;
+}
+
+// Same along columns: colval[nt][e] summed over the thread's 8 rows; lanes sharing a column (lane>>2) via shuffles,
+// then the 2 M-warps through smem.  Result for column c valid in thread c (threads 0..127).
+__device__ __forceinline__ double tile_col_reduce(double (&colval)[4][2], double* red /* >= 2*128 doubles */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            double x = colval[nt][e];
+            x += __shfl_xor_sync(0xffffffffu, x, 4);
+            x += __shfl_xor_sync(0xffffffffu, x, 8);
+            x += __shfl_xor_sync(0xffffffffu, x, 16);
+            if ((lane >> 2) == 0) red[wm * 128 + wn * 32 + nt * 8 + (lane & 3) * 2 + e] = x;
+        }
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x < 128) r = red[threadIdx.x] + red[128 + threadIdx.x];
+    __syncthreads();
+    return r;
+}
+
+}  // namespace hdbo

@@ -1,0 +1,89 @@
+// Internal declarations shared by the .cu files of libhdbo_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hdbo_b200.h"
+
+namespace hdbo {
+
+constexpr double SQRT5 = 2.23606797749978969640917366873128;
+constexpr double INV_SQRT_2 = 0.70710678118654752440084436210485;
+constexpr double INV_SQRT_2PI = 0.39894228040143267793994605993438;
+constexpr double LOG_2PI = 1.83787706640934548356065947281123;
+constexpr double LOG_SQRT_PI_DIV_2 = 0.22579135264472743236309761494744;
+
+// k-block range selectors for triangular operands (tile indices are relative to the sub-matrix handed in, which is
+// always aligned on the diagonal of the triangular operand).
+enum KRange : int {
+    KR_FULL = 0,   // [0, K)
+    KR_LE_N = 1,   // k-tile <= n-tile   (B lower triangular, row-major)
+    KR_LE_M = 2,   // k-tile <= m-tile   (A lower triangular)
+    KR_GE_N = 3,   // k-tile >= n-tile   (B upper triangular)
+    KR_GE_M = 4,   // k-tile >= m-tile   (A upper triangular)
+    KR_GE_MN = 5,  // k-tile >= max(m,n) (both upper)
+};
+
+struct GemmParams {
+    const double* A; const double* B; double* C; double* Ct;  // C = alpha*A*B^T + beta*C ; Ct (optional) gets the transpose
+    int lda, ldb, ldc, ldct;
+    long long bsA, bsB, bsC, bsCt;                            // batch strides (elements)
+    int mtiles, ntiles, kblocks;                              // 128-tiles in M and N; 16-blocks in K
+    int krange;                                               // KRange
+    int lower_only;                                           // only tiles with m-tile >= n-tile (grid.x enumerates them)
+    double alpha, beta;
+};
+
+// kernel value k(r^2) and derivative dk/dr^2 for unit outputscale.  kind: 0 Matern-5/2, 1 RBF.
+__device__ __forceinline__ void kernel_eval(int kind, double r2, double& k, double& dk) {
+    if (kind == 0) {
+        double r = sqrt(fmax(r2, 1e-30));
+        double e = exp(-SQRT5 * r);
+        double t = 1.0 + SQRT5 * r;
+        k = (t + (5.0 / 3.0) * r * r) * e;
+        dk = -(5.0 / 6.0) * t * e;
+    } else {
+        double e = exp(-0.5 * r2);
+        k = e;
+        dk = -0.5 * e;
+    }
+}
+
+// ---- launch wrappers (each enqueues on `stream` and returns cudaGetLastError()) ----
+cudaError_t launch_gemm_nt(const GemmParams& p, int batch, cudaStream_t stream);
+
+cudaError_t launch_scale_inputs(const double* X, int ldx, long long bsX, int nrows, int d, const double* center,
+                                const double* inv_ls, long long bs_ls, double* Xs, int d_pad, int rows_pad,
+                                long long bsXs, double* norms, long long bsn, int batch, cudaStream_t stream);
+
+struct CrossParams {
+    const double* Zs; const double* Xs; const double* zn; const double* xn; const double* alpha; const double* hyp;
+    double* Kstar; double* DK; double* meanpart;
+    int ldz, ldx, ldk;
+    long long bsZ, bsX, bszn, bsxn, bsalpha, bsK, bsmp;
+    int m, n, mtiles, ntiles, kblocks, kind;
+};
+cudaError_t launch_cross(const CrossParams& p, int batch, cudaStream_t stream);
+
+struct SymBuildParams {
+    const double* Xs; const double* xn; const double* hyp;
+    double* Khat; double* R2;
+    int ldx, ldk;
+    long long bsX, bsxn, bsK;
+    int n, tiles, kblocks, kind;
+};
+cudaError_t launch_sym_build(const SymBuildParams& p, int batch, cudaStream_t stream);
+
+struct VarParams {
+    const double* Kstar; const double* Linv; double* V; double* varpart;
+    int ldk, ldl, ldv;
+    long long bsK, bsL, bsV, bsvp;
+    int mtiles, ntiles;
+};
+cudaError_t launch_var(const VarParams& p, int batch, cudaStream_t stream);
+
+// Cholesky factor + inverse of the padded SPD matrix (recursive, GEMM-rich); see kernels_chol.cu
+cudaError_t chol_inverse(double* Awork, double* L, double* Linv, double* Linvt, int ld, long long bs, int tiles,
+                         int n_true, int32_t* info, int batch, cudaStream_t stream);
+
+}  // namespace hdbo

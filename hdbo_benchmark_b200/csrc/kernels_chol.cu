@@ -1,0 +1,157 @@
+// FP64 Cholesky factor AND its inverse for the padded SPD matrix Khat = K + noise I  (SURVEY.md §8a row A2).
+//
+// Recursive block algorithm over 128-tiles [a, b), split at h:
+//     chol_inv([a,h))                                  -> L11, L11^-1 (and its transpose)
+//     L21    = A21 * L11^-T                            GEMM, B lower-triangular  (k-tile <= n-tile)
+//     A22   -= L21 * L21^T                             SYRK, lower tiles only
+//     chol_inv([h,b))                                  -> L22, L22^-1
+//     T^T    = L11^-T(as U11) * L21^T                  GEMM, A upper-triangular  (k-tile >= m-tile), scratch = upper-right of Awork
+//     L21inv = -L22^-1 * T                             GEMM, A lower-triangular  (k-tile <= m-tile), also stored transposed
+// so every flop above the 128x128 leaves runs in the DMMA mainloop with large K (n^3/3 for the factor, n^3/3 for
+// the inverse).  Having L^-1 explicitly turns every later triangular solve on the hot path (posterior variance,
+// alpha, K^-1 for the MLL gradient) into a GEMM / matvec -- the same trade BoTorch's fast_pred_var cache makes.
+//
+// The leaf factors one 128x128 diagonal tile in shared memory (rank-1 updates in LDL^T form, one barrier per
+// column) and inverts it in place.  A non-positive pivot records info = 1-based global index (first one wins) and
+// continues with a unit pivot so the stream never hangs; the host applies the jitter schedule.
+#include "gemm_core.cuh"
+#include "kernels.cuh"
+
+namespace hdbo {
+
+constexpr int LEAF_THREADS = 512;
+constexpr int LLD = 129;
+constexpr int LEAF_SMEM_BYTES = (128 * LLD + 128 + 8) * 8;
+
+__global__ void __launch_bounds__(LEAF_THREADS, 1)
+k_leaf_chol_inv(double* __restrict__ Awork, double* __restrict__ L, double* __restrict__ Linv, double* __restrict__ Linvt,
+                int ld, long long bs, int tile, int32_t* __restrict__ info) {
+    extern __shared__ __align__(16) double sm[];
+    double* S = sm;                 // [128][129]
+    double* col = sm + 128 * LLD;   // [128] staging column
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;   // 16 warps
+    const size_t base = (size_t)b * bs + (size_t)tile * 128 * ld + (size_t)tile * 128;
+    const double* Ag = Awork + base;
+    for (int e = tid; e < 128 * 128; e += LEAF_THREADS) {
+        int i = e >> 7, k = e & 127;
+        S[i * LLD + k] = (k <= i) ? Ag[(size_t)i * ld + k] : 0.0;
+    }
+    // ---- factorisation: S[i][k] -= S[i][j] S[k][j] / S[j][j]  (columns stay unscaled until the end) ----
+    for (int j = 0; j < 127; j++) {
+        __syncthreads();
+        double ajj = S[j * LLD + j];
+        if (!(ajj > 0.0)) {
+            if (tid == 0) { atomicCAS(info + b, 0, tile * 128 + j + 1); }
+            __syncthreads();
+            if (tid == 0) S[j * LLD + j] = 1.0;
+            __syncthreads();
+            ajj = 1.0;
+        }
+        const double inv = 1.0 / ajj;
+        for (int i = j + 1 + warp; i < 128; i += 16) {
+            const double lij = S[i * LLD + j] * inv;
+            for (int k = j + 1 + lane; k <= i; k += 32) S[i * LLD + k] = fma(-lij, S[k * LLD + j], S[i * LLD + k]);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double a = S[127 * LLD + 127];
+        if (!(a > 0.0)) { atomicCAS(info + b, 0, tile * 128 + 128); S[127 * LLD + 127] = 1.0; }
+    }
+    __syncthreads();
+    if (tid < 128) col[tid] = sqrt(S[tid * LLD + tid]);
+    __syncthreads();
+    for (int e = tid; e < 128 * 128; e += LEAF_THREADS) {
+        int i = e >> 7, k = e & 127;
+        if (k < i) S[i * LLD + k] = S[i * LLD + k] / col[k];
+        else if (k == i) S[i * LLD + k] = col[k];
+    }
+    __syncthreads();
+    double* Lg = L + base;
+    for (int e = tid; e < 128 * 128; e += LEAF_THREADS) {
+        int i = e >> 7, k = e & 127;
+        Lg[(size_t)i * ld + k] = S[i * LLD + k];
+    }
+    // ---- in-place inverse of the lower-triangular tile, columns right to left ----
+    // Linv[i][j] = -(sum_{k=j+1..i} Linv[i][k] L[k][j]) / L[j][j]; 4 threads per row, shuffle-combined.
+    const int row = tid >> 2, part = tid & 3;
+    for (int j = 127; j >= 0; j--) {
+        __syncthreads();
+        if (tid < 128) col[tid] = S[tid * LLD + j];   // old column j of L (rows >= j meaningful)
+        __syncthreads();
+        const double dinv = 1.0 / col[j];
+        double s = 0.0;
+        if (row > j) {
+            for (int k = j + 1 + part; k <= row; k += 4) s = fma(S[row * LLD + k], col[k], s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (part == 0) {
+            if (row > j) S[row * LLD + j] = -s * dinv;
+            else if (row == j) S[row * LLD + j] = dinv;
+        }
+    }
+    __syncthreads();
+    double* Lig = Linv + base;
+    double* Ltg = Linvt + base;
+    for (int e = tid; e < 128 * 128; e += LEAF_THREADS) {
+        int i = e >> 7, k = e & 127;
+        Lig[(size_t)i * ld + k] = S[i * LLD + k];
+        Ltg[(size_t)i * ld + k] = S[k * LLD + i];
+    }
+}
+
+static cudaError_t launch_leaf(double* Awork, double* L, double* Linv, double* Linvt, int ld, long long bs, int tile,
+                               int32_t* info, int batch, cudaStream_t stream) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_leaf_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    k_leaf_chol_inv<<<batch, LEAF_THREADS, LEAF_SMEM_BYTES, stream>>>(Awork, L, Linv, Linvt, ld, bs, tile, info);
+    return cudaGetLastError();
+}
+
+#define HDBO_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return _e; } while (0)
+
+static cudaError_t rec(double* Aw, double* L, double* Li, double* Lt, int ld, long long bs, int a, int b, int32_t* info,
+                       int batch, cudaStream_t stream) {
+    if (b - a == 1) return launch_leaf(Aw, L, Li, Lt, ld, bs, a, info, batch, stream);
+    const int h = a + (b - a + 1) / 2;
+    HDBO_TRY(rec(Aw, L, Li, Lt, ld, bs, a, h, info, batch, stream));
+    auto at = [&](double* base, int r, int c) { return base + (size_t)r * 128 * ld + (size_t)c * 128; };
+    GemmParams g{};
+    g.lda = g.ldb = g.ldc = g.ldct = ld;
+    g.bsA = g.bsB = g.bsC = g.bsCt = bs;
+    // L21 = A21 * Linv11^T
+    g.A = at(Aw, h, a); g.B = at(Li, a, a); g.C = at(L, h, a); g.Ct = nullptr;
+    g.mtiles = b - h; g.ntiles = h - a; g.kblocks = (h - a) * KB_PER_TILE; g.krange = KR_LE_N; g.lower_only = 0;
+    g.alpha = 1.0; g.beta = 0.0;
+    HDBO_TRY(launch_gemm_nt(g, batch, stream));
+    // A22 -= L21 L21^T (lower tiles)
+    g.A = at(L, h, a); g.B = at(L, h, a); g.C = at(Aw, h, h);
+    g.mtiles = g.ntiles = b - h; g.krange = KR_FULL; g.lower_only = 1; g.alpha = -1.0; g.beta = 1.0;
+    HDBO_TRY(launch_gemm_nt(g, batch, stream));
+    HDBO_TRY(rec(Aw, L, Li, Lt, ld, bs, h, b, info, batch, stream));
+    // T^T[j,i] = sum_{k>=j} U11[j,k] L21[i,k]   -> scratch in the (unused) upper-right block of Awork
+    g.A = at(Lt, a, a); g.B = at(L, h, a); g.C = at(Aw, a, h);
+    g.mtiles = h - a; g.ntiles = b - h; g.kblocks = (h - a) * KB_PER_TILE; g.krange = KR_GE_M; g.lower_only = 0;
+    g.alpha = 1.0; g.beta = 0.0;
+    HDBO_TRY(launch_gemm_nt(g, batch, stream));
+    // Linv21[i,j] = -sum_{k<=i} Linv22[i,k] T^T[j,k]   (+ transposed copy into Linv^T)
+    g.A = at(Li, h, h); g.B = at(Aw, a, h); g.C = at(Li, h, a); g.Ct = at(Lt, a, h);
+    g.mtiles = b - h; g.ntiles = h - a; g.kblocks = (b - h) * KB_PER_TILE; g.krange = KR_LE_M;
+    g.alpha = -1.0; g.beta = 0.0;
+    HDBO_TRY(launch_gemm_nt(g, batch, stream));
+    return cudaSuccess;
+}
+
+cudaError_t chol_inverse(double* Awork, double* L, double* Linv, double* Linvt, int ld, long long bs, int tiles,
+                         int n_true, int32_t* info, int batch, cudaStream_t stream) {
+    (void)n_true;
+    return rec(Awork, L, Linv, Linvt, ld, bs, 0, tiles, info, batch, stream);
+}
+
+}  // namespace hdbo

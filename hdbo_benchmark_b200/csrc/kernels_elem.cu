@@ -1,0 +1,241 @@
+// HBM-bound kernels of the GP hot path: input centring/scaling, triangular mat-vecs (alpha, quadratic form),
+// log-determinant, the acquisition epilogue (EI / LogEI / UCB, value and partial derivatives) and argmax.
+// All reductions are deterministic (fixed shuffle trees, fixed partial order).
+#include "kernels.cuh"
+#include "elem.cuh"
+
+namespace hdbo {
+
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+// block-wide sum (blockDim.x multiple of 32, <= 1024); result valid in all threads
+__device__ __forceinline__ double block_sum(double x, double* red /* 32 doubles */) {
+    x = warp_sum(x);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = x;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < nw; w++) s += red[w];
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Xs[i][k] = (X[i][k] - center[k]) * inv_ls[k]  (k < d), zero padding to d_pad and rows_pad; norms[i] = |Xs[i]|^2.
+// One warp per row, lanes stride the row (coalesced).  A1 "centred inputs / lengthscale" step.
+__global__ void k_scale_inputs(const double* __restrict__ X, int ldx, long long bsX, int nrows, int d,
+                               const double* __restrict__ center, const double* __restrict__ inv_ls, long long bs_ls,
+                               double* __restrict__ Xs, int d_pad, int rows_pad, long long bsXs,
+                               double* __restrict__ norms, long long bsn) {
+    const int b = blockIdx.y;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows_pad) return;
+    const double* x = X + b * bsX + (size_t)row * ldx;
+    const double* il = inv_ls + b * bs_ls;
+    double* o = Xs + b * bsXs + (size_t)row * d_pad;
+    double s = 0.0;
+    for (int k = lane; k < d_pad; k += 32) {
+        double v = 0.0;
+        if (row < nrows && k < d) v = (x[k] - center[k]) * il[k];
+        o[k] = v;
+        s = fma(v, v, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) norms[b * bsn + row] = s;
+}
+
+cudaError_t launch_scale_inputs(const double* X, int ldx, long long bsX, int nrows, int d, const double* center,
+                                const double* inv_ls, long long bs_ls, double* Xs, int d_pad, int rows_pad,
+                                long long bsXs, double* norms, long long bsn, int batch, cudaStream_t stream) {
+    dim3 grid((rows_pad + 7) / 8, batch);
+    k_scale_inputs<<<grid, 256, 0, stream>>>(X, ldx, bsX, nrows, d, center, inv_ls, bs_ls, Xs, d_pad, rows_pad, bsXs,
+                                             norms, bsn);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// out[i] = sum_{j in range(i)} M[i][j] v[j]; lower: j <= i, upper: j >= i.  One warp per row.
+// rhs mode: v[j] = y[j] - mean (j < n) when y != nullptr, else v = vin.
+__global__ void k_tri_matvec(const double* __restrict__ M, int ld, long long bsM, int n_pad, int upper,
+                             const double* __restrict__ vin, long long bsv, const double* __restrict__ y, int n,
+                             const double* __restrict__ hyp, double* __restrict__ out, long long bso) {
+    const int b = blockIdx.y;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n_pad) return;
+    const double* m = M + b * bsM + (size_t)row * ld;
+    const double mean = y ? hyp[b * 4 + 2] : 0.0;
+    const int j0 = upper ? row : 0, j1 = upper ? n_pad : row + 1;
+    double s = 0.0;
+    for (int j = j0 + lane; j < j1; j += 32) {
+        double v = y ? ((j < n) ? y[j] - mean : 0.0) : vin[b * bsv + j];
+        s = fma(m[j], v, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) out[b * bso + row] = s;
+}
+
+cudaError_t launch_tri_matvec(const double* M, int ld, long long bsM, int n_pad, int upper, const double* vin,
+                              long long bsv, const double* y, int n, const double* hyp, double* out, long long bso,
+                              int batch, cudaStream_t stream) {
+    dim3 grid((n_pad + 7) / 8, batch);
+    k_tri_matvec<<<grid, 256, 0, stream>>>(M, ld, bsM, n_pad, upper, vin, bsv, y, n, hyp, out, bso);
+    return cudaGetLastError();
+}
+
+// scal[b][0] = logdet = 2 sum log L_ii ; scal[b][1] = quad = w.w ; scal[b][2] = data term of n*mll:
+// -1/2 quad - 1/2 logdet - n/2 log 2pi ; scal[b][3] = sum alpha.   One block per GP.
+__global__ void k_fit_scalars(const double* __restrict__ L, int ld, long long bsL, const double* __restrict__ w,
+                              const double* __restrict__ alpha, long long bsv, int n, int n_pad, double* __restrict__ scal) {
+    __shared__ double red[32];
+    const int b = blockIdx.x;
+    double sl = 0.0, sq = 0.0, sa = 0.0;
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+        sl += log(L[b * bsL + (size_t)i * ld + i]);
+        double wi = w[b * bsv + i];
+        sq = fma(wi, wi, sq);
+        sa += alpha[b * bsv + i];
+    }
+    sl = block_sum(sl, red);
+    sq = block_sum(sq, red);
+    sa = block_sum(sa, red);
+    if (threadIdx.x == 0) {
+        scal[b * 8 + 0] = 2.0 * sl;
+        scal[b * 8 + 1] = sq;
+        scal[b * 8 + 2] = -0.5 * sq - sl - 0.5 * n * LOG_2PI;
+        scal[b * 8 + 3] = sa;
+    }
+}
+
+cudaError_t launch_fit_scalars(const double* L, int ld, long long bsL, const double* w, const double* alpha,
+                               long long bsv, int n, int n_pad, double* scal, int batch, cudaStream_t stream) {
+    k_fit_scalars<<<batch, 512, 0, stream>>>(L, ld, bsL, w, alpha, bsv, n, n_pad, scal);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Per candidate: mean = m0 + sum_t meanpart[t][i]; var = outputscale - sum_t varpart[t][i] (+ noise);
+// acquisition value (A5) and, if requested, d acq / d mean and d acq / d var.
+__global__ void k_finalize_acq(const double* __restrict__ meanpart, const double* __restrict__ varpart, long long bsp,
+                               int ntiles, int rows_pad, int m, const double* __restrict__ hyp, int observation_noise,
+                               int acq_kind, double acq_param, double* __restrict__ mean_out,
+                               double* __restrict__ var_out, double* __restrict__ acq_out, long long bso) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    double sm = 0.0, sv = 0.0;
+    for (int t = 0; t < ntiles; t++) {
+        sm += meanpart[b * bsp + (size_t)t * rows_pad + i];
+        sv += varpart[b * bsp + (size_t)t * rows_pad + i];
+    }
+    const double os = hyp[b * 4 + 0], noise = hyp[b * 4 + 1], m0 = hyp[b * 4 + 2];
+    const double mean = m0 + sm;
+    double var = os - sv;
+    if (observation_noise) var += noise;
+    if (mean_out) mean_out[b * bso + i] = mean;
+    if (var_out) var_out[b * bso + i] = var;
+    if (acq_out) {
+        double a, dm, dv;
+        acq_eval(acq_kind, acq_param, mean, var, a, dm, dv);
+        acq_out[b * bso + i] = a;
+    }
+}
+
+cudaError_t launch_finalize_acq(const double* meanpart, const double* varpart, long long bsp, int ntiles, int rows_pad,
+                                int m, const double* hyp, int observation_noise, int acq_kind, double acq_param,
+                                double* mean_out, double* var_out, double* acq_out, long long bso, int batch,
+                                cudaStream_t stream) {
+    dim3 grid((m + 255) / 256, batch);
+    k_finalize_acq<<<grid, 256, 0, stream>>>(meanpart, varpart, bsp, ntiles, rows_pad, m, hyp, observation_noise,
+                                            acq_kind, acq_param, mean_out, var_out, acq_out, bso);
+    return cudaGetLastError();
+}
+
+// acquisition from given mean / var arrays: value + partials (used by the autograd path and tested on its own)
+__global__ void k_acq_elem(const double* __restrict__ mean, const double* __restrict__ var, long long m, int acq_kind,
+                           double acq_param, double* __restrict__ acq, double* __restrict__ dmean, double* __restrict__ dvar) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    double a, dm, dv;
+    acq_eval(acq_kind, acq_param, mean[i], var[i], a, dm, dv);
+    if (acq) acq[i] = a;
+    if (dmean) dmean[i] = dm;
+    if (dvar) dvar[i] = dv;
+}
+
+cudaError_t launch_acq_elem(const double* mean, const double* var, long long m, int acq_kind, double acq_param, double* acq,
+                            double* dmean, double* dvar, cudaStream_t stream) {
+    if (m == 0) return cudaSuccess;
+    k_acq_elem<<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(mean, var, m, acq_kind, acq_param, acq, dmean, dvar);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// argmax with first-index tie-break; NaNs are ignored.  Two phases in one launch (last block reduces the partials).
+__global__ void k_argmax(const double* __restrict__ v, long long m, double* __restrict__ pval, long long* __restrict__ pidx,
+                         unsigned int* __restrict__ counter, double* __restrict__ out_val, long long* __restrict__ out_idx) {
+    __shared__ double sv[32];
+    __shared__ long long si[32];
+    __shared__ bool last;
+    double best = -INFINITY; long long bi = -1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+        double x = v[i];
+        if (x > best || (bi < 0 && x == x)) { best = x; bi = i; }
+    }
+    auto combine = [](double& a, long long& ai, double b, long long bidx) {
+        if (bidx >= 0 && (ai < 0 || b > a || (b == a && bidx < ai))) { a = b; ai = bidx; }
+    };
+    auto block_reduce = [&](double& a, long long& ai) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ob = __shfl_xor_sync(0xffffffffu, a, o);
+            long long oi = __shfl_xor_sync(0xffffffffu, ai, o);
+            combine(a, ai, ob, oi);
+        }
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        __syncthreads();
+        if (lane == 0) { sv[warp] = a; si[warp] = ai; }
+        __syncthreads();
+        if (warp == 0) {
+            a = (lane < (blockDim.x >> 5)) ? sv[lane] : -INFINITY;
+            ai = (lane < (blockDim.x >> 5)) ? si[lane] : -1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                double ob = __shfl_xor_sync(0xffffffffu, a, o);
+                long long oi = __shfl_xor_sync(0xffffffffu, ai, o);
+                combine(a, ai, ob, oi);
+            }
+        }
+    };
+    block_reduce(best, bi);
+    if (threadIdx.x == 0) {
+        pval[blockIdx.x] = best; pidx[blockIdx.x] = bi;
+        __threadfence();
+        unsigned int t = atomicAdd(counter, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    best = -INFINITY; bi = -1;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) combine(best, bi, pval[i], pidx[i]);
+    block_reduce(best, bi);
+    if (threadIdx.x == 0) { *out_val = best; *out_idx = bi; *counter = 0u; }
+}
+
+cudaError_t launch_argmax(const double* v, long long m, void* work, double* out_val, long long* out_idx, cudaStream_t stream) {
+    // work: [0,8) counter (must be zero on entry; reset on exit), then 296 doubles, then 296 int64
+    const int nblocks = 296;
+    unsigned int* counter = reinterpret_cast<unsigned int*>(work);
+    double* pval = reinterpret_cast<double*>(reinterpret_cast<char*>(work) + 8);
+    long long* pidx = reinterpret_cast<long long*>(pval + nblocks);
+    k_argmax<<<nblocks, 256, 0, stream>>>(v, m, pval, pidx, counter, out_val, out_idx);
+    return cudaGetLastError();
+}
+
+}  // namespace hdbo

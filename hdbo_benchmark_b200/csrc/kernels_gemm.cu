@@ -1,0 +1,236 @@
+// GEMM-shaped kernels of the GP hot path, all built on gemm_nt_mainloop (DMMA.8x8x4, cp.async ring).
+//   k_gemm_nt    generic C = alpha*A*B^T + beta*C with triangular k-ranges   (potrf / trtri / K^-1 / beta phases)
+//   k_cross      K*(Z, X): scaled-candidate x scaled-train GEMM + distance->kernel epilogue + partial K* alpha  (A1, A4)
+//   k_sym_build  K(X, X) + noise I (lower tiles) and the squared-distance matrix                                 (A1, A2)
+//   k_var        V = K* L^-T with the triangular k-range, row sum-of-squares epilogue                            (A4)
+#include "gemm_core.cuh"
+#include "kernels.cuh"
+
+namespace hdbo {
+
+__device__ __forceinline__ void krange_blocks(int mode, int bm, int bn, int kblocks, int& kb0, int& kb1) {
+    kb0 = 0; kb1 = kblocks;
+    switch (mode) {
+        case KR_LE_N: kb1 = min(kblocks, (bn + 1) * KB_PER_TILE); break;
+        case KR_LE_M: kb1 = min(kblocks, (bm + 1) * KB_PER_TILE); break;
+        case KR_GE_N: kb0 = bn * KB_PER_TILE; break;
+        case KR_GE_M: kb0 = bm * KB_PER_TILE; break;
+        case KR_GE_MN: kb0 = max(bm, bn) * KB_PER_TILE; break;
+        default: break;
+    }
+}
+
+__device__ __forceinline__ void lower_tile_decode(int t, int& bm, int& bn) {
+    // t enumerates (bm, bn) with bm >= bn row by row: t = bm(bm+1)/2 + bn
+    int r = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((r + 1) * (r + 2) / 2 <= t) r++;
+    while (r * (r + 1) / 2 > t) r--;
+    bm = r; bn = t - r * (r + 1) / 2;
+}
+
+// --------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1) k_gemm_nt(GemmParams p) {
+    extern __shared__ __align__(16) double smem[];
+    int bm, bn;
+    if (p.lower_only) lower_tile_decode(blockIdx.x, bm, bn);
+    else { bm = blockIdx.x; bn = blockIdx.y; }
+    const int b = blockIdx.z;
+    int kb0, kb1;
+    krange_blocks(p.krange, bm, bn, p.kblocks, kb0, kb1);
+    Frag acc; acc.zero();
+    gemm_nt_mainloop(p.A + b * p.bsA + (size_t)bm * BM * p.lda, p.lda, p.B + b * p.bsB + (size_t)bn * BN * p.ldb, p.ldb,
+                     kb0, kb1, smem, acc);
+    double* C = p.C + b * p.bsC;
+    double* Ct = p.Ct ? p.Ct + b * p.bsCt : nullptr;
+#pragma unroll
+    for (int mt = 0; mt < 8; mt++) {
+        const int i = bm * BM + frag_row(mt);
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            const int j = bn * BN + frag_col(nt);
+            double2* dst = reinterpret_cast<double2*>(C + (size_t)i * p.ldc + j);
+            double2 o;
+            o.x = p.alpha * acc.v[mt][nt][0];
+            o.y = p.alpha * acc.v[mt][nt][1];
+            if (p.beta != 0.0) { double2 c = *dst; o.x += p.beta * c.x; o.y += p.beta * c.y; }
+            *dst = o;
+            if (Ct) { Ct[(size_t)j * p.ldct + i] = o.x; Ct[(size_t)(j + 1) * p.ldct + i] = o.y; }
+        }
+    }
+}
+
+cudaError_t launch_gemm_nt(const GemmParams& p, int batch, cudaStream_t stream) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid;
+    if (p.lower_only) grid = dim3(p.mtiles * (p.mtiles + 1) / 2, 1, batch);
+    else grid = dim3(p.mtiles, p.ntiles, batch);
+    if (grid.x == 0 || grid.y == 0) return cudaSuccess;
+    k_gemm_nt<<<grid, NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// K*(Z, X) tile: r2 = |z|^2 + |x|^2 - 2 z.x (clamped at 0), k(r2) * outputscale, masked beyond n; plus the partial
+// dot with alpha over this tile's 128 columns (posterior mean), written to meanpart[bn][row].
+__global__ void __launch_bounds__(NTHREADS, 1) k_cross(CrossParams p) {
+    extern __shared__ __align__(16) double smem[];
+    const int bm = blockIdx.x, bn = blockIdx.y, b = blockIdx.z;
+    Frag acc; acc.zero();
+    gemm_nt_mainloop(p.Zs + b * p.bsZ + (size_t)bm * BM * p.ldz, p.ldz, p.Xs + b * p.bsX + (size_t)bn * BN * p.ldx, p.ldx,
+                     0, p.kblocks, smem, acc);
+    const double os = p.hyp[b * 4 + 0];
+    const double* zn = p.zn + b * p.bszn + bm * BM;
+    const double* xn = p.xn + b * p.bsxn + bn * BN;
+    const double* al = p.alpha + b * p.bsalpha + bn * BN;
+    double* Kst = p.Kstar + b * p.bsK;
+    double* DK = p.DK ? p.DK + b * p.bsK : nullptr;
+    double xnv[4][2], alv[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) { int c = frag_col(nt) + e; xnv[nt][e] = xn[c]; alv[nt][e] = al[c]; }
+    double rowval[8];
+#pragma unroll
+    for (int mt = 0; mt < 8; mt++) {
+        const int r = frag_row(mt);
+        const double znr = zn[r];
+        double s = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            const int c = frag_col(nt);
+            double kv[2], dv[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                double r2 = fmax((znr + xnv[nt][e]) - 2.0 * acc.v[mt][nt][e], 0.0);
+                double k, dk;
+                kernel_eval(p.kind, r2, k, dk);
+                bool valid = (bn * BN + c + e) < p.n;
+                kv[e] = valid ? os * k : 0.0;
+                dv[e] = valid ? os * dk : 0.0;
+                s += kv[e] * alv[nt][e];
+            }
+            size_t off = (size_t)(bm * BM + r) * p.ldk + bn * BN + c;
+            *reinterpret_cast<double2*>(Kst + off) = make_double2(kv[0], kv[1]);
+            if (DK) *reinterpret_cast<double2*>(DK + off) = make_double2(dv[0], dv[1]);
+        }
+        rowval[mt] = s;
+    }
+    double r = tile_row_reduce(rowval, smem);
+    if (threadIdx.x < 128) p.meanpart[b * p.bsmp + (size_t)bn * (p.mtiles * BM) + bm * BM + threadIdx.x] = r;
+}
+
+cudaError_t launch_cross(const CrossParams& p, int batch, cudaStream_t stream) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_cross, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid(p.mtiles, p.ntiles, batch);
+    k_cross<<<grid, NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// Train covariance, lower tiles only: Khat = outputscale*k(r2) + (noise + jitter) on the diagonal; rows/cols >= n are
+// the identity so that the padded matrix stays SPD and its factor / inverse are block-diagonal with I.  R2 gets the
+// full symmetric squared-distance matrix (diagonal exactly 0, padding 0) when requested (needed by the MLL gradient).
+__global__ void __launch_bounds__(NTHREADS, 1) k_sym_build(SymBuildParams p) {
+    extern __shared__ __align__(16) double smem[];
+    int bm, bn;
+    lower_tile_decode(blockIdx.x, bm, bn);
+    const int b = blockIdx.z;
+    Frag acc; acc.zero();
+    const double* Xs = p.Xs + b * p.bsX;
+    gemm_nt_mainloop(Xs + (size_t)bm * BM * p.ldx, p.ldx, Xs + (size_t)bn * BN * p.ldx, p.ldx, 0, p.kblocks, smem, acc);
+    const double os = p.hyp[b * 4 + 0], noise = p.hyp[b * 4 + 1], jitter = p.hyp[b * 4 + 3];
+    const double* xn = p.xn + b * p.bsxn;
+    double* Kh = p.Khat + b * p.bsK;
+    double* R2 = p.R2 ? p.R2 + b * p.bsK : nullptr;
+#pragma unroll
+    for (int mt = 0; mt < 8; mt++) {
+        const int i = bm * BM + frag_row(mt);
+        const double xi = xn[i];
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            const int j0 = bn * BN + frag_col(nt);
+            double kv[2], rv[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int j = j0 + e;
+                double r2 = fmax((xi + xn[j]) - 2.0 * acc.v[mt][nt][e], 0.0);
+                if (i == j) r2 = 0.0;
+                double k, dk;
+                kernel_eval(p.kind, r2, k, dk);
+                const bool valid = (i < p.n) && (j < p.n);
+                kv[e] = valid ? os * k + ((i == j) ? (noise + jitter) : 0.0) : ((i == j) ? 1.0 : 0.0);
+                rv[e] = valid ? r2 : 0.0;
+            }
+            *reinterpret_cast<double2*>(Kh + (size_t)i * p.ldk + j0) = make_double2(kv[0], kv[1]);
+            if (R2) {
+                *reinterpret_cast<double2*>(R2 + (size_t)i * p.ldk + j0) = make_double2(rv[0], rv[1]);
+                if (bm != bn) { R2[(size_t)j0 * p.ldk + i] = rv[0]; R2[(size_t)(j0 + 1) * p.ldk + i] = rv[1]; }
+            }
+        }
+    }
+}
+
+cudaError_t launch_sym_build(const SymBuildParams& p, int batch, cudaStream_t stream) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_sym_build, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid(p.tiles * (p.tiles + 1) / 2, 1, batch);
+    k_sym_build<<<grid, NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// V = K* L^-T : V[c,i] = sum_{j<=i} K*[c,j] Linv[i,j].  Column tile bn only needs k-tiles <= bn (n^2 flops per candidate,
+// not 2n^2).  Heavy column tiles are scheduled first (blockIdx.y = 0 -> last column tile).  Epilogue: per-row sum of
+// squares over this tile's 128 columns -> varpart[bn][row]; V itself is stored only for the gradient path.
+__global__ void __launch_bounds__(NTHREADS, 1) k_var(VarParams p) {
+    extern __shared__ __align__(16) double smem[];
+    const int bm = blockIdx.x, bn = p.ntiles - 1 - blockIdx.y, b = blockIdx.z;
+    Frag acc; acc.zero();
+    gemm_nt_mainloop(p.Kstar + b * p.bsK + (size_t)bm * BM * p.ldk, p.ldk, p.Linv + b * p.bsL + (size_t)bn * BN * p.ldl,
+                     p.ldl, 0, (bn + 1) * KB_PER_TILE, smem, acc);
+    double rowval[8];
+    double* V = p.V ? p.V + b * p.bsV : nullptr;
+#pragma unroll
+    for (int mt = 0; mt < 8; mt++) {
+        double s = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            s = fma(acc.v[mt][nt][0], acc.v[mt][nt][0], s);
+            s = fma(acc.v[mt][nt][1], acc.v[mt][nt][1], s);
+            if (V)
+                *reinterpret_cast<double2*>(V + (size_t)(bm * BM + frag_row(mt)) * p.ldv + bn * BN + frag_col(nt)) =
+                    make_double2(acc.v[mt][nt][0], acc.v[mt][nt][1]);
+        }
+        rowval[mt] = s;
+    }
+    double r = tile_row_reduce(rowval, smem);
+    if (threadIdx.x < 128) p.varpart[b * p.bsvp + (size_t)bn * (p.mtiles * BM) + bm * BM + threadIdx.x] = r;
+}
+
+cudaError_t launch_var(const VarParams& p, int batch, cudaStream_t stream) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_var, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid(p.mtiles, p.ntiles, batch);
+    k_var<<<grid, NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace hdbo

@@ -1,0 +1,164 @@
+"""Device-resident exact-GP state and the calls into libhdbo_b200.so.
+
+`DeviceGP` owns (through torch's caching allocator) every buffer the C ABI needs for one GP or a
+batch of GPs that share training data but differ in hyper-parameters (fully Bayesian / SAAS
+samples).  It is the thin layer between the BoTorch-shaped classes in `models.py` /
+`acquisition.py` and the C ABI; it contains no arithmetic of its own.
+
+Data layout in HBM (all FP64, row-major, padded: n_pad = roundup(n,128), d_pad = roundup(d,16)):
+    Xs   [B][n_pad][d_pad]   centred inputs / lengthscale          xn    [B][n_pad]  row norms^2
+    Awork[B][n_pad][n_pad]   K + noise I (consumed)                 R2    [B][n_pad][n_pad] (MLL gradient only)
+    L, Linv (lower), Linvt (upper) [B][n_pad][n_pad]                w, alpha [B][n_pad]
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import HdboGp, check, ptr
+
+DEFAULT_CHUNK_ROWS = 148 * 128  # one 128-row tile per SM per column tile
+
+
+def _rup(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class NotPSDError(RuntimeError):
+    """Raised when K + noise I is not positive definite even after the jitter schedule
+    (linear_operator.utils.errors.NotPSDError upstream)."""
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class DeviceGP:
+    def __init__(self, X: torch.Tensor, y: torch.Tensor, kind: int, batch: int = 1, keep_r2: bool = False):
+        if not X.is_cuda:
+            raise _lib.HdboError("DeviceGP needs CUDA tensors: the hot path has no CPU implementation")
+        self.lib = _lib.load()
+        self.device = X.device
+        self.X = X.detach().to(torch.float64).contiguous()
+        self.y = y.detach().to(torch.float64).reshape(-1).contiguous()
+        self.n, self.d = self.X.shape
+        assert self.y.numel() == self.n
+        self.kind = int(kind)
+        self.batch = int(batch)
+        self.n_pad = _rup(self.n, 128)
+        self.d_pad = _rup(self.d, 16)
+        self.keep_r2 = keep_r2
+        B, npad, dpad = self.batch, self.n_pad, self.d_pad
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self.center = self.X.mean(dim=0).contiguous()
+        self.inv_ls = torch.ones(B, self.d, **f64)
+        self.hyp = torch.zeros(B, 4, **f64)
+        self.Xs = torch.empty(B, npad, dpad, **f64)
+        self.xn = torch.empty(B, npad, **f64)
+        self.R2 = torch.empty(B, npad, npad, **f64) if keep_r2 else None
+        self.Awork = torch.empty(B, npad, npad, **f64)
+        self.L = torch.empty(B, npad, npad, **f64)
+        # the strictly-upper tiles of Linv / strictly-lower tiles of Linvt are never written nor read
+        self.Linv = torch.zeros(B, npad, npad, **f64)
+        self.Linvt = torch.zeros(B, npad, npad, **f64)
+        self.w = torch.empty(B, npad, **f64)
+        self.alpha = torch.empty(B, npad, **f64)
+        self.scal = torch.zeros(B, 8, **f64)
+        self.info = torch.zeros(B, dtype=torch.int32, device=self.device)
+        self._ws: Optional[torch.Tensor] = None
+        self._argmax_work = torch.zeros(8192, dtype=torch.uint8, device=self.device)
+        self.fitted = False
+        self.jitter_used = 0.0
+        self.desc = HdboGp(
+            n=self.n, d=self.d, n_pad=npad, d_pad=dpad, kind=self.kind, batch=B,
+            X=ptr(self.X), ldx=self.X.stride(0), y=ptr(self.y), center=ptr(self.center), inv_ls=ptr(self.inv_ls),
+            hyp=ptr(self.hyp), Xs=ptr(self.Xs), xn=ptr(self.xn), R2=ptr(self.R2), Awork=ptr(self.Awork), L=ptr(self.L),
+            Linv=ptr(self.Linv), Linvt=ptr(self.Linvt), w=ptr(self.w), alpha=ptr(self.alpha), scal=ptr(self.scal),
+            info=ptr(self.info),
+        )
+
+    # ---- hyper-parameters (device tensors; no host sync) ----
+    def set_hyper(self, lengthscale, outputscale, noise, mean, jitter: float = 0.0) -> None:
+        """lengthscale [d] or [B,d]; outputscale / noise / mean scalars or [B] (tensors or floats)."""
+        f64 = dict(dtype=torch.float64, device=self.device)
+        ls = torch.as_tensor(lengthscale, **f64).detach().reshape(-1, self.d)
+        self.inv_ls.copy_((1.0 / ls).expand(self.batch, self.d))
+        for col, v in enumerate((outputscale, noise, mean, jitter)):
+            self.hyp[:, col] = torch.as_tensor(v, **f64).detach().reshape(-1)
+        self.fitted = False
+
+    # ---- A1 + A2: kernel build, Cholesky, inverse, alpha, logdet ----
+    def fit_once(self, need_r2: Optional[bool] = None) -> None:
+        need = self.keep_r2 if need_r2 is None else need_r2
+        check(self.lib.hdbo_gp_fit(C.byref(self.desc), int(bool(need)), _stream()), "hdbo_gp_fit")
+
+    def fit(self, need_r2: Optional[bool] = None, max_tries: int = 3) -> float:
+        """Factorise with the psd_safe_cholesky jitter schedule (1e-8 * 10**i, i < max_tries).  One host sync."""
+        self.fit_once(need_r2)
+        jitter = 0.0
+        if int(self.info.max().item()) != 0:
+            for i in range(max_tries):
+                jitter = 1e-8 * (10 ** i)
+                self.hyp[:, 3] = jitter
+                self.fit_once(need_r2)
+                if int(self.info.max().item()) == 0:
+                    break
+            else:
+                self.hyp[:, 3] = 0.0
+                raise NotPSDError(f"Matrix not positive definite after adding jitter up to {jitter:.1e}")
+            self.hyp[:, 3] = 0.0
+        self.fitted = True
+        self.jitter_used = jitter
+        return jitter
+
+    # ---- workspace ----
+    def workspace(self, rows: int, keep: bool = False) -> torch.Tensor:
+        need = self.lib.hdbo_posterior_workspace_bytes(C.byref(self.desc), rows, int(keep))
+        if need == 0:
+            raise _lib.HdboError("hdbo_posterior_workspace_bytes rejected its arguments")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # ---- A4 + A5: posterior mean / variance / acquisition over a candidate pool (no grad) ----
+    def posterior_acq(self, Z: torch.Tensor, acq_kind: int = _lib.ACQ_NONE, acq_param: float = 0.0,
+                      observation_noise: bool = False, want_mean: bool = True, want_var: bool = True,
+                      chunk_rows: int = DEFAULT_CHUNK_ROWS, out: Optional[dict] = None):
+        assert self.fitted, "call fit() first"
+        Z = Z.detach()
+        if Z.dtype != torch.float64 or Z.stride(-1) != 1:
+            Z = Z.to(torch.float64).contiguous()
+        m = Z.shape[0]
+        rows = min(_rup(max(m, 1), 128), _rup(chunk_rows, 128))
+        ws = self.workspace(rows)
+        f64 = dict(dtype=torch.float64, device=self.device)
+        out = out or {}
+        mean = out.get("mean") if "mean" in out else (torch.empty(self.batch, m, **f64) if want_mean else None)
+        var = out.get("var") if "var" in out else (torch.empty(self.batch, m, **f64) if want_var else None)
+        acq = out.get("acq") if "acq" in out else (torch.empty(self.batch, m, **f64) if acq_kind >= 0 else None)
+        check(self.lib.hdbo_posterior_acq(C.byref(self.desc), ptr(Z), Z.stride(0), m, int(observation_noise), acq_kind,
+                                          float(acq_param), ptr(mean), ptr(var), ptr(acq), m, ptr(ws), ws.numel(),
+                                          _stream()), "hdbo_posterior_acq")
+        return mean, var, acq
+
+    def argmax(self, v: torch.Tensor):
+        v = v.reshape(-1)
+        out_val = torch.empty(1, dtype=torch.float64, device=self.device)
+        out_idx = torch.empty(1, dtype=torch.int64, device=self.device)
+        check(self.lib.hdbo_argmax(ptr(v), v.numel(), ptr(self._argmax_work), ptr(out_val), ptr(out_idx), _stream()),
+              "hdbo_argmax")
+        return out_val, out_idx
+
+    # ---- convenience accessors (unpadded views) ----
+    @property
+    def logdet(self) -> torch.Tensor:
+        return self.scal[:, 0]
+
+    @property
+    def mll_data_term(self) -> torch.Tensor:
+        """n * mll without priors: -1/2 r^T Khat^-1 r - 1/2 logdet - n/2 log 2pi."""
+        return self.scal[:, 2]

@@ -1,0 +1,135 @@
+/* libhdbo_b200.so -- C ABI of the B200-native GP-surrogate + acquisition hot path.
+ *
+ * This is the drop-in boundary.  The reference (MachineLearningLifeScience/hdbo_benchmark) has no FFI of its own:
+ * its hot path is reached through the BoTorch / GPyTorch Python API (un-vendored), at the call sites
+ *   /root/reference/src/hdbo_benchmark/utils/experiments/load_solvers.py:118-194   (solvers -> SingleTaskGP,
+ *                                                  fit_gpytorch_mll, (Log)EI, optimize_acqf, SAAS)
+ *   /root/reference/src/hdbo_benchmark/utils/experiments/load_solvers.py:124-145   (gpytorch kernel constructor)
+ *   /root/reference/src/hdbo_benchmark/utils/experiments/training_gps.py:49-145    (ExactMarginalLogLikelihood,
+ *                                                  model(train_x), eval-mode model(test_x))
+ *   /root/reference/src/hdbo_benchmark/utils/experiments/training_gps.py:11-29     (pairwise cdist de-duplication)
+ * Each entry point below names the upstream operation it replaces.  The Python host layer
+ * (hdbo_benchmark_b200/) binds these with ctypes and re-exposes the BoTorch surface; see INTEGRATION.md.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to FP64 (or as typed), owned by the caller; the library never allocates,
+ *    frees or retains memory and has no global state besides one-time kernel attributes;
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*), no implicit synchronisation;
+ *  - return value: 0 ok; > 0 a cudaError_t from a launch; < 0 the (negated, 1-based) index of an invalid argument;
+ *  - matrices are row-major.  Internal ("state") matrices are padded: n_pad = roundup(n,128), d_pad = roundup(d,16),
+ *    leading dimension = padded width; the padding of Khat is the identity, everything else zero;
+ *  - `batch` independent GPs (SAAS hyper-parameter samples) are laid out with explicit element strides.
+ */
+#ifndef HDBO_B200_H
+#define HDBO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HDBO_KERNEL_MATERN52 0
+#define HDBO_KERNEL_RBF 1
+
+#define HDBO_ACQ_EI 0
+#define HDBO_ACQ_LOGEI 1
+#define HDBO_ACQ_UCB 2
+#define HDBO_ACQ_MEAN 3
+#define HDBO_ACQ_PI 4
+#define HDBO_ACQ_NONE (-1)
+
+/* One (batch of) exact GP(s).  hyp[b] = {outputscale, noise, constant mean, jitter}. */
+typedef struct hdbo_gp {
+    int32_t n, d, n_pad, d_pad, kind, batch;
+    const double* X;        /* [n][d] raw training inputs (shared by the batch), leading dimension ldx          */
+    int64_t ldx;
+    const double* y;        /* [n] targets (shared by the batch)                                                */
+    const double* center;   /* [d] centring vector (training mean)                                              */
+    const double* inv_ls;   /* [batch][d] reciprocal ARD lengthscales                                           */
+    const double* hyp;      /* [batch][4]                                                                       */
+    double* Xs;             /* [batch][n_pad][d_pad] centred, scaled inputs                                     */
+    double* xn;             /* [batch][n_pad]        squared norms of the rows of Xs                            */
+    double* R2;             /* [batch][n_pad][n_pad] scaled squared distances (may be NULL when no MLL gradient)*/
+    double* Awork;          /* [batch][n_pad][n_pad] K + noise I, destroyed by the factorisation                */
+    double* L;              /* [batch][n_pad][n_pad] Cholesky factor (lower)                                    */
+    double* Linv;           /* [batch][n_pad][n_pad] L^-1 (lower)                                               */
+    double* Linvt;          /* [batch][n_pad][n_pad] L^-T (upper)                                               */
+    double* w;              /* [batch][n_pad]        L^-1 (y - m)                                               */
+    double* alpha;          /* [batch][n_pad]        Khat^-1 (y - m)                                            */
+    double* scal;           /* [batch][8]: logdet, quad, n*mll data term, sum(alpha), ...                       */
+    int32_t* info;          /* [batch] 0 or 1-based index of the first non-positive pivot                       */
+} hdbo_gp;
+
+/* library / build identification */
+int hdbo_version(void);
+
+/* Replaces: kernel build (gpytorch MaternKernel/RBFKernel/ScaleKernel forward on train x train),
+ * GaussianLikelihood noise add, linear_operator psd_safe_cholesky (one attempt; the host applies the jitter
+ * schedule by re-calling with hyp[3] = jitter), cholesky_solve for alpha, and the log-determinant.
+ * need_r2 != 0 also keeps the squared-distance matrix for hdbo_mll_grad. */
+int hdbo_gp_fit(const hdbo_gp* gp, int need_r2, void* stream);
+
+/* Replaces: autograd backward of gpytorch ExactMarginalLogLikelihood (data term; priors are added on the host).
+ * Inputs: a fitted hdbo_gp with R2.  Kinv, G: [batch][n_pad][n_pad] scratch (Kinv may alias gp->L).
+ * XsT: [batch][d_pad_t][n_pad] scratch, d_pad_t = roundup(d,128).  part: [batch][(n_pad/128)][d_pad_t + 4*128] scratch.
+ * grad: [batch][d + 3] = d(n*mll_data)/d{lengthscale[d], outputscale, noise, mean}. */
+int hdbo_mll_grad(const hdbo_gp* gp, double* Kinv, double* G, double* XsT, double* part, double* grad, void* stream);
+
+/* Workspace (bytes) for hdbo_posterior_acq with `rows` (multiple of 128) candidates resident at a time. */
+size_t hdbo_posterior_workspace_bytes(const hdbo_gp* gp, int64_t rows, int keep_grad_state);
+
+/* Replaces: model.posterior(X).mean/.variance for X of shape [m,1,d] followed by an analytic acquisition
+ * (botorch ExpectedImprovement / LogExpectedImprovement / UpperConfidenceBound forward), no-grad candidate-pool
+ * evaluation as in optimize_acqf's raw-sample screening.  Z [m][d] (ldz), shared by the batch.
+ * Outputs (each may be NULL): mean, var, acq: [batch][m] with stride bso.  Processes the pool in chunks that
+ * fit `workspace`. */
+int hdbo_posterior_acq(const hdbo_gp* gp, const double* Z, int64_t ldz, int64_t m, int observation_noise, int acq_kind,
+                       double acq_param, double* mean, double* var, double* acq, int64_t bso, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* Forward of the differentiable posterior for m <= rows candidates, keeping Kstar, dKstar_dr2 and V in the workspace
+ * (layout fixed by hdbo_posterior_workspace_bytes(keep_grad_state=1)) for hdbo_posterior_bwd.
+ * Replaces: model.posterior(X) under autograd. */
+int hdbo_posterior_fwd(const hdbo_gp* gp, const double* Z, int64_t ldz, int64_t m, int observation_noise, double* mean,
+                       double* var, int64_t bso, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Joint covariance for q-batches after hdbo_posterior_fwd: Z viewed as [m/q][q][d];
+ * Sigma [batch][m/q][q][q] = k(Zq,Zq) - V V^T (+ noise I).  Replaces: posterior.mvn.covariance_matrix for q > 1. */
+int hdbo_posterior_joint_cov(const hdbo_gp* gp, const double* Z, int64_t ldz, int64_t m, int q, int observation_noise,
+                             double* Sigma, int64_t bsS, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward: given d loss/d mean [batch][m], d loss/d var [batch][m] (gSigma NULL) or d loss/d Sigma
+ * [batch][m/q][q][q] (q > 1; the diagonal carries d/d var), returns dZ [m][d] summed over the batch.
+ * Replaces: autograd through posterior(X) (A6). */
+int hdbo_posterior_bwd(const hdbo_gp* gp, const double* Z, int64_t ldz, int64_t m, int q, const double* gmean,
+                       const double* gvar, const double* gSigma, int64_t bsg, int64_t bsS, double* dZ, int64_t lddz,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces: botorch analytic acquisition forward + autograd partials on given (mean, var). */
+int hdbo_acq_elementwise(const double* mean, const double* var, int64_t m, int acq_kind, double acq_param, double* acq,
+                         double* dacq_dmean, double* dacq_dvar, void* stream);
+
+/* Replaces: botorch qExpectedImprovement.forward (+ backward): mean [R][q], Sigma [R][q][q], base samples [S][q]
+ * (SobolQMCNormalSampler, fixed), jitter added to diag(Sigma) before its Cholesky.  q <= 8.
+ * Outputs: value [R]; gmean [R][q], gSigma [R][q][q] (may be NULL).  info [R]: q x q Cholesky failure flag. */
+int hdbo_qei(const double* mean, const double* Sigma, const double* base_samples, int64_t R, int q, int64_t S,
+             double best_f, double jitter, double* value, double* gmean, double* gSigma, int32_t* info, void* stream);
+
+/* argmax with first-index tie-break (torch.argmax semantics on a 1-d tensor).  work: >= 8192 bytes, zeroed once. */
+int hdbo_argmax(const double* v, int64_t m, void* work, double* out_val, int64_t* out_idx, void* stream);
+
+/* Generic FP64 C = alpha * A * B^T + beta * C on padded operands (rows multiples of 128, K multiple of 16);
+ * exported for tests of the DMMA mainloop and for the pairwise-distance helper. */
+int hdbo_dgemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t m_pad,
+                  int64_t n_pad, int64_t k_pad, double alpha, double beta, int krange, int lower_only, void* stream);
+
+/* Replaces: torch.cdist(x, x) in filter_close_points (training_gps.py:11-13): D [n][n] Euclidean distances.
+ * Xs/xn/work as produced internally: caller passes scratch Xs [n_pad][d_pad], xn [n_pad], D_pad [n_pad][n_pad]. */
+int hdbo_cdist(const double* X, int64_t ldx, int n, int d, double* Xs, double* xn, double* D_pad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HDBO_B200_H */
