@@ -40,15 +40,16 @@ _SIGNATURES = {
     "hdbo_version": (C.c_int, []),
     "hdbo_gp_fit": (C.c_int, [C.POINTER(HdboGp), C.c_int, _dp]),
     "hdbo_mll_grad": (C.c_int, [C.POINTER(HdboGp), _dp, _dp, _dp, _dp, _dp, _dp]),
+    "hdbo_mll_grad_part_bytes": (C.c_size_t, [C.POINTER(HdboGp)]),
     "hdbo_posterior_workspace_bytes": (C.c_size_t, [C.POINTER(HdboGp), C.c_int64, C.c_int]),
     "hdbo_posterior_acq": (C.c_int, [C.POINTER(HdboGp), _dp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_double,
                                      _dp, _dp, _dp, C.c_int64, _dp, C.c_size_t, _dp]),
     "hdbo_posterior_fwd": (C.c_int, [C.POINTER(HdboGp), _dp, C.c_int64, C.c_int64, C.c_int, _dp, _dp, C.c_int64,
                                      _dp, C.c_size_t, _dp]),
-    "hdbo_posterior_joint_cov": (C.c_int, [C.POINTER(HdboGp), _dp, C.c_int64, C.c_int64, C.c_int, C.c_int, _dp,
-                                           C.c_int64, _dp, C.c_size_t, _dp]),
-    "hdbo_posterior_bwd": (C.c_int, [C.POINTER(HdboGp), _dp, C.c_int64, C.c_int64, C.c_int, _dp, _dp, _dp, C.c_int64,
-                                     C.c_int64, _dp, C.c_int64, _dp, C.c_size_t, _dp]),
+    "hdbo_posterior_joint_cov": (C.c_int, [C.POINTER(HdboGp), C.c_int64, C.c_int, C.c_int, _dp, C.c_int64, _dp,
+                                           C.c_size_t, _dp]),
+    "hdbo_posterior_bwd": (C.c_int, [C.POINTER(HdboGp), C.c_int64, C.c_int, _dp, _dp, _dp, C.c_int64, C.c_int64, _dp,
+                                     C.c_int64, C.c_int64, _dp, C.c_size_t, _dp]),
     "hdbo_acq_elementwise": (C.c_int, [_dp, _dp, C.c_int64, C.c_int, C.c_double, _dp, _dp, _dp, _dp]),
     "hdbo_qei": (C.c_int, [_dp, _dp, _dp, C.c_int64, C.c_int, C.c_int64, C.c_double, C.c_double, _dp, _dp, _dp, _dp,
                            _dp]),

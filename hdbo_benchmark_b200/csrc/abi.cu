@@ -47,7 +47,7 @@ extern "C" int hdbo_gp_fit(const hdbo_gp* gp, int need_r2, void* stream_) {
 // ------------------------------------------------------------------------------------------------------------
 namespace {
 struct PostWs {
-    double *Zs, *zn, *Kstar, *meanpart, *varpart, *DK, *V, *T;
+    double *Zs, *zn, *Kstar, *meanpart, *varpart, *DK, *V, *T, *XsT;
     size_t bytes;
 };
 PostWs carve(const hdbo_gp* gp, int64_t rows, int keep, void* base) {
@@ -64,6 +64,7 @@ PostWs carve(const hdbo_gp* gp, int64_t rows, int keep, void* base) {
         w.DK = take(B * rows * np);
         w.V = take(B * rows * np);
         w.T = take(B * rows * np);
+        w.XsT = take(B * (size_t)rup(gp->d, 128) * np);
     }
     w.bytes = off * sizeof(double);
     return w;
@@ -105,9 +106,9 @@ extern "C" int hdbo_posterior_acq(const hdbo_gp* gp, const double* Z, int64_t ld
                                   int acq_kind, double acq_param, double* mean, double* var, double* acq, int64_t bso,
                                   void* workspace, size_t workspace_bytes, void* stream_) {
     if (int e = check_gp(gp)) return e;
-    if (!Z || ldz < gp->d) return -2;
     if (m < 0) return -4;
-    if (m == 0) return 0;
+    if (m == 0) return 0;   /* empty pool: nothing to do (Z may be NULL) */
+    if (!Z || ldz < gp->d) return -2;
     if (!workspace) return -12;
     cudaStream_t st = (cudaStream_t)stream_;
     // largest multiple of 128 rows that fits the workspace
@@ -159,5 +160,102 @@ extern "C" int hdbo_dgemm_nt(const double* A, int64_t lda, const double* B, int6
     g.mtiles = (int)(m_pad / 128); g.ntiles = (int)(n_pad / 128); g.kblocks = (int)(k_pad / 16);
     g.krange = krange; g.lower_only = lower_only; g.alpha = alpha; g.beta = beta;
     TRY_CUDA(launch_gemm_nt(g, 1, (cudaStream_t)stream_));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int hdbo_mll_grad(const hdbo_gp* gp, double* Kinv, double* G, double* XsT, double* part, double* grad,
+                             void* stream_) {
+    if (int e = check_gp(gp)) return e;
+    if (!gp->R2) return -1;
+    if (!Kinv) return -2;
+    if (!G) return -3;
+    if (!XsT) return -4;
+    if (!part) return -5;
+    if (!grad) return -6;
+    TRY_CUDA(mll_grad(gp, Kinv, G, XsT, part, grad, (cudaStream_t)stream_));
+    return 0;
+}
+
+extern "C" size_t hdbo_mll_grad_part_bytes(const hdbo_gp* gp) {
+    if (check_gp(gp)) return 0;
+    return mll_grad_part_doubles(gp) * sizeof(double);
+}
+
+extern "C" int hdbo_posterior_fwd(const hdbo_gp* gp, const double* Z, int64_t ldz, int64_t m, int observation_noise,
+                                  double* mean, double* var, int64_t bso, void* workspace, size_t workspace_bytes,
+                                  void* stream_) {
+    if (int e = check_gp(gp)) return e;
+    if (!Z || ldz < gp->d) return -2;
+    if (m <= 0) return -4;
+    const int64_t rows = rup(m, 128);
+    if (!workspace || carve(gp, rows, 1, nullptr).bytes > workspace_bytes) return -9;
+    cudaStream_t st = (cudaStream_t)stream_;
+    PostWs w = carve(gp, rows, 1, workspace);
+    const int nt = gp->n_pad / 128;
+    TRY_CUDA(posterior_chunk(gp, w, rows, Z, ldz, m, 1, st));
+    TRY_CUDA(launch_finalize_acq(w.meanpart, w.varpart, (long long)nt * rows, nt, (int)rows, (int)m, gp->hyp,
+                                 observation_noise, HDBO_ACQ_NONE, 0.0, mean, var, nullptr, bso, gp->batch, st));
+    return 0;
+}
+
+extern "C" int hdbo_posterior_joint_cov(const hdbo_gp* gp, int64_t m, int q, int observation_noise, double* Sigma,
+                                        int64_t bsS, void* workspace, size_t workspace_bytes, void* stream_) {
+    if (int e = check_gp(gp)) return e;
+    if (m <= 0) return -2;
+    if (q < 1 || q > 8 || m % q) return -3;
+    if (!Sigma) return -5;
+    const int64_t rows = rup(m, 128);
+    if (!workspace || carve(gp, rows, 1, nullptr).bytes > workspace_bytes) return -7;
+    PostWs w = carve(gp, rows, 1, workspace);
+    TRY_CUDA(launch_joint_cov(w.Zs, gp->d_pad, (long long)rows * gp->d_pad, w.V, gp->n_pad, (long long)rows * gp->n_pad,
+                              gp->hyp, (int)(m / q), q, gp->kind, observation_noise, Sigma, bsS, gp->batch,
+                              (cudaStream_t)stream_));
+    return 0;
+}
+
+extern "C" int hdbo_posterior_bwd(const hdbo_gp* gp, int64_t m, int q, const double* gmean, const double* gvar,
+                                  const double* gSigma, int64_t bsg, int64_t bsS, double* dZ, int64_t lddz, int64_t bsdz,
+                                  void* workspace, size_t workspace_bytes, void* stream_) {
+    if (int e = check_gp(gp)) return e;
+    if (m <= 0) return -2;
+    if (q < 1 || q > 8 || m % q) return -3;
+    if (gvar && gSigma) return -5;
+    if (!dZ || lddz < gp->d) return -9;
+    const int64_t rows = rup(m, 128);
+    if (!workspace || carve(gp, rows, 1, nullptr).bytes > workspace_bytes) return -12;
+    PostWs w = carve(gp, rows, 1, workspace);
+    BwdBuffers b{w.Zs, w.Kstar, w.DK, w.V, w.T, w.XsT, w.meanpart};
+    TRY_CUDA(posterior_bwd(gp, b, rows, m, q, gmean, gvar, gSigma, bsg, bsS, dZ, (int)lddz, bsdz, (cudaStream_t)stream_));
+    return 0;
+}
+
+extern "C" int hdbo_qei(const double* mean, const double* Sigma, const double* base_samples, int64_t R, int q, int64_t S,
+                        double best_f, double jitter, double* value, double* gmean, double* gSigma, int32_t* info,
+                        void* stream_) {
+    if (!mean) return -1;
+    if (!Sigma) return -2;
+    if (!base_samples) return -3;
+    if (R < 0) return -4;
+    if (q < 1 || q > 8) return -5;
+    if (S <= 0) return -6;
+    if (!value) return -9;
+    TRY_CUDA(launch_qei(mean, Sigma, base_samples, R, q, S, best_f, jitter, value, gmean, gSigma, info, (cudaStream_t)stream_));
+    return 0;
+}
+
+extern "C" int hdbo_cdist(const double* X, int64_t ldx, int n, int d, double* Xs, double* xn, double* D_pad, void* stream_) {
+    if (!X || ldx < d) return -1;
+    if (n <= 0 || d <= 0) return -3;
+    if (!Xs || !xn || !D_pad) return -5;
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int np = (int)rup(n, 128), dp = (int)rup(d, 16);
+    TRY_CUDA(launch_scale_inputs(X, (int)ldx, 0, n, d, nullptr, nullptr, 0, Xs, dp, np, 0, xn, 0, 1, st));
+    GemmParams g{};
+    g.A = Xs; g.B = Xs; g.C = D_pad; g.Ct = nullptr;
+    g.lda = g.ldb = dp; g.ldc = np; g.mtiles = g.ntiles = np / 128; g.kblocks = dp / BK; g.krange = KR_FULL;
+    g.lower_only = 0; g.alpha = 1.0; g.beta = 0.0;
+    TRY_CUDA(launch_gemm_nt(g, 1, st));
+    TRY_CUDA(launch_cdist_finish(D_pad, np, xn, np, st));
     return 0;
 }

@@ -41,7 +41,7 @@ __global__ void k_scale_inputs(const double* __restrict__ X, int ldx, long long 
     double s = 0.0;
     for (int k = lane; k < d_pad; k += 32) {
         double v = 0.0;
-        if (row < nrows && k < d) v = (x[k] - center[k]) * il[k];
+        if (row < nrows && k < d) v = (x[k] - (center ? center[k] : 0.0)) * (inv_ls ? il[k] : 1.0);
         o[k] = v;
         s = fma(v, v, s);
     }

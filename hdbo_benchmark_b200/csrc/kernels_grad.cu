@@ -1,0 +1,426 @@
+// Gradient-path kernels.
+//   MLL gradient (A3):        K^-1 = L^-T L^-1 (SYRK in the DMMA mainloop), G = (alpha alpha^T - K^-1) o (-2 os dk/dr2),
+//                             lengthscale gradient from one n x n x d GEMM with a column-dot epilogue, scalar traces by
+//                             warp-shuffle + block reductions.
+//   posterior backward (A6):  dV -> dK* = dV L^-1 (triangular GEMM) -> C = dK* o dK*/dr2 -> dZ = 2/l o (z rowsum(C) - C Xs).
+//   joint q x q covariance (A7) and its pairwise gradient term.
+#include "gemm_core.cuh"
+#include "kernels.cuh"
+#include "elem.cuh"
+#include "grad.cuh"
+
+namespace hdbo {
+
+__device__ __forceinline__ double warp_sum_g(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// out[c][r] = in[r][c]  (in: [rows][ld_in] using cols columns; out: [cols_pad][ld_out], zero padded rows >= cols)
+__global__ void k_transpose(const double* __restrict__ in, int ld_in, long long bs_in, int rows, int cols,
+                            double* __restrict__ out, int ld_out, long long bs_out, int cols_pad) {
+    __shared__ double t[32][33];
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int i = ty; i < 32; i += 8) {
+        int r = r0 + i, c = c0 + tx;
+        t[i][tx] = (r < rows && c < cols) ? in[b * bs_in + (size_t)r * ld_in + c] : 0.0;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        int c = c0 + i, r = r0 + tx;
+        if (c < cols_pad && r < ld_out) out[b * bs_out + (size_t)c * ld_out + r] = t[tx][i];
+    }
+}
+
+cudaError_t launch_transpose(const double* in, int ld_in, long long bs_in, int rows, int cols, double* out, int ld_out,
+                             long long bs_out, int cols_pad, int batch, cudaStream_t st) {
+    dim3 grid((ld_out + 31) / 32, (cols_pad + 31) / 32, batch);
+    k_transpose<<<grid, 256, 0, st>>>(in, ld_in, bs_in, rows, cols, out, ld_out, bs_out, cols_pad);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// G[i][j] = (alpha_i alpha_j - Kinv_ij) * (-2 os dk/dr2(R2_ij)) for i,j < n, else 0.  Kinv holds lower tiles only; the
+// upper half is read transposed through shared memory.  Grid: (n_pad/32 row stripes, NSEG column segments, batch).
+// Per (stripe, segment): partial row sums of G, partial sum(W o K), partial tr(W).
+constexpr int G_NSEG = 4;
+__global__ void __launch_bounds__(256) k_mll_G(const double* __restrict__ Kinv, const double* __restrict__ R2, int ld,
+                                               long long bsM, const double* __restrict__ alpha, long long bsv,
+                                               const double* __restrict__ hyp, int n, int n_pad, int kind,
+                                               double* __restrict__ G, double* __restrict__ rowpart /*[B][NSEG][n_pad]*/,
+                                               double* __restrict__ scalpart /*[B][stripes*NSEG][2]*/) {
+    __shared__ double t[32][33];
+    __shared__ double red[32];
+    const int b = blockIdx.z, stripe = blockIdx.x, seg = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double os = hyp[b * 4 + 0];
+    const double* Ki = Kinv + b * bsM;
+    const double* R = R2 + b * bsM;
+    const double* al = alpha + b * bsv;
+    double* Gg = G + b * bsM;
+    const int ntile = n_pad / 32;
+    const int per = (ntile + G_NSEG - 1) / G_NSEG;
+    const int t0 = seg * per, t1 = min(ntile, t0 + per);
+    double rs[4] = {0, 0, 0, 0};
+    double swk = 0.0, trw = 0.0;
+    double ai[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) ai[r] = al[stripe * 32 + warp * 4 + r];
+    for (int tj = t0; tj < t1; tj++) {
+        const bool upper = tj > stripe;
+        if (upper) {
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < 4; r++) t[warp * 4 + r][lane] = Ki[(size_t)(tj * 32 + warp * 4 + r) * ld + stripe * 32 + lane];
+            __syncthreads();
+        }
+        const int j = tj * 32 + lane;
+        const double aj = al[j];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int i = stripe * 32 + warp * 4 + r;
+            double kin;
+            if (upper) kin = t[lane][warp * 4 + r];
+            else if (tj < stripe || lane <= warp * 4 + r) kin = Ki[(size_t)i * ld + j];
+            else kin = Ki[(size_t)j * ld + i];   // upper part of a diagonal 32x32 tile (stored tile is a full lower-tile member)
+            double g = 0.0;
+            if (i < n && j < n) {
+                const double W = ai[r] * aj - kin;
+                double k, dk;
+                kernel_eval(kind, R[(size_t)i * ld + j], k, dk);
+                g = W * (-2.0 * os * dk);
+                swk = fma(W, os * k, swk);
+                if (i == j) trw += W;
+            }
+            Gg[(size_t)i * ld + j] = g;
+            rs[r] += g;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        double s = warp_sum_g(rs[r]);
+        if (lane == 0) rowpart[((size_t)b * G_NSEG + seg) * n_pad + stripe * 32 + warp * 4 + r] = s;
+    }
+    swk = warp_sum_g(swk); trw = warp_sum_g(trw);
+    __syncthreads();
+    if (lane == 0) { red[warp] = swk; red[8 + warp] = trw; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, c = 0;
+        for (int w = 0; w < 8; w++) { a += red[w]; c += red[8 + w]; }
+        size_t o = ((size_t)b * gridDim.x * G_NSEG + (size_t)stripe * G_NSEG + seg) * 2;
+        scalpart[o] = a; scalpart[o + 1] = c;
+    }
+}
+
+// T = G * Xs (as NT GEMM with B = Xs^T), epilogue: colpart[bm][k] = sum_{i in tile} Xs[i][k] (Xs[i][k] s_i - T[i][k])
+struct GxaParams {
+    const double* G; const double* XsT; const double* Xs; const double* rowpart; double* colpart;
+    int ldg, ldt, ldx, n_pad, mtiles, ntiles;
+    long long bsG, bsT, bsX, bsrow, bscol;
+};
+__global__ void __launch_bounds__(NTHREADS, 1) k_gxa(GxaParams p) {
+    extern __shared__ __align__(16) double smem[];
+    const int bm = blockIdx.x, bn = blockIdx.y, b = blockIdx.z;
+    Frag acc; acc.zero();
+    gemm_nt_mainloop(p.G + b * p.bsG + (size_t)bm * BM * p.ldg, p.ldg, p.XsT + b * p.bsT + (size_t)bn * BN * p.ldt, p.ldt, 0,
+                     p.n_pad / BK, smem, acc);
+    const double* Xs = p.Xs + b * p.bsX;
+    const double* rp = p.rowpart + b * p.bsrow;
+    double colval[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+#pragma unroll
+    for (int mt = 0; mt < 8; mt++) {
+        const int i = bm * BM + frag_row(mt);
+        double s = 0.0;
+#pragma unroll
+        for (int sg = 0; sg < G_NSEG; sg++) s += rp[(size_t)sg * p.n_pad + i];
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int k = bn * BN + frag_col(nt) + e;
+                const double x = (k < p.ldx) ? Xs[(size_t)i * p.ldx + k] : 0.0;
+                colval[nt][e] += x * (x * s - acc.v[mt][nt][e]);
+            }
+    }
+    double r = tile_col_reduce(colval, smem);
+    if (threadIdx.x < 128) p.colpart[b * p.bscol + (size_t)bm * (p.ntiles * BN) + bn * BN + threadIdx.x] = r;
+}
+
+__global__ void k_mll_grad_final(const double* __restrict__ colpart, long long bscol, int mtiles, int dpt,
+                                 const double* __restrict__ scalpart, int nscal, const double* __restrict__ inv_ls,
+                                 const double* __restrict__ hyp, const double* __restrict__ scal, int d,
+                                 double* __restrict__ grad) {
+    const int b = blockIdx.x;
+    for (int k = threadIdx.x; k < d; k += blockDim.x) {
+        double s = 0.0;
+        for (int t = 0; t < mtiles; t++) s += colpart[b * bscol + (size_t)t * dpt + k];
+        grad[(size_t)b * (d + 3) + k] = s * inv_ls[(size_t)b * d + k];
+    }
+    if (threadIdx.x == 0) {
+        double a = 0.0, c = 0.0;
+        for (int t = 0; t < nscal; t++) { a += scalpart[((size_t)b * nscal + t) * 2]; c += scalpart[((size_t)b * nscal + t) * 2 + 1]; }
+        grad[(size_t)b * (d + 3) + d] = 0.5 * a / hyp[b * 4 + 0];
+        grad[(size_t)b * (d + 3) + d + 1] = 0.5 * c;
+        grad[(size_t)b * (d + 3) + d + 2] = scal[b * 8 + 3];
+    }
+}
+
+cudaError_t mll_grad(const hdbo_gp* gp, double* Kinv, double* G, double* XsT, double* part, double* grad, cudaStream_t st) {
+    const int np = gp->n_pad, dp = gp->d_pad, B = gp->batch, T = np / 128;
+    const long long nn = (long long)np * np;
+    const int dpt = (gp->d + 127) / 128 * 128;
+    cudaError_t e;
+    // K^-1 = U U^T, lower tiles, k-tile >= m-tile
+    GemmParams g{};
+    g.A = gp->Linvt; g.B = gp->Linvt; g.C = Kinv; g.Ct = nullptr;
+    g.lda = g.ldb = g.ldc = np; g.bsA = g.bsB = g.bsC = nn;
+    g.mtiles = g.ntiles = T; g.kblocks = np / BK; g.krange = KR_GE_M; g.lower_only = 1; g.alpha = 1.0; g.beta = 0.0;
+    if ((e = launch_gemm_nt(g, B, st)) != cudaSuccess) return e;
+    // part layout per batch: rowpart [G_NSEG][np] | scalpart [np/32*G_NSEG][2] | colpart [T][dpt]
+    const long long per_b = (long long)G_NSEG * np + (long long)(np / 32) * G_NSEG * 2 + (long long)T * dpt;
+    double* rowpart = part;
+    double* scalpart = part + (long long)B * G_NSEG * np;
+    double* colpart = scalpart + (long long)B * (np / 32) * G_NSEG * 2;
+    (void)per_b;
+    dim3 gg(np / 32, G_NSEG, B);
+    k_mll_G<<<gg, 256, 0, st>>>(Kinv, gp->R2, np, nn, gp->alpha, np, gp->hyp, gp->n, np, gp->kind, G, rowpart, scalpart);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = launch_transpose(gp->Xs, dp, (long long)np * dp, np, dp, XsT, np, (long long)dpt * np, dpt, B, st)) != cudaSuccess)
+        return e;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if ((e = cudaFuncSetAttribute(k_gxa, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES)) != cudaSuccess) return e;
+        attr_done = true;
+    }
+    GxaParams x{};
+    x.G = G; x.XsT = XsT; x.Xs = gp->Xs; x.rowpart = rowpart; x.colpart = colpart;
+    x.ldg = np; x.ldt = np; x.ldx = dp; x.n_pad = np; x.mtiles = T; x.ntiles = dpt / 128;
+    x.bsG = nn; x.bsT = (long long)dpt * np; x.bsX = (long long)np * dp; x.bsrow = (long long)G_NSEG * np; x.bscol = (long long)T * dpt;
+    k_gxa<<<dim3(T, dpt / 128, B), NTHREADS, GEMM_SMEM_BYTES, st>>>(x);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    k_mll_grad_final<<<B, 256, 0, st>>>(colpart, (long long)T * dpt, T, dpt, scalpart, (np / 32) * G_NSEG, gp->inv_ls, gp->hyp,
+                                        gp->scal, gp->d, grad);
+    return cudaGetLastError();
+}
+
+size_t mll_grad_part_doubles(const hdbo_gp* gp) {
+    const size_t np = gp->n_pad, B = gp->batch, T = np / 128, dpt = (gp->d + 127) / 128 * 128;
+    return B * (G_NSEG * np + (np / 32) * G_NSEG * 2 + T * dpt);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// posterior backward pieces
+// dV[c][:] = -sum_b S[a][b] V[b][:], S = gSigma + gSigma^T within the q-group of row c (q == 1: S = 2 gvar).
+__global__ void k_make_dV(const double* __restrict__ V, int ld, long long bsV, const double* __restrict__ gvar,
+                          const double* __restrict__ gSigma, long long bsg, long long bsS, int m, int q, int rows_pad,
+                          double* __restrict__ dV) {
+    const int b = blockIdx.y;
+    const int c = blockIdx.x;                       // one block per candidate row (including padding rows)
+    double* o = dV + b * bsV + (size_t)c * ld;
+    if (c >= m) { for (int j = threadIdx.x; j < ld; j += blockDim.x) o[j] = 0.0; return; }
+    const int g = c / q, a = c - g * q;
+    double S[8];
+    for (int bb = 0; bb < q; bb++) {
+        if (gSigma) S[bb] = gSigma[b * bsS + ((size_t)g * q + a) * q + bb] + gSigma[b * bsS + ((size_t)g * q + bb) * q + a];
+        else S[bb] = 2.0 * gvar[b * bsg + c];
+    }
+    const double* Vg = V + b * bsV + (size_t)g * q * ld;
+    for (int j = threadIdx.x; j < ld; j += blockDim.x) {
+        double s = 0.0;
+        for (int bb = 0; bb < q; bb++) s = fma(S[bb], Vg[(size_t)bb * ld + j], s);
+        o[j] = -s;
+    }
+}
+
+// C[c][j] = (gmean_c alpha_j + Bm[c][j]) * DK[c][j] in place over Bm; csum[c] = sum_j C[c][j].  One warp per row.
+__global__ void k_make_C(double* __restrict__ Bm, const double* __restrict__ DK, int ld, long long bsM,
+                         const double* __restrict__ gmean, long long bsg, const double* __restrict__ alpha, long long bsa,
+                         int m, int rows_pad, double* __restrict__ csum, long long bsc) {
+    const int b = blockIdx.y;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= rows_pad) return;
+    double* row = Bm + b * bsM + (size_t)c * ld;
+    const double* dk = DK + b * bsM + (size_t)c * ld;
+    const double gm = (c < m && gmean) ? gmean[b * bsg + c] : 0.0;
+    double s = 0.0;
+    for (int j = lane; j < ld; j += 32) {
+        double v = (c < m) ? (gm * alpha[b * bsa + j] + row[j]) * dk[j] : 0.0;
+        row[j] = v;
+        s += v;
+    }
+    s = warp_sum_g(s);
+    if (lane == 0) csum[b * bsc + c] = s;
+}
+
+// dZ[c][k] = 2 inv_ls[k] (Zs[c][k] csum[c] - (C Xs)[c][k])
+struct DzParams {
+    const double* Cm; const double* XsT; const double* Zs; const double* csum; const double* inv_ls; double* dZ;
+    int ldc, ldt, ldz, lddz, n_pad, m, d;
+    long long bsC, bsT, bsZ, bscs, bsdz;
+};
+__global__ void __launch_bounds__(NTHREADS, 1) k_dz(DzParams p) {
+    extern __shared__ __align__(16) double smem[];
+    const int bm = blockIdx.x, bn = blockIdx.y, b = blockIdx.z;
+    Frag acc; acc.zero();
+    gemm_nt_mainloop(p.Cm + b * p.bsC + (size_t)bm * BM * p.ldc, p.ldc, p.XsT + b * p.bsT + (size_t)bn * BN * p.ldt, p.ldt, 0,
+                     p.n_pad / BK, smem, acc);
+#pragma unroll
+    for (int mt = 0; mt < 8; mt++) {
+        const int c = bm * BM + frag_row(mt);
+        if (c >= p.m) continue;
+        const double cs = p.csum[b * p.bscs + c];
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int k = bn * BN + frag_col(nt) + e;
+                if (k < p.d)
+                    p.dZ[b * p.bsdz + (size_t)c * p.lddz + k] =
+                        2.0 * p.inv_ls[(size_t)b * p.d + k] * (p.Zs[b * p.bsZ + (size_t)c * p.ldz + k] * cs - acc.v[mt][nt][e]);
+            }
+    }
+}
+
+// joint covariance of each q-group: Sigma[a][b] = os k(r2(z_a,z_b)) - V_a.V_b (+ noise on the diagonal).  One block per group.
+__global__ void k_joint_cov(const double* __restrict__ Zs, int ldz, long long bsZ, const double* __restrict__ V, int ldv,
+                            long long bsV, const double* __restrict__ hyp, int q, int kind, int observation_noise,
+                            double* __restrict__ Sigma, long long bsS) {
+    const int b = blockIdx.y, g = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const double os = hyp[b * 4 + 0], noise = hyp[b * 4 + 1];
+    for (int pr = warp; pr < q * q; pr += nw) {
+        const int a = pr / q, c = pr - a * q;
+        if (c > a) continue;
+        const double* va = V + b * bsV + (size_t)(g * q + a) * ldv;
+        const double* vc = V + b * bsV + (size_t)(g * q + c) * ldv;
+        double dot = 0.0;
+        for (int j = lane; j < ldv; j += 32) dot = fma(va[j], vc[j], dot);
+        dot = warp_sum_g(dot);
+        double r2 = 0.0;
+        if (a != c) {
+            const double* za = Zs + b * bsZ + (size_t)(g * q + a) * ldz;
+            const double* zc = Zs + b * bsZ + (size_t)(g * q + c) * ldz;
+            for (int k = lane; k < ldz; k += 32) { double t = za[k] - zc[k]; r2 = fma(t, t, r2); }
+            r2 = warp_sum_g(r2);
+        }
+        if (lane == 0) {
+            double k, dk;
+            kernel_eval(kind, r2, k, dk);
+            double s = os * k - dot;
+            if (a == c && observation_noise) s += noise;
+            Sigma[b * bsS + ((size_t)g * q + a) * q + c] = s;
+            Sigma[b * bsS + ((size_t)g * q + c) * q + a] = s;
+        }
+    }
+}
+
+// dZ[a] += sum_{b != a} (gS_ab + gS_ba) os dk/dr2(r2_ab) 2 (za - zb) inv_ls   (k(Zq,Zq) term of the joint covariance)
+__global__ void k_dz_pairs(const double* __restrict__ Zs, int ldz, long long bsZ, const double* __restrict__ gSigma,
+                           long long bsS, const double* __restrict__ hyp, const double* __restrict__ inv_ls, int q, int d,
+                           int kind, double* __restrict__ dZ, int lddz, long long bsdz) {
+    const int b = blockIdx.y, g = blockIdx.x;
+    __shared__ double coef[64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const double os = hyp[b * 4 + 0];
+    for (int pr = warp; pr < q * q; pr += nw) {
+        const int a = pr / q, c = pr - a * q;
+        double cf = 0.0;
+        if (a != c) {
+            const double* za = Zs + b * bsZ + (size_t)(g * q + a) * ldz;
+            const double* zc = Zs + b * bsZ + (size_t)(g * q + c) * ldz;
+            double r2 = 0.0;
+            for (int k = lane; k < ldz; k += 32) { double t = za[k] - zc[k]; r2 = fma(t, t, r2); }
+            r2 = warp_sum_g(r2);
+            double k, dk;
+            kernel_eval(kind, r2, k, dk);
+            cf = (gSigma[b * bsS + ((size_t)g * q + a) * q + c] + gSigma[b * bsS + ((size_t)g * q + c) * q + a]) * os * dk * 2.0;
+        }
+        if (lane == 0) coef[pr] = cf;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < q * d; e += blockDim.x) {
+        const int a = e / d, k = e - a * d;
+        const double za = Zs[b * bsZ + (size_t)(g * q + a) * ldz + k];
+        double s = 0.0;
+        for (int c = 0; c < q; c++)
+            if (c != a) s = fma(coef[a * q + c], za - Zs[b * bsZ + (size_t)(g * q + c) * ldz + k], s);
+        dZ[b * bsdz + (size_t)(g * q + a) * lddz + k] += s * inv_ls[(size_t)b * d + k];
+    }
+}
+
+cudaError_t launch_joint_cov(const double* Zs, int ldz, long long bsZ, const double* V, int ldv, long long bsV,
+                             const double* hyp, int groups, int q, int kind, int observation_noise, double* Sigma,
+                             long long bsS, int batch, cudaStream_t st) {
+    if (groups == 0) return cudaSuccess;
+    k_joint_cov<<<dim3(groups, batch), 256, 0, st>>>(Zs, ldz, bsZ, V, ldv, bsV, hyp, q, kind, observation_noise, Sigma, bsS);
+    return cudaGetLastError();
+}
+
+cudaError_t posterior_bwd(const hdbo_gp* gp, const BwdBuffers& w, int64_t rows_alloc, int64_t m, int q, const double* gmean,
+                          const double* gvar, const double* gSigma, long long bsg, long long bsS, double* dZ, int lddz,
+                          long long bsdz, cudaStream_t st) {
+    const int np = gp->n_pad, dp = gp->d_pad, B = gp->batch;
+    const int rp = (int)((m + 127) / 128 * 128), mt = rp / 128;
+    const int dpt = (gp->d + 127) / 128 * 128;
+    const long long bsM = (long long)rows_alloc * np;
+    cudaError_t e;
+    const bool have_v = (gvar != nullptr) || (gSigma != nullptr);
+    // (1) dV into T, (2) Bm = dV * Linv into Kstar
+    if (have_v) {
+        k_make_dV<<<dim3(rp, B), 256, 0, st>>>(w.V, np, bsM, gvar, gSigma, bsg, bsS, (int)m, q, rp, w.T);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        GemmParams g{};
+        g.A = w.T; g.B = gp->Linvt; g.C = w.Kstar; g.Ct = nullptr;
+        g.lda = np; g.ldb = np; g.ldc = np; g.bsA = bsM; g.bsB = (long long)np * np; g.bsC = bsM;
+        g.mtiles = mt; g.ntiles = np / 128; g.kblocks = np / BK; g.krange = KR_GE_N; g.lower_only = 0; g.alpha = 1.0; g.beta = 0.0;
+        if ((e = launch_gemm_nt(g, B, st)) != cudaSuccess) return e;
+    } else {
+        if ((e = cudaMemsetAsync(w.Kstar, 0, sizeof(double) * (size_t)B * bsM, st)) != cudaSuccess) return e;
+    }
+    // (3) C and its row sums
+    k_make_C<<<dim3((rp + 7) / 8, B), 256, 0, st>>>(w.Kstar, w.DK, np, bsM, gmean, bsg, gp->alpha, np, (int)m, rp, w.csum, rows_alloc);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    // (4) dZ = 2/l o (z csum - C Xs)
+    if ((e = launch_transpose(gp->Xs, dp, (long long)np * dp, np, dp, w.XsT, np, (long long)dpt * np, dpt, B, st)) != cudaSuccess) return e;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if ((e = cudaFuncSetAttribute(k_dz, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES)) != cudaSuccess) return e;
+        attr_done = true;
+    }
+    DzParams p{};
+    p.Cm = w.Kstar; p.XsT = w.XsT; p.Zs = w.Zs; p.csum = w.csum; p.inv_ls = gp->inv_ls; p.dZ = dZ;
+    p.ldc = np; p.ldt = np; p.ldz = dp; p.lddz = lddz; p.n_pad = np; p.m = (int)m; p.d = gp->d;
+    p.bsC = bsM; p.bsT = (long long)dpt * np; p.bsZ = (long long)rows_alloc * dp; p.bscs = rows_alloc; p.bsdz = bsdz;
+    k_dz<<<dim3(mt, dpt / 128, B), NTHREADS, GEMM_SMEM_BYTES, st>>>(p);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (gSigma && q > 1) {
+        k_dz_pairs<<<dim3((unsigned)(m / q), B), 256, 0, st>>>(w.Zs, dp, (long long)rows_alloc * dp, gSigma, bsS, gp->hyp, gp->inv_ls, q,
+                                                               gp->d, gp->kind, dZ, lddz, bsdz);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// cdist finish: D = sqrt(max(xn_i + xn_j - 2 G, 0)), exact 0 on the diagonal
+__global__ void k_cdist_finish(double* __restrict__ D, int ld, const double* __restrict__ xn, int n_pad) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n_pad * n_pad) return;
+    const int i = (int)(idx / n_pad), j = (int)(idx - (size_t)i * n_pad);
+    const double g = D[(size_t)i * ld + j];
+    D[(size_t)i * ld + j] = (i == j) ? 0.0 : sqrt(fmax(xn[i] + xn[j] - 2.0 * g, 0.0));
+}
+
+cudaError_t launch_cdist_finish(double* D, int ld, const double* xn, int n_pad, cudaStream_t st) {
+    const size_t tot = (size_t)n_pad * n_pad;
+    k_cdist_finish<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(D, ld, xn, n_pad);
+    return cudaGetLastError();
+}
+
+}  // namespace hdbo

@@ -73,9 +73,10 @@ int hdbo_gp_fit(const hdbo_gp* gp, int need_r2, void* stream);
 
 /* Replaces: autograd backward of gpytorch ExactMarginalLogLikelihood (data term; priors are added on the host).
  * Inputs: a fitted hdbo_gp with R2.  Kinv, G: [batch][n_pad][n_pad] scratch (Kinv may alias gp->L).
- * XsT: [batch][d_pad_t][n_pad] scratch, d_pad_t = roundup(d,128).  part: [batch][(n_pad/128)][d_pad_t + 4*128] scratch.
+ * XsT: [batch][d_pad_t][n_pad] scratch, d_pad_t = roundup(d,128).  part: hdbo_mll_grad_part_bytes(gp) bytes of scratch.
  * grad: [batch][d + 3] = d(n*mll_data)/d{lengthscale[d], outputscale, noise, mean}. */
 int hdbo_mll_grad(const hdbo_gp* gp, double* Kinv, double* G, double* XsT, double* part, double* grad, void* stream);
+size_t hdbo_mll_grad_part_bytes(const hdbo_gp* gp);
 
 /* Workspace (bytes) for hdbo_posterior_acq with `rows` (multiple of 128) candidates resident at a time. */
 size_t hdbo_posterior_workspace_bytes(const hdbo_gp* gp, int64_t rows, int keep_grad_state);
@@ -97,15 +98,16 @@ int hdbo_posterior_fwd(const hdbo_gp* gp, const double* Z, int64_t ldz, int64_t 
 
 /* Joint covariance for q-batches after hdbo_posterior_fwd: Z viewed as [m/q][q][d];
  * Sigma [batch][m/q][q][q] = k(Zq,Zq) - V V^T (+ noise I).  Replaces: posterior.mvn.covariance_matrix for q > 1. */
-int hdbo_posterior_joint_cov(const hdbo_gp* gp, const double* Z, int64_t ldz, int64_t m, int q, int observation_noise,
-                             double* Sigma, int64_t bsS, void* workspace, size_t workspace_bytes, void* stream);
+int hdbo_posterior_joint_cov(const hdbo_gp* gp, int64_t m, int q, int observation_noise, double* Sigma, int64_t bsS,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward: given d loss/d mean [batch][m], d loss/d var [batch][m] (gSigma NULL) or d loss/d Sigma
- * [batch][m/q][q][q] (q > 1; the diagonal carries d/d var), returns dZ [m][d] summed over the batch.
- * Replaces: autograd through posterior(X) (A6). */
-int hdbo_posterior_bwd(const hdbo_gp* gp, const double* Z, int64_t ldz, int64_t m, int q, const double* gmean,
-                       const double* gvar, const double* gSigma, int64_t bsg, int64_t bsS, double* dZ, int64_t lddz,
-                       void* workspace, size_t workspace_bytes, void* stream);
+ * [batch][m/q][q][q] (q > 1; the diagonal carries d/d var), returns dZ [batch][m][d] (row stride lddz, batch stride
+ * bsdz); the caller sums over the batch for mixture acquisitions.  Must follow hdbo_posterior_fwd on the same
+ * workspace and m.  Replaces: autograd through posterior(X) (A6). */
+int hdbo_posterior_bwd(const hdbo_gp* gp, int64_t m, int q, const double* gmean, const double* gvar, const double* gSigma,
+                       int64_t bsg, int64_t bsS, double* dZ, int64_t lddz, int64_t bsdz, void* workspace,
+                       size_t workspace_bytes, void* stream);
 
 /* Replaces: botorch analytic acquisition forward + autograd partials on given (mean, var). */
 int hdbo_acq_elementwise(const double* mean, const double* var, int64_t m, int acq_kind, double acq_param, double* acq,

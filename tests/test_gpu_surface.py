@@ -1,0 +1,224 @@
+"""GPU tests of the differentiable paths and of the BoTorch-shaped surface (model.posterior, acqf(X) with autograd,
+fit_gpytorch_mll, optimize_acqf, qExpectedImprovement) against the CPU oracle."""
+import math
+
+import pytest
+import torch
+
+from oracle import gp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-6
+
+
+def _rel(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+
+
+def _legacy_model(dev, n=200, d=12, kind=O.MATERN52, seed=0):
+    """SingleTaskGP (Matern/RBF + ScaleKernel, no outcome transform) with fixed hyper-parameters + the oracle state."""
+    from hdbo_benchmark_b200 import gp_modules as G
+    from hdbo_benchmark_b200.models import SingleTaskGP
+
+    X, y, ls, os_, nz, mu = O.synthetic_problem(n, d, "prior", 1e-3, seed=seed)
+    os_, mu = 1.4, 0.1
+    base = (G.MaternKernel if kind == O.MATERN52 else G.RBFKernel)(ard_num_dims=d)
+    model = SingleTaskGP(X, y.unsqueeze(-1), covar_module=G.ScaleKernel(base), likelihood=G.GaussianLikelihood(),
+                         outcome_transform=None)
+    model.covar_module.base_kernel.lengthscale = ls
+    model.covar_module.outputscale = os_
+    model.likelihood.noise = nz
+    model.mean_module.constant = mu
+    model.eval()
+    st = O.fit_state(X, y, ls, os_, nz, mu, kind)
+    return model, st, (X, y, ls, os_, nz, mu)
+
+
+@pytest.mark.parametrize("kind", [O.MATERN52, O.RBF])
+def test_posterior_surface_shapes_and_values(cuda_device, kind):
+    model, st, (X, y, *_r) = _legacy_model(cuda_device, kind=kind)
+    Z = O.sobol_candidates(50, X.shape[1])
+    post = model.posterior(Z.unsqueeze(1))  # b x 1 x d, host tensor in -> host tensor out
+    assert post.mean.shape == (50, 1, 1) and post.variance.shape == (50, 1, 1) and post.mean.device.type == "cpu"
+    m_o, v_o = O.posterior(st, Z)
+    assert _rel(post.mean.reshape(-1), m_o) < REL and _rel(post.variance.reshape(-1), v_o) < REL
+    # joint q-batch covariance
+    Zq = Z[:48].reshape(12, 4, -1)
+    pq = model.posterior(Zq)
+    mq_o, S_o = O.posterior_joint(st, Zq)
+    assert pq.mean.shape == (12, 4, 1)
+    assert _rel(pq.mean.squeeze(-1), mq_o) < REL
+    assert _rel(pq.covariance_matrix, S_o) < REL
+    s = pq.rsample(torch.Size([16]))
+    assert s.shape == (16, 12, 4, 1) and torch.isfinite(s).all()
+
+
+@pytest.mark.parametrize("kind", [O.MATERN52, O.RBF])
+@pytest.mark.parametrize("acq", ["ei", "logei", "ucb"])
+def test_analytic_acquisition_value_and_gradient(cuda_device, kind, acq):
+    from hdbo_benchmark_b200 import acquisition as A
+
+    model, st, (X, y, *_r) = _legacy_model(cuda_device, kind=kind)
+    best_f = float(y.max()) - 0.3
+    d = X.shape[1]
+    Z = O.sobol_candidates(40, d, seed=7)
+    if acq == "ei":
+        f, kind_id, prm = A.ExpectedImprovement(model, best_f=best_f), O.ACQ_EI, best_f
+    elif acq == "logei":
+        f, kind_id, prm = A.LogExpectedImprovement(model, best_f=best_f), O.ACQ_LOGEI, best_f
+    else:
+        f, kind_id, prm = A.UpperConfidenceBound(model, beta=3.0), O.ACQ_UCB, 3.0
+    a_o, g_o = O.acquisition_value_and_grad_autograd(st, Z, kind_id, prm)
+    with torch.no_grad():
+        a_fused = f(Z.unsqueeze(1))
+    Zg = Z.clone().unsqueeze(1).requires_grad_(True)
+    a = f(Zg)
+    (g,) = torch.autograd.grad(a.sum(), Zg)
+    assert a.shape == (40,) and g.shape == (40, 1, d)
+    tol = REL * max(1.0, float(a_o.abs().max()))
+    assert float((a.detach() - a_o).abs().max()) < tol and float((a_fused - a_o).abs().max()) < tol
+    assert _rel(g.squeeze(1), g_o) < REL
+
+
+def test_minimize_flag_and_standardize_equivariance(cuda_device):
+    from hdbo_benchmark_b200 import acquisition as A
+    from hdbo_benchmark_b200.models import SingleTaskGP
+
+    X, y, ls, os_, nz, mu = O.synthetic_problem(150, 8, "prior", 1e-3)
+    y_raw = 5.0 + 3.0 * y
+    model = SingleTaskGP(X, y_raw.unsqueeze(-1))  # default: Standardize outcome transform, RBF ARD
+    model.covar_module.lengthscale = ls
+    model.likelihood.noise = nz
+    model.eval()
+    ys = (y_raw - y_raw.mean()) / y_raw.std()
+    st = O.fit_state(X, ys, ls, 1.0, nz, 0.0, O.RBF)
+    Z = O.sobol_candidates(30, 8, seed=11)
+    m_o, v_o = O.posterior(st, Z)
+    s, sh = float(y_raw.std()), float(y_raw.mean())
+    post = model.posterior(Z.unsqueeze(1))
+    assert _rel(post.mean.reshape(-1), m_o * s + sh) < REL and _rel(post.variance.reshape(-1), v_o * s * s) < REL
+    best = float(y_raw.max())
+    ei = A.ExpectedImprovement(model, best_f=best)(Z.unsqueeze(1))
+    assert _rel(ei, O.expected_improvement(m_o * s + sh, v_o * s * s, best)) < 1e-5
+    lei = A.LogExpectedImprovement(model, best_f=best)(Z.unsqueeze(1))
+    assert float((lei - O.log_expected_improvement(m_o * s + sh, v_o * s * s, best)).abs().max()) < 1e-6 * 50
+    ucb = A.UpperConfidenceBound(model, beta=2.0)(Z.unsqueeze(1))
+    assert _rel(ucb, O.upper_confidence_bound(m_o * s + sh, v_o * s * s, 2.0)) < REL
+    ei_min = A.ExpectedImprovement(model, best_f=float(y_raw.min()), maximize=False)(Z.unsqueeze(1))
+    want = O.expected_improvement(-(m_o * s + sh), v_o * s * s, -float(y_raw.min()))
+    assert _rel(ei_min, want) < 1e-5
+
+
+@pytest.mark.parametrize("q", [1, 2, 4])
+def test_qei_value_and_gradient(cuda_device, q):
+    from hdbo_benchmark_b200 import acquisition as A
+    from hdbo_benchmark_b200.sampling import SobolQMCNormalSampler
+
+    model, st, (X, y, *_r) = _legacy_model(cuda_device, n=160, d=10)
+    d = X.shape[1]
+    sampler = SobolQMCNormalSampler(sample_shape=torch.Size([256]), seed=6)
+    best_f = float(y.mean())
+    f = A.qExpectedImprovement(model, best_f=best_f, sampler=sampler)
+    Zq = O.sobol_candidates(6 * q, d, seed=5).reshape(6, q, d)
+    base = sampler.base_samples(q, cuda_device).cpu()
+    v_o, g_o = O.qei_value_and_grad_autograd(st, Zq, base, best_f, jitter=1e-8)
+    Zg = Zq.clone().requires_grad_(True)
+    v = f(Zg)
+    (g,) = torch.autograd.grad(v.sum(), Zg)
+    assert _rel(v, v_o) < REL
+    assert _rel(g, g_o) < 1e-5
+
+
+def test_mll_surface_matches_oracle_and_adam_loop_runs(cuda_device):
+    """ExactMarginalLogLikelihood(model(train_x), y).backward() as in the reference's training_gps.py:53-74."""
+    from hdbo_benchmark_b200 import gp_modules as G
+    from hdbo_benchmark_b200.models import ExactMarginalLogLikelihood, SingleTaskGP
+
+    X, y, ls, os_, nz, mu = O.synthetic_problem(180, 9, "prior", 1e-2)
+    d = X.shape[1]
+    ls_prior = G.LogNormalPrior(math.log(d) / 2, 1.0)  # the reference's kernel: load_solvers.py:131-138
+    kernel = G.ScaleKernel(G.RBFKernel(ard_num_dims=d, lengthscale_prior=ls_prior))
+    model = SingleTaskGP(X, y.unsqueeze(-1), covar_module=kernel, likelihood=G.GaussianLikelihood(), outcome_transform=None)
+    model.covar_module.base_kernel.lengthscale = ls
+    model.covar_module.outputscale = 1.3
+    model.likelihood.noise = nz
+    model.mean_module.constant = 0.2
+    mll = ExactMarginalLogLikelihood(model.likelihood, model)
+    model.train()
+    loss = -mll(model(model.train_inputs[0]), model.train_targets)
+    loss.backward()
+    # oracle: same quantity with torch autograd through the softplus transforms and the prior
+    raw_ls = model.covar_module.base_kernel.raw_lengthscale.detach().cpu().clone().requires_grad_(True)
+    raw_os = model.covar_module.raw_outputscale.detach().cpu().clone().requires_grad_(True)
+    raw_nz = model.likelihood.noise_covar.raw_noise.detach().cpu().clone().requires_grad_(True)
+    raw_mu = model.mean_module.raw_constant.detach().cpu().clone().requires_grad_(True)
+    sp = torch.nn.functional.softplus
+    ls_t = sp(raw_ls).reshape(-1)
+    lp = O.lognormal_log_prob(ls_t, math.log(d) / 2, 1.0) if False else (
+        -torch.log(ls_t) - math.log(1.0) - 0.5 * O.LOG_2PI - 0.5 * ((torch.log(ls_t) - math.log(d) / 2) / 1.0) ** 2).sum()
+    want = -O.exact_mll(X, y, ls_t, sp(raw_os), sp(raw_nz).reshape(()) + 1e-4, raw_mu, O.RBF, log_prior=lp)
+    want.backward()
+    assert abs(loss.item() - want.item()) < REL * abs(want.item())
+    assert _rel(model.covar_module.base_kernel.raw_lengthscale.grad, raw_ls.grad) < REL
+    assert _rel(model.covar_module.raw_outputscale.grad, raw_os.grad) < REL
+    assert _rel(model.likelihood.noise_covar.raw_noise.grad, raw_nz.grad) < REL
+    assert _rel(model.mean_module.raw_constant.grad, raw_mu.grad) < REL
+    # Adam loop (reference trainer) decreases the loss
+    opt = torch.optim.Adam(model.parameters(), lr=0.05)
+    first = None
+    for it in range(15):
+        opt.zero_grad()
+        loss = -mll(model(model.train_inputs[0]), model.train_targets)
+        loss.backward()
+        opt.step()
+        first = loss.item() if first is None else first
+    assert loss.item() < first
+    sd = model.state_dict()
+    for key in ("covar_module.base_kernel.raw_lengthscale", "covar_module.raw_outputscale",
+                "likelihood.noise_covar.raw_noise", "mean_module.raw_constant"):
+        assert key in sd
+
+
+def test_fit_gpytorch_mll_and_optimize_acqf_end_to_end(cuda_device):
+    from hdbo_benchmark_b200 import acquisition as A
+    from hdbo_benchmark_b200.fit import fit_gpytorch_mll
+    from hdbo_benchmark_b200.models import ExactMarginalLogLikelihood, SingleTaskGP
+    from hdbo_benchmark_b200.optim import optimize_acqf
+
+    torch.manual_seed(0)
+    d = 6
+    X = torch.rand(40, d, dtype=torch.float64)
+    y = -((X - 0.4) ** 2).sum(-1, keepdim=True) + 0.01 * torch.randn(40, 1, dtype=torch.float64)
+    model = SingleTaskGP(X, y)
+    mll = ExactMarginalLogLikelihood(model.likelihood, model)
+    model.train()
+    before = mll(model(model.train_inputs[0]), model.train_targets).item()
+    fit_gpytorch_mll(mll)
+    model.train()
+    after = mll(model(model.train_inputs[0]), model.train_targets).item()
+    model.eval()
+    assert after > before
+    # the fitted hyper-parameters reproduce the oracle's MLL and posterior
+    ys = model.train_targets.cpu()
+    ls = model.covar_module.lengthscale.detach().cpu().reshape(-1)
+    nz = float(model.likelihood.noise.detach().cpu())
+    mu = float(model.mean_module.constant.detach().cpu())
+    lp = O.lognormal_log_prob(ls, math.sqrt(2) + 0.5 * math.log(d), math.sqrt(3)) + O.lognormal_log_prob(torch.tensor(nz), -4.0, 1.0)
+    want = O.exact_mll(X, ys, ls, 1.0, nz, mu, O.RBF, log_prior=lp).item()
+    assert abs(after - want) < REL * abs(want)
+    acqf = A.LogExpectedImprovement(model, best_f=float(y.max()))
+    bounds = torch.stack([torch.zeros(d), torch.ones(d)]).double()
+    cand, val = optimize_acqf(acqf, bounds, q=1, num_restarts=8, raw_samples=256, options={"seed": 1})
+    assert cand.shape == (1, d) and (cand >= 0).all() and (cand <= 1).all()
+    # the optimiser's answer is at least as good as the best raw sample, evaluated by the oracle
+    st = O.fit_state(X, ys, ls, 1.0, nz, mu, O.RBF)
+    s, sh = float(y.std()), float(y.mean())
+    def oracle_logei(Z):
+        m, v = O.posterior(st, Z)
+        return O.log_expected_improvement(m * s + sh, v * s * s, float(y.max()))
+    from hdbo_benchmark_b200.sampling import draw_sobol_samples
+    raw = draw_sobol_samples(bounds, 256, 1, seed=1).squeeze(1)
+    assert oracle_logei(cand)[0] >= oracle_logei(raw).max() - 1e-9
+    assert abs(float(val) - float(oracle_logei(cand)[0])) < 1e-6 * max(1.0, abs(float(val)))
