@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Headline benchmark: acquisition evaluations per second at n=4096, d=256 (BASELINE.json metric, config #3).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N ...            # the reference arm: CPU FP64 restatement on the host cores
+
+One step = posterior mean + variance + LogEI for every candidate of a scrambled-Sobol pool (2^20 per GPU) against a
+fitted exact GP (n=4096, d=256, ARD Matern-5/2; L^-1 and alpha resident) + the arg-max.  `value` times the pool
+resident in HBM; `e2e` times the same work from pinned HOST memory (H2D of the candidates and D2H of the
+acquisition values inside the timed region).  Multi-GPU: every rank owns an independent pool shard (weak scaling),
+the only collective is a 16-byte/rank all-gather of (max, argmax) per step.
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+METRIC = "acq evals/sec at n=4096,d=256"
+UNIT = "evals/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=3)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--n", type=int, default=4096)
+    p.add_argument("--d", type=int, default=256)
+    p.add_argument("--pool", type=int, default=1 << 20, help="candidates per GPU per step")
+    p.add_argument("--cpu-sample", type=int, default=8192, help="candidates per CPU-baseline batch")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"synthetic GP n={args.n}, d={args.d}, ARD Matern-5/2, posterior+LogEI+argmax over a 2^{int(math.log2(args.pool))}"
+                    f"-candidate scrambled-Sobol pool per GPU (BASELINE.json configs[2])",
+        "n_train": args.n, "d": args.d, "pool_per_gpu": args.pool, "pool_total": args.pool * world,
+        "acquisition": "LogExpectedImprovement", "kernel": "matern52_ard", "noise": 1e-3,
+        "parallelism": f"pool-shard x{world}", "cache": "inputs larger than L2 (K* chunk 620 MB per launch, L^-1 67 MB; 126 MB L2)",
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_rate(args, st, Z_sample, best_f, budget_s=12.0):
+    """The reference path on the host cores: plain-torch FP64 restatement (oracle) of BoTorch's
+    model.posterior + LogExpectedImprovement, no grad, all threads."""
+    from oracle import gp_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        m, v = O.posterior(st, Z_sample)  # warm-up
+        O.log_expected_improvement(m, v, best_f)
+        t0 = time.perf_counter()
+        reps = 0
+        while True:
+            m, v = O.posterior(st, Z_sample)
+            a = O.log_expected_improvement(m, v, best_f)
+            int(a.argmax())
+            reps += 1
+            dt = time.perf_counter() - t0
+            if dt > budget_s or reps >= 200:
+                break
+    return reps * Z_sample.shape[0] / dt, reps, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import gp_oracle as O
+
+    X, y, ls, os_, nz, mu = O.synthetic_problem(args.n, args.d)
+    torch.set_num_threads(os.cpu_count() or 1)
+    st = O.fit_state(X, y, ls, os_, nz, mu, O.MATERN52)
+    Z = O.sobol_candidates(args.cpu_sample, args.d)
+    best_f = float(y.max())
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 1)):
+            m, v = O.posterior(st, Z); O.log_expected_improvement(m, v, best_f)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            m, v = O.posterior(st, Z)
+            a = O.log_expected_improvement(m, v, best_f)
+            int(a.argmax())
+        dt = time.perf_counter() - t0
+    value = args.steps * args.cpu_sample / dt
+    cores = torch.get_num_threads()
+    sample = f"{args.cpu_sample} Sobol candidates per step (bounded sample of the 2^20 pool), oracle/gp_oracle.py posterior+LogEI+argmax"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "botorch/gpytorch are not installable offline (not in /opt/wheelhouse); the reference arm is the CPU FP64 "
+                "restatement of their exact path (oracle port), all host threads",
+    }))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch.distributed as dist
+
+    from hdbo_benchmark_b200 import _lib
+    from hdbo_benchmark_b200.distributed import global_argmax
+    from hdbo_benchmark_b200.engine import DEFAULT_CHUNK_ROWS, DeviceGP, _rup
+    from hdbo_benchmark_b200.models import mll_gradient
+    from oracle import gp_oracle as O  # synthetic workload generator + cpu_baseline leg only
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    n, d, m = args.n, args.d, args.pool
+    X, y, ls, os_, nz, mu = O.synthetic_problem(n, d)
+    best_f = float(y.max())
+    gp = DeviceGP(X.to(dev), y.to(dev), _lib.KERNEL_MATERN52, keep_r2=True)
+    gp.set_hyper(ls.to(dev), os_, nz, mu)
+    gp.fit()
+
+    # ---- secondary metric: exact MLL value + full hyper-gradient (kernel build -> potrf -> inverse -> gradient) ----
+    def mll_once():
+        gp.fit_once(need_r2=True)
+        return mll_gradient(gp)
+    for _ in range(2):
+        mll_once()
+    torch.cuda.synchronize()
+    mll_ms = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); mll_once(); e1.record(); torch.cuda.synchronize()
+        mll_ms.append(e0.elapsed_time(e1))
+    gp.fit(need_r2=False)
+
+    # ---- candidate pool of this rank: scrambled Sobol, fast-forwarded to the rank's shard ----
+    eng = torch.quasirandom.SobolEngine(d, scramble=True, seed=3)
+    if rank:
+        eng.fast_forward(rank * m)
+    Z_host = torch.empty(m, d, dtype=torch.float64).pin_memory()
+    eng.draw(m, out=Z_host, dtype=torch.float64)
+    Z_dev = Z_host.to(dev)
+    acq_host = torch.empty(m, dtype=torch.float64).pin_memory()
+
+    def step_resident():
+        _, _, acq = gp.posterior_acq(Z_dev, _lib.ACQ_LOGEI, best_f, want_mean=False, want_var=False)
+        v, i = gp.argmax(acq[0])
+        return global_argmax(v, i, rank * m) if world > 1 else (v, i)
+
+    def step_e2e():
+        _, v, i = gp.posterior_acq_host(Z_host, _lib.ACQ_LOGEI, best_f, out_host=acq_host)
+        return global_argmax(v, i, rank * m) if world > 1 else (v, i)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
+    # ---- FP64 tensor peak, measured live (denominator of the roofline) ----
+    scratch = torch.zeros(8, dtype=torch.float64, device=dev)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    fl = C.c_double(0.0)
+    peak = 0.0
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.hdbo_fp64_peak_probe(scratch.data_ptr(), 16384, sms, C.byref(fl), torch.cuda.current_stream().cuda_stream), "peak")
+        e1.record(); torch.cuda.synchronize()
+        peak = max(peak, fl.value / e0.elapsed_time(e1) / 1e9)
+
+    for _ in range(args.warmup):
+        step_resident()
+    clocks = ClockSampler(local)
+    clocks.start()
+    lib.hdbo_profile_enable(1)
+    ms_total, (best_v, best_i) = timed(step_resident, args.steps)
+    prof_ms = (C.c_double * 2)()
+    prof_n = (C.c_int64 * 2)()
+    lib.hdbo_profile_collect(prof_ms, prof_n)
+    lib.hdbo_profile_enable(0)
+    clk = clocks.stop()
+    value = args.steps * m * world / (ms_total / 1e3)
+
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_e2e()
+        ms_e2e, (best_v2, best_i2) = timed(step_e2e, args.steps)
+        assert int(best_i2) == int(best_i), "host path and resident path disagree on the arg-max"
+        e2e = {"value": args.steps * m * world / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+               "h2d_bytes_per_step": m * d * 8 * world, "d2h_bytes_per_step": (m * 8 + 16) * world,
+               "api": "DeviceGP.posterior_acq_host (pinned host candidates in, pinned host acquisition values + argmax out)"}
+
+    if rank == 0:
+        chunks = math.ceil(m / DEFAULT_CHUNK_ROWS)
+        launches = 4 * chunks + 1  # scale, cross, var, finalize per chunk + argmax
+        var_ms, var_n = prof_ms[1], prof_n[1]
+        cross_ms = prof_ms[0]
+        alg_var = float(args.steps) * m * float(n) * n  # n^2 flops per candidate (triangular V = K* L^-T)
+        alg_cross = float(args.steps) * m * 2.0 * n * d
+        achieved = alg_var / (var_ms / 1e3) / 1e12 if var_ms > 0 else None
+        traffic = None
+        ncu_path = ROOT / "profiles" / "ncu_summary.json"
+        if ncu_path.exists():
+            try:
+                traffic = json.loads(ncu_path.read_text()).get("k_var", {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, world), "clocks": clk,
+            "gpu_launches": launches * args.steps, "argmax_index": int(best_i),
+            "roofline": {
+                "kernel": "k_var (V = K* L^-T, triangular k-range, DMMA.8x8x4)", "bound": "tensor",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": traffic, "launches": int(var_n), "avg_launch_ms": var_ms / max(int(var_n), 1),
+                "share_of_step": var_ms / ms_total,
+                "algorithmic_flops_per_launch": alg_var / max(int(var_n), 1),
+                "peak_source": "FP64 DMMA.8x8x4 issue ceiling measured live by hdbo_fp64_peak_probe (MEASURED_PEAKS.json has "
+                               "no FP64 entry; tcgen05 has no f64 kind, so the bf16 figure there does not bound this path)",
+                "cross_kernel": {"achieved": alg_cross / (cross_ms / 1e3) / 1e12 if cross_ms > 0 else None,
+                                 "share_of_step": cross_ms / ms_total},
+                "whole_step_tflops": args.steps * m * (2.0 * n * d + float(n) * n + 2 * n) / (ms_total / 1e3) / 1e12,
+            },
+            "mll_fit_grad_ms": min(mll_ms),
+        }
+        if e2e is not None:
+            out["e2e"] = e2e
+        if not args.no_cpu_baseline:
+            st = O.fit_state(X, y, ls, os_, nz, mu, O.MATERN52)
+            Zs = Z_host[: args.cpu_sample].clone()
+            rate, reps, dt = cpu_reference_rate(args, st, Zs, best_f)
+            out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                   "sample": f"{reps} x {args.cpu_sample} candidates of the same pool in {dt:.1f} s, "
+                                             "oracle/gp_oracle.py posterior+LogEI+argmax (torch FP64, MKL)"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -5,6 +5,8 @@
 #include "elem.cuh"
 #include "grad.cuh"
 
+#include <vector>
+
 using namespace hdbo;
 
 #define TRY_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return (int)_e; } while (0)
@@ -45,6 +47,46 @@ extern "C" int hdbo_gp_fit(const hdbo_gp* gp, int need_r2, void* stream_) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// ---- opt-in profiling: CUDA events around the GEMM phases of the posterior, recorded on the caller's stream ----
+namespace {
+constexpr int PROF_CLASSES = 2;   // 0 = cross-kernel build (k_cross), 1 = variance contraction (k_var)
+struct Prof {
+    bool on = false;
+    std::vector<cudaEvent_t> ev[PROF_CLASSES];   // pairs: start, stop
+    size_t used[PROF_CLASSES] = {0, 0};
+} g_prof;
+void prof_mark(int cls, cudaStream_t st) {
+    if (!g_prof.on) return;
+    if (g_prof.used[cls] == g_prof.ev[cls].size()) {
+        cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return;
+        g_prof.ev[cls].push_back(e);
+    }
+    cudaEventRecord(g_prof.ev[cls][g_prof.used[cls]++], st);
+}
+}  // namespace
+
+extern "C" int hdbo_profile_enable(int on) {
+    g_prof.on = on != 0;
+    for (int c = 0; c < PROF_CLASSES; c++) g_prof.used[c] = 0;
+    return 0;
+}
+
+extern "C" int hdbo_profile_collect(double* ms_by_class, int64_t* launches_by_class) {
+    for (int c = 0; c < PROF_CLASSES; c++) {
+        double tot = 0.0; int64_t cnt = 0;
+        for (size_t i = 0; i + 1 < g_prof.used[c]; i += 2) {
+            float ms = 0.f;
+            if (cudaEventSynchronize(g_prof.ev[c][i + 1]) != cudaSuccess) return (int)cudaGetLastError();
+            if (cudaEventElapsedTime(&ms, g_prof.ev[c][i], g_prof.ev[c][i + 1]) != cudaSuccess) return (int)cudaGetLastError();
+            tot += ms; cnt++;
+        }
+        if (ms_by_class) ms_by_class[c] = tot;
+        if (launches_by_class) launches_by_class[c] = cnt;
+        g_prof.used[c] = 0;
+    }
+    return 0;
+}
+
 namespace {
 struct PostWs {
     double *Zs, *zn, *Kstar, *meanpart, *varpart, *DK, *V, *T, *XsT;
@@ -86,14 +128,19 @@ cudaError_t posterior_chunk(const hdbo_gp* gp, const PostWs& w, int64_t rows_all
     c.bsZ = (long long)rows_alloc * dp; c.bsX = (long long)np * dp; c.bszn = rows_alloc; c.bsxn = np; c.bsalpha = np;
     c.bsK = (long long)rows_alloc * np; c.bsmp = (long long)nt * rows_alloc;
     c.m = (int)mc; c.n = gp->n; c.mtiles = mt; c.ntiles = nt; c.kblocks = dp / BK; c.kind = gp->kind;
+    prof_mark(0, st);
     e = launch_cross(c, B, st);
+    prof_mark(0, st);
     if (e != cudaSuccess) return e;
     VarParams v{};
     v.Kstar = w.Kstar; v.Linv = gp->Linv; v.V = keep ? w.V : nullptr; v.varpart = w.varpart;
     v.ldk = np; v.ldl = np; v.ldv = np;
     v.bsK = (long long)rows_alloc * np; v.bsL = (long long)np * np; v.bsV = (long long)rows_alloc * np;
     v.bsvp = (long long)nt * rows_alloc; v.mtiles = mt; v.ntiles = nt;
-    return launch_var(v, B, st);
+    prof_mark(1, st);
+    e = launch_var(v, B, st);
+    prof_mark(1, st);
+    return e;
 }
 }  // namespace
 
@@ -257,5 +304,30 @@ extern "C" int hdbo_cdist(const double* X, int64_t ldx, int n, int d, double* Xs
     g.lower_only = 0; g.alpha = 1.0; g.beta = 0.0;
     TRY_CUDA(launch_gemm_nt(g, 1, st));
     TRY_CUDA(launch_cdist_finish(D_pad, np, xn, np, st));
+    return 0;
+}
+
+// ---- FP64 tensor (DMMA.8x8x4) issue-ceiling probe: the denominator of every FP64 roofline fraction ----
+__global__ void __launch_bounds__(512) k_dmma_peak(double* out, int iters) {
+    double a = threadIdx.x * 1e-9, b = threadIdx.x * 2e-9;
+    double c[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { c[j][0] = 0; c[j][1] = 0; }
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) dmma884(c[j][0], c[j][1], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s += c[j][0] + c[j][1];
+    if (s == 12345.678) out[0] = s;
+}
+
+extern "C" int hdbo_fp64_peak_probe(double* scratch, int iters, int sms, double* flops_out, void* stream_) {
+    if (!scratch) return -1;
+    if (iters <= 0 || sms <= 0) return -2;
+    k_dmma_peak<<<sms, 512, 0, (cudaStream_t)stream_>>>(scratch, iters);
+    TRY_CUDA(cudaGetLastError());
+    if (flops_out) *flops_out = 2.0 * 256 * 8 * (double)iters * 16 * sms;   /* host pointer */
     return 0;
 }

@@ -145,6 +145,45 @@ class DeviceGP:
                                           _stream()), "hdbo_posterior_acq")
         return mean, var, acq
 
+    def posterior_acq_host(self, Z_host: torch.Tensor, acq_kind: int, acq_param: float, out_host: Optional[torch.Tensor] = None,
+                           copy_rows: int = 1 << 17, chunk_rows: int = DEFAULT_CHUNK_ROWS):
+        """End-to-end pool evaluation from HOST memory (pinned for full overlap): candidates are streamed to the device in
+        `copy_rows` slabs on a copy stream (double-buffered) while the previous slab is evaluated; the acquisition values
+        [m] come back to `out_host` and the arg-max (value, index) is reduced on the device.  batch == 1 only."""
+        assert self.fitted and self.batch == 1
+        m, d = Z_host.shape
+        f64 = dict(dtype=torch.float64, device=self.device)
+        main = torch.cuda.current_stream()
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._slabs = None
+        if self._slabs is None or self._slabs[0].shape[0] < min(copy_rows, m) or self._slabs[0].shape[1] != d:
+            self._slabs = [torch.empty(min(copy_rows, m), d, **f64) for _ in range(2)]
+        rows = min(_rup(min(copy_rows, m), 128), _rup(chunk_rows, 128))
+        ws = self.workspace(rows)
+        acq = torch.empty(m, **f64)
+        ready = [torch.cuda.Event() for _ in range(2)]
+        free = [torch.cuda.Event() for _ in range(2)]
+        for ev in free:
+            ev.record(main)
+        step = self._slabs[0].shape[0]
+        for i, off in enumerate(range(0, m, step)):
+            mc = min(step, m - off)
+            slab = self._slabs[i % 2]
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(free[i % 2])
+                slab[:mc].copy_(Z_host[off:off + mc], non_blocking=True)
+                ready[i % 2].record(self._copy_stream)
+            main.wait_event(ready[i % 2])
+            check(self.lib.hdbo_posterior_acq(C.byref(self.desc), ptr(slab), slab.stride(0), mc, 0, acq_kind, float(acq_param),
+                                              0, 0, acq.data_ptr() + off * 8, m, ptr(ws), ws.numel(), main.cuda_stream),
+                  "hdbo_posterior_acq")
+            free[i % 2].record(main)
+        val, idx = self.argmax(acq)
+        if out_host is not None:
+            out_host.copy_(acq, non_blocking=True)
+        return acq, val, idx
+
     def argmax(self, v: torch.Tensor):
         v = v.reshape(-1)
         out_val = torch.empty(1, dtype=torch.float64, device=self.device)

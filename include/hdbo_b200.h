@@ -131,6 +131,17 @@ int hdbo_dgemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, do
  * Xs/xn/work as produced internally: caller passes scratch Xs [n_pad][d_pad], xn [n_pad], D_pad [n_pad][n_pad]. */
 int hdbo_cdist(const double* X, int64_t ldx, int n, int d, double* Xs, double* xn, double* D_pad, void* stream);
 
+/* Opt-in profiling for bench.py: while enabled, CUDA events are recorded on the caller's stream around the two GEMM
+ * phases of the posterior (class 0 = cross-kernel build, class 1 = variance contraction).  collect() synchronises on
+ * the recorded events, returns total milliseconds and launch counts per class (host arrays of 2) and resets.
+ * This is the only mutable global state of the library and is off by default. */
+int hdbo_profile_enable(int on);
+int hdbo_profile_collect(double* ms_by_class, int64_t* launches_by_class);
+
+/* Launches a register-only DMMA.8x8x4 loop on `sms` CTAs x 512 threads (scratch: >= 8 bytes of device memory) and
+ * writes the flops it performs to *flops_out (HOST pointer).  Timed by the caller: measured FP64 tensor peak. */
+int hdbo_fp64_peak_probe(double* scratch, int iters, int sms, double* flops_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
