@@ -1,0 +1,164 @@
+"""CPU tests (`-m "not gpu"`): the C-ABI library loads and exports every symbol the header declares, the host-side
+mirror of the BoTorch/GPyTorch interface behaves (constraints, priors, parameter names, initial-condition
+heuristics, samplers), and the product path fails loudly -- never falls back -- when there is no GPU."""
+import math
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    from hdbo_benchmark_b200 import _lib
+
+    header = (ROOT / "include" / "hdbo_b200.h").read_text()
+    declared = set(re.findall(r"\b(hdbo_[a-z0-9_]+)\s*\(", header))
+    declared.discard("hdbo_gp")
+    assert declared, "no declarations parsed"
+    lib = _lib.load()  # raises if the .so is missing or lacks a symbol of the ctypes table
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/hdbo_b200.h but not exported"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    assert lib.hdbo_version() >= 100
+
+
+def test_abi_rejects_bad_arguments_without_touching_the_gpu():
+    import ctypes as C
+
+    from hdbo_benchmark_b200 import _lib
+
+    lib = _lib.load()
+    gp = _lib.HdboGp(n=10, d=3, n_pad=100, d_pad=16, kind=0, batch=1)  # n_pad is not roundup(n, 128)
+    assert lib.hdbo_gp_fit(C.byref(gp), 0, None) < 0
+    assert lib.hdbo_posterior_workspace_bytes(C.byref(gp), 128, 0) == 0
+    gp = _lib.HdboGp(n=10, d=3, n_pad=128, d_pad=16, kind=7, batch=1)  # unknown kernel
+    assert lib.hdbo_gp_fit(C.byref(gp), 0, None) < 0
+    gp = _lib.HdboGp(n=10, d=3, n_pad=128, d_pad=16, kind=0, batch=1)
+    assert lib.hdbo_posterior_workspace_bytes(C.byref(gp), 100, 0) == 0  # rows not a multiple of 128
+    need = lib.hdbo_posterior_workspace_bytes(C.byref(gp), 256, 0)
+    assert need >= 8 * 256 * (16 + 1 + 128 + 2)
+    assert lib.hdbo_posterior_workspace_bytes(C.byref(gp), 256, 1) > need
+    assert lib.hdbo_qei(None, None, None, 1, 4, 16, 0.0, 0.0, None, None, None, None, None) < 0
+    assert lib.hdbo_dgemm_nt(None, 16, None, 16, None, 16, 128, 128, 16, 1.0, 0.0, 0, 0, None) < 0
+
+
+def test_product_path_fails_loudly_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from hdbo_benchmark_b200 import _lib
+    from hdbo_benchmark_b200.engine import DeviceGP
+    from hdbo_benchmark_b200.models import SingleTaskGP
+
+    X, y = torch.rand(8, 2, dtype=torch.float64), torch.rand(8, 1, dtype=torch.float64)
+    with pytest.raises(_lib.HdboError):
+        SingleTaskGP(X, y)
+    with pytest.raises(_lib.HdboError):
+        DeviceGP(X, y.squeeze(-1), 0)
+
+
+def test_product_package_never_imports_the_oracle():
+    for path in (ROOT / "hdbo_benchmark_b200").rglob("*.py"):
+        text = path.read_text()
+        assert "oracle" not in text.replace("the oracle", "").replace("CPU oracle", ""), f"{path} mentions the oracle"
+
+
+def test_constraints_round_trip_and_bounds():
+    from hdbo_benchmark_b200 import gp_modules as G
+
+    for c in (G.Positive(), G.GreaterThan(1e-4), G.Interval(0.5, 3.0), G.GreaterThan(2.5e-2, transform=None), G.LessThan(4.0)):
+        v = torch.tensor([0.7, 1.9, 2.5], dtype=torch.float64)
+        torch.testing.assert_close(c.transform(c.inverse_transform(v)), v, rtol=1e-12, atol=1e-12)
+    assert G.GreaterThan(2.5e-2, transform=None).raw_bounds() == (2.5e-2, math.inf)
+    assert G.Positive().raw_bounds() == (-math.inf, math.inf)
+    sp = G.GreaterThan(1e-4)
+    assert float(sp.transform(torch.tensor(-50.0, dtype=torch.float64))) >= 1e-4
+
+
+def test_priors_match_torch_distributions():
+    from hdbo_benchmark_b200 import gp_modules as G
+
+    x = torch.tensor([0.3, 1.7, 4.0], dtype=torch.float64)
+    torch.testing.assert_close(G.GammaPrior(3.0, 6.0).log_prob(x), torch.distributions.Gamma(3.0, 6.0).log_prob(x))
+    torch.testing.assert_close(G.LogNormalPrior(1.2, 0.8).log_prob(x), torch.distributions.LogNormal(1.2, 0.8).log_prob(x))
+    torch.testing.assert_close(G.NormalPrior(0.2, 1.5).log_prob(x), torch.distributions.Normal(0.2, 1.5).log_prob(x))
+    torch.testing.assert_close(G.HalfCauchyPrior(0.1).log_prob(x), torch.distributions.HalfCauchy(0.1).log_prob(x))
+    assert abs(float(G.LogNormalPrior(1.0, 0.5).mode) - math.exp(1.0 - 0.25)) < 1e-12
+    assert abs(float(G.GammaPrior(3.0, 6.0).mode) - 2.0 / 6.0) < 1e-12
+
+
+def test_reference_kernel_constructor_and_gpytorch_parameter_names():
+    """The kernel the reference builds (load_solvers.py:131-138) and the raw-parameter names its trainer saves
+    (training_gps.py:101-108)."""
+    from hdbo_benchmark_b200 import gp_modules as G
+
+    d = 128
+    kernel = G.ScaleKernel(G.RBFKernel(ard_num_dims=d, lengthscale_prior=G.LogNormalPrior(math.log(d) / 2, 1.0)))
+    names = dict(kernel.named_parameters())
+    assert set(names) == {"raw_outputscale", "base_kernel.raw_lengthscale"}
+    assert names["base_kernel.raw_lengthscale"].shape == (1, d)
+    assert abs(float(kernel.outputscale) - math.log(2.0)) < 1e-12  # softplus(0), GPyTorch's default init
+    kernel.base_kernel.lengthscale = 3.0
+    torch.testing.assert_close(kernel.base_kernel.lengthscale, torch.full((1, d), 3.0, dtype=torch.float64))
+    pri = list(kernel.named_priors_with_values("covar_module."))
+    assert [p[0] for p in pri] == ["covar_module.base_kernel.lengthscale_prior"]
+    lik = G.GaussianLikelihood()
+    assert set(dict(lik.named_parameters())) == {"noise_covar.raw_noise"}
+    assert float(lik.noise) > 1e-4
+    lik.noise = 0.02
+    assert abs(float(lik.noise) - 0.02) < 1e-12
+    sd = kernel.state_dict()
+    assert "base_kernel.raw_lengthscale_constraint.lower_bound" in sd and "base_kernel.lengthscale_prior.loc" in sd
+    k2 = G.ScaleKernel(G.RBFKernel(ard_num_dims=d, lengthscale_prior=G.LogNormalPrior(0.0, 1.0)))
+    k2.load_state_dict(sd)
+    torch.testing.assert_close(k2.base_kernel.lengthscale, kernel.base_kernel.lengthscale)
+    with pytest.raises(NotImplementedError):
+        G.MaternKernel(nu=1.5)
+
+
+def test_initial_condition_heuristics_keep_the_argmax():
+    from hdbo_benchmark_b200.optim import initialize_q_batch, initialize_q_batch_nonneg
+
+    g = torch.Generator().manual_seed(0)
+    X = torch.rand(200, 2, 3, generator=g, dtype=torch.float64)
+    Y = torch.randn(200, generator=g, dtype=torch.float64)
+    ics = initialize_q_batch(X, Y, 10, generator=g)
+    assert ics.shape == (10, 2, 3)
+    assert any(torch.equal(ic, X[Y.argmax()]) for ic in ics)
+    Ypos = Y.abs()
+    ics = initialize_q_batch_nonneg(X, Ypos, 10, generator=g)
+    assert any(torch.equal(ic, X[Ypos.argmax()]) for ic in ics)
+    assert initialize_q_batch(X, torch.zeros(200, dtype=torch.float64), 5, generator=g).shape == (5, 2, 3)  # degenerate: random
+    assert initialize_q_batch_nonneg(X, torch.zeros(200, dtype=torch.float64), 5, generator=g).shape == (5, 2, 3)
+    with pytest.raises(RuntimeError):
+        initialize_q_batch(X, Y, 500)
+    huge = Y * 1e4  # exp overflow path: eta is halved until the weights are finite
+    assert initialize_q_batch(X, huge, 10, generator=g).shape == (10, 2, 3)
+
+
+def test_samplers():
+    from hdbo_benchmark_b200.sampling import SobolQMCNormalSampler, draw_sobol_normal_samples, draw_sobol_samples
+
+    b = torch.tensor([[-5.0, 0.0], [5.0, 2.0]], dtype=torch.float64)
+    S = draw_sobol_samples(b, n=64, q=3, seed=1)
+    assert S.shape == (64, 3, 2) and (S[..., 0] >= -5).all() and (S[..., 0] <= 5).all() and (S[..., 1] <= 2).all()
+    torch.testing.assert_close(S, draw_sobol_samples(b, n=64, q=3, seed=1))
+    z = draw_sobol_normal_samples(4, 4096, seed=0)
+    assert torch.isfinite(z).all() and abs(float(z.mean())) < 0.02 and abs(float(z.std()) - 1.0) < 0.02
+    s = SobolQMCNormalSampler(sample_shape=torch.Size([128]), seed=3)
+    a1, a2 = s.base_samples(4, "cpu"), s.base_samples(4, "cpu")
+    assert a1.shape == (128, 4) and a1 is a2  # fixed across calls
+
+
+def test_shard_bounds_cover_everything():
+    from hdbo_benchmark_b200.distributed import shard_bounds
+
+    for total in (0, 1, 7, 1 << 20, 1000003):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [e - s for s, e in spans]
+            assert max(sizes) - min(sizes) <= 1
