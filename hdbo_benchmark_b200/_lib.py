@@ -39,7 +39,9 @@ class HdboError(RuntimeError):
 _SIGNATURES = {
     "hdbo_version": (C.c_int, []),
     "hdbo_gp_fit": (C.c_int, [C.POINTER(HdboGp), C.c_int, _dp]),
-    "hdbo_mll_grad": (C.c_int, [C.POINTER(HdboGp), _dp, _dp, _dp, _dp, _dp, _dp]),
+    "hdbo_gp_fit_downdated": (C.c_int, [C.POINTER(HdboGp), C.c_int, _dp, C.c_int64, C.c_int64, _dp]),
+    "hdbo_posterior_workspace_V": (C.c_void_p, [C.POINTER(HdboGp), C.c_int64, _dp]),
+    "hdbo_mll_grad":(C.c_int, [C.POINTER(HdboGp), _dp, _dp, _dp, _dp, _dp, _dp]),
     "hdbo_mll_grad_part_bytes": (C.c_size_t, [C.POINTER(HdboGp)]),
     "hdbo_posterior_workspace_bytes": (C.c_size_t, [C.POINTER(HdboGp), C.c_int64, C.c_int]),
     "hdbo_posterior_acq": (C.c_int, [C.POINTER(HdboGp), _dp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_double,

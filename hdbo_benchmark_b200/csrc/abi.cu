@@ -25,8 +25,14 @@ extern "C" int hdbo_version(void) { return 100; }
 
 // ------------------------------------------------------------------------------------------------------------
 extern "C" int hdbo_gp_fit(const hdbo_gp* gp, int need_r2, void* stream_) {
+    return hdbo_gp_fit_downdated(gp, need_r2, nullptr, 0, 0, stream_);
+}
+
+extern "C" int hdbo_gp_fit_downdated(const hdbo_gp* gp, int need_r2, const double* V, int64_t ldv, int64_t k_pad,
+                                     void* stream_) {
     if (int e = check_gp(gp)) return e;
     if (need_r2 && !gp->R2) return -2;
+    if (V && (gp->batch != 1 || ldv < k_pad || k_pad % 128 || ldv % 2)) return -4;
     cudaStream_t st = (cudaStream_t)stream_;
     const int np = gp->n_pad, dp = gp->d_pad, B = gp->batch;
     const long long nn = (long long)np * np;
@@ -38,6 +44,13 @@ extern "C" int hdbo_gp_fit(const hdbo_gp* gp, int need_r2, void* stream_) {
     sb.ldx = dp; sb.ldk = np; sb.bsX = (long long)np * dp; sb.bsxn = np; sb.bsK = nn;
     sb.n = gp->n; sb.tiles = np / 128; sb.kblocks = dp / BK; sb.kind = gp->kind;
     TRY_CUDA(launch_sym_build(sb, B, st));
+    if (V) {   // Khat -= V V^T on the lower tiles (joint predictive covariance K(Z,Z) + noise I - V V^T)
+        GemmParams g{};
+        g.A = V; g.B = V; g.C = gp->Awork; g.Ct = nullptr;
+        g.lda = g.ldb = (int)ldv; g.ldc = np; g.mtiles = g.ntiles = np / 128; g.kblocks = (int)(k_pad / BK);
+        g.krange = KR_FULL; g.lower_only = 1; g.alpha = -1.0; g.beta = 1.0;
+        TRY_CUDA(launch_gemm_nt(g, 1, st));
+    }
     TRY_CUDA(chol_inverse(gp->Awork, gp->L, gp->Linv, gp->Linvt, np, nn, np / 128, gp->n, gp->info, B, st));
     // w = Linv (y - m);  alpha = Linv^T w
     TRY_CUDA(launch_tri_matvec(gp->Linv, np, nn, np, 0, nullptr, 0, gp->y, gp->n, gp->hyp, gp->w, np, B, st));
@@ -147,6 +160,11 @@ cudaError_t posterior_chunk(const hdbo_gp* gp, const PostWs& w, int64_t rows_all
 extern "C" size_t hdbo_posterior_workspace_bytes(const hdbo_gp* gp, int64_t rows, int keep_grad_state) {
     if (check_gp(gp) || rows <= 0 || rows % 128) return 0;
     return carve(gp, rows, keep_grad_state, nullptr).bytes;
+}
+
+extern "C" double* hdbo_posterior_workspace_V(const hdbo_gp* gp, int64_t rows, void* workspace) {
+    if (check_gp(gp) || rows <= 0 || rows % 128 || !workspace) return nullptr;
+    return carve(gp, rows, 1, workspace).V;
 }
 
 extern "C" int hdbo_posterior_acq(const hdbo_gp* gp, const double* Z, int64_t ldz, int64_t m, int observation_noise,

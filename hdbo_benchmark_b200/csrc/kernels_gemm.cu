@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cross(CrossParams p) {
                 double r2 = fmax((znr + xnv[nt][e]) - 2.0 * acc.v[mt][nt][e], 0.0);
                 double k, dk;
                 kernel_eval(p.kind, r2, k, dk);
-                bool valid = (bn * BN + c + e) < p.n;
+                bool valid = ((bn * BN + c + e) < p.n) && ((bm * BM + r) < p.m);   // padding rows / columns are exact zeros
                 kv[e] = valid ? os * k : 0.0;
                 dv[e] = valid ? os * dk : 0.0;
                 s += kv[e] * alv[nt][e];

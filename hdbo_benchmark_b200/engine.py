@@ -21,6 +21,7 @@ from . import _lib
 from ._lib import HdboGp, check, ptr
 
 DEFAULT_CHUNK_ROWS = 148 * 128  # one 128-row tile per SM per column tile
+WORKSPACE_CAP_BYTES = 8 << 30
 
 
 def _rup(x: int, m: int) -> int:
@@ -134,6 +135,9 @@ class DeviceGP:
             Z = Z.to(torch.float64).contiguous()
         m = Z.shape[0]
         rows = min(_rup(max(m, 1), 128), _rup(chunk_rows, 128))
+        # keep the resident K* slab of a batched (fully Bayesian) GP below ~8 GiB
+        per_row = 8 * self.batch * (self.n_pad + self.d_pad + 2 * (self.n_pad // 128) + 1)
+        rows = max(128, min(rows, (WORKSPACE_CAP_BYTES // per_row) // 128 * 128))
         ws = self.workspace(rows)
         f64 = dict(dtype=torch.float64, device=self.device)
         out = out or {}

@@ -443,3 +443,92 @@ class ExactMarginalLogLikelihood(MarginalLogLikelihood):
 
 def legacy_single_task_gp(train_X, train_Y, **kwargs) -> SingleTaskGP:
     return SingleTaskGP(train_X, train_Y, legacy_defaults=True, **kwargs)
+
+
+# ------------------------------------------------------------------------------------------------------
+# fully Bayesian (SAAS) model: S hyper-parameter samples = one batched device GP  (A10)
+# ------------------------------------------------------------------------------------------------------
+class SaasFullyBayesianSingleTaskGP(ExactGPBase):
+    """Drop-in for botorch.models.fully_bayesian.SaasFullyBayesianSingleTaskGP once MCMC samples exist
+    (the `saas_bo` solver, /root/reference/src/hdbo_benchmark/utils/experiments/load_solvers.py:183-194).
+
+    `load_mcmc_samples({"lengthscale": [S,d], "outputscale": [S], "mean": [S], "noise": [S]})` installs a batch of S
+    Matern-5/2 ARD GPs that share the training data; kernel build, Cholesky, inverse and posterior run batched on the
+    device (grid.z = S).  `posterior(X)` returns a Gaussian-mixture posterior with the MCMC dimension at -3
+    (mean: b x S x q x 1, plus `.mixture_mean` / `.mixture_variance`).  The NUTS sampler itself (Pyro control flow) is
+    out of scope; `sample_saas_prior` draws hyper-parameters from the SAAS prior for synthetic workloads."""
+
+    _is_fully_bayesian = True
+
+    def __init__(self, train_X, train_Y, train_Yvar=None, outcome_transform=None, input_transform=None):
+        super().__init__()
+        if train_Yvar is not None:
+            raise NotImplementedError("fixed-noise SAAS models are not on the hdbo_benchmark hot path")
+        self._init_data(train_X, train_Y, outcome_transform, input_transform)
+        self.mean_module = None
+        self.covar_module = None
+        self.likelihood = None
+        self._num_samples = 0
+
+    @property
+    def batch_shape(self) -> torch.Size:
+        return torch.Size([self._num_samples]) if self._num_samples else torch.Size([])
+
+    @property
+    def num_mcmc_samples(self) -> int:
+        return self._num_samples
+
+    def load_mcmc_samples(self, mcmc_samples) -> None:
+        ls = torch.as_tensor(mcmc_samples["lengthscale"], dtype=torch.float64)
+        S, d = ls.shape[0], self.train_inputs[0].shape[-1]
+        ls = ls.reshape(S, -1)
+        if ls.shape[1] != d:
+            raise ValueError(f"lengthscale samples must be S x {d}")
+        bs = torch.Size([S])
+        self.covar_module = ScaleKernel(MaternKernel(nu=2.5, ard_num_dims=d, batch_shape=bs))
+        self.mean_module = ConstantMean(batch_shape=bs)
+        self.likelihood = GaussianLikelihood(batch_shape=bs, noise_constraint=GreaterThan(1e-6))
+        self._num_samples = S
+        self.to(self._dev)
+        self.covar_module.base_kernel.lengthscale = ls.reshape(S, 1, d)
+        self.covar_module.outputscale = torch.as_tensor(mcmc_samples["outputscale"], dtype=torch.float64).reshape(S)
+        self.mean_module.constant = torch.as_tensor(mcmc_samples["mean"], dtype=torch.float64).reshape(S)
+        noise = mcmc_samples.get("noise")
+        noise = torch.full((S,), 1e-6, dtype=torch.float64) if noise is None else torch.as_tensor(noise, dtype=torch.float64)
+        self.likelihood.noise = noise.reshape(S, 1).clamp_min(1e-6 * (1 + 1e-9) + 1e-12)
+        self._gp = None
+        self.eval()
+
+    @property
+    def median_lengthscale(self) -> torch.Tensor:
+        return self.covar_module.base_kernel.lengthscale.detach().reshape(self._num_samples, -1).median(0).values
+
+    def forward(self, X):
+        if self._num_samples == 0:
+            raise RuntimeError("load_mcmc_samples() must be called before evaluating the model")
+        return super().forward(X)
+
+    def posterior(self, X, observation_noise: bool = False, posterior_transform=None, **kwargs):
+        if self._num_samples == 0:
+            raise RuntimeError("load_mcmc_samples() must be called before evaluating the model")
+        return super().posterior(X, observation_noise=observation_noise, posterior_transform=posterior_transform, **kwargs)
+
+
+def sample_saas_prior(S: int, d: int, seed: int = 4):
+    """Hyper-parameter draws from the SAAS prior: tau ~ HalfCauchy(0.1),
+    1/l_k^2 ~ tau * HalfCauchy(1) clamped to [1e-4, 1e2], outputscale ~ Gamma(2, 0.15), noise ~ Gamma(0.9, 10) + 1e-4,
+    mean ~ N(0, 1).  Returns the dict `load_mcmc_samples` expects (CPU float64 tensors)."""
+    g = torch.Generator().manual_seed(seed)
+    def half_cauchy(shape, scale):
+        u = torch.rand(shape, generator=g, dtype=torch.float64)
+        return scale * torch.tan(0.5 * math.pi * u)
+    tau = half_cauchy((S, 1), 0.1)
+    inv_l2 = (tau * half_cauchy((S, d), 1.0)).clamp(1e-4, 1e2)
+    def gamma(shape, conc, rate):
+        return torch._standard_gamma(torch.full(shape, conc, dtype=torch.float64), generator=g) / rate
+    return {
+        "lengthscale": inv_l2.rsqrt(),
+        "outputscale": gamma((S,), 2.0, 0.15).clamp_min(1e-2),
+        "noise": gamma((S,), 0.9, 10.0) + 1e-4,
+        "mean": torch.randn(S, generator=g, dtype=torch.float64),
+    }

@@ -71,6 +71,12 @@ int hdbo_version(void);
  * need_r2 != 0 also keeps the squared-distance matrix for hdbo_mll_grad. */
 int hdbo_gp_fit(const hdbo_gp* gp, int need_r2, void* stream);
 
+/* Same, but factorises K + noise I - V V^T (V: [n_pad][k_pad] row-major, leading dimension ldv, padding rows zero;
+ * batch == 1).  With X = test inputs, y = test targets - posterior mean and V from hdbo_posterior_fwd this yields the
+ * joint predictive log-density that gpytorch's eval-mode `mll(model(test_x), test_y)` computes
+ * (/root/reference/src/hdbo_benchmark/utils/experiments/training_gps.py:77-94): scal[2] = log N(y | mu, Sigma). */
+int hdbo_gp_fit_downdated(const hdbo_gp* gp, int need_r2, const double* V, int64_t ldv, int64_t k_pad, void* stream);
+
 /* Replaces: autograd backward of gpytorch ExactMarginalLogLikelihood (data term; priors are added on the host).
  * Inputs: a fitted hdbo_gp with R2.  Kinv, G: [batch][n_pad][n_pad] scratch (Kinv may alias gp->L).
  * XsT: [batch][d_pad_t][n_pad] scratch, d_pad_t = roundup(d,128).  part: hdbo_mll_grad_part_bytes(gp) bytes of scratch.
@@ -80,6 +86,10 @@ size_t hdbo_mll_grad_part_bytes(const hdbo_gp* gp);
 
 /* Workspace (bytes) for hdbo_posterior_acq with `rows` (multiple of 128) candidates resident at a time. */
 size_t hdbo_posterior_workspace_bytes(const hdbo_gp* gp, int64_t rows, int keep_grad_state);
+
+/* Address of V = K* L^-T ([rows][n_pad], leading dimension n_pad) inside a keep_grad_state workspace of `rows` rows,
+ * valid after hdbo_posterior_fwd. */
+double* hdbo_posterior_workspace_V(const hdbo_gp* gp, int64_t rows, void* workspace);
 
 /* Replaces: model.posterior(X).mean/.variance for X of shape [m,1,d] followed by an analytic acquisition
  * (botorch ExpectedImprovement / LogExpectedImprovement / UpperConfidenceBound forward), no-grad candidate-pool
