@@ -1,4 +1,4 @@
-// FP64 "NT" GEMM tile mainloop for sm_100a:  acc[128x128] += A[128 x K] * B[128 x K]^T
+// FP64 "NT" GEMM tile mainloop for sm_100a:  acc[TM x TN] += A[TM x K] * B[TN x K]^T
 //
 // Both operands are row-major with the contraction index contiguous, which is how every
 // contraction on the GP hot path is laid out in HBM (scaled inputs [rows x d], K* [m x n],
@@ -6,12 +6,14 @@
 //
 // Hardware mapping (measured, profiles/r01_fp64_peak.json): tcgen05 has no f64 kind, the FP64
 // tensor instruction on sm_100a is DMMA.8x8x4 (every mma.sync f64 shape lowers to it), peak
-// 37.0 TFLOP/s = 64 FMA/clk/SM.  One CTA = 256 threads = 8 warps in a 2 (M) x 4 (N) grid, each warp
-// owns a 64x32 sub-tile = 8x4 DMMA tiles = 64 accumulator doubles per thread.  Operands are staged
-// with cp.async (LDGSTS, 16 B) through a 3-stage ring of [128 x 16] slabs; the smem row stride is
-// 20 doubles so that the 8 rows x 4 k fragment read of a warp hits 16 distinct 8-byte banks per
-// half-warp (conflict-free).  Per k4 step a warp issues 12 LDS.64 and 32 DMMA, so the DMMA pipe is
-// the only saturated resource (smem traffic is 24 B/clk/SM of 128).
+// 37.0 TFLOP/s = 64 FMA/clk/SM.  The default configuration G128 is one CTA = 256 threads = 8 warps in a
+// 2 (M) x 4 (N) grid, each warp owning a 64x32 sub-tile = 8x4 DMMA tiles = 64 accumulator doubles per
+// thread.  Operands are staged with cp.async (LDGSTS, 16 B) through a 3-stage ring of [rows x 16] slabs; the
+// smem row stride is 20 doubles so that the 8 rows x 4 k fragment read of a warp hits 16 distinct 8-byte
+// banks per half-warp (conflict-free).  Per k4 step a G128 warp issues 12 LDS.64 and 32 DMMA, so the DMMA
+// pipe is the only saturated resource (smem traffic is 24 B/clk/SM of 128).
+// G64 (64x64, 4 warps) and G32 (32x32, 4 warps) exist for the latency-bound nodes of the Cholesky /
+// inverse recursion, where a launch has far fewer than 148 128-tiles and smaller tiles buy SM parallelism.
 //
 // All operand matrices handed to the mainloop are padded: row counts to multiples of 128, the
 // contraction length to a multiple of 16, leading dimensions to multiples of 16 doubles (128 B), so
@@ -22,15 +24,9 @@
 
 namespace hdbo {
 
-constexpr int BM = 128;
-constexpr int BN = 128;
 constexpr int BK = 16;
 constexpr int STAGES = 3;
 constexpr int SLD = BK + 4;                  // smem row stride (doubles)
-constexpr int NTHREADS = 256;
-constexpr int TILE_ELEMS = BM * SLD;         // doubles per operand per stage
-constexpr int GEMM_SMEM_BYTES = STAGES * 2 * TILE_ELEMS * 8;   // 122880
-constexpr int KB_PER_TILE = BM / BK;         // k-blocks per 128-wide tile (8)
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -48,78 +44,111 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-// accumulator fragment of one thread: acc[mt][nt][e] = C[wm*64 + mt*8 + (lane>>2)][wn*32 + nt*8 + (lane&3)*2 + e]
-struct Frag {
-    double v[8][4][2];
-    __device__ __forceinline__ void zero() {
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) { v[i][j][0] = 0.0; v[i][j][1] = 0.0; }
-    }
-};
+template <int TM_, int TN_, int WM_, int WN_>
+struct GemmT {
+    static constexpr int TM = TM_, TN = TN_, WM = WM_, WN = WN_;
+    static constexpr int THREADS = 32 * WM * WN;
+    static constexpr int MT = TM / (8 * WM);     // DMMA tiles per warp along M
+    static constexpr int NT = TN / (8 * WN);     // DMMA tiles per warp along N
+    static constexpr int A_ELEMS = TM * SLD, B_ELEMS = TN * SLD;
+    static constexpr int SMEM_BYTES = STAGES * (A_ELEMS + B_ELEMS) * 8;
+    static constexpr int KB_PER_TM = TM / BK, KB_PER_TN = TN / BK;
 
-__device__ __forceinline__ int frag_row(int mt) { return ((threadIdx.x >> 5) >> 2) * 64 + mt * 8 + ((threadIdx.x & 31) >> 2); }
-__device__ __forceinline__ int frag_col(int nt) { return ((threadIdx.x >> 5) & 3) * 32 + nt * 8 + ((threadIdx.x & 3) << 1); }
-
-__device__ __forceinline__ void load_slab(double* s, const double* __restrict__ g, int ld, int kb, int tid) {
+    // accumulator fragment of one thread: v[mt][nt][e] = C[frag_row(mt)][frag_col(nt) + e]
+    struct Frag {
+        double v[MT][NT][2];
+        __device__ __forceinline__ void zero() {
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        int c = tid + i * NTHREADS;
-        int row = c >> 3, ch = c & 7;
-        cp_async16(s + row * SLD + ch * 2, g + (size_t)row * ld + (size_t)kb * BK + ch * 2);
-    }
-}
-
-// gA / gB point at the first row of the 128-row operand slabs (column 0).  k-blocks [kb_begin, kb_end).
-__device__ __forceinline__ void gemm_nt_mainloop(const double* __restrict__ gA, int lda, const double* __restrict__ gB,
-                                                 int ldb, int kb_begin, int kb_end, double* smem, Frag& acc) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;
-    double* sA = smem;
-    double* sB = smem + STAGES * TILE_ELEMS;
-    const int nkb = kb_end - kb_begin;
+            for (int i = 0; i < MT; i++)
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; s++) {
-        if (s < nkb) {
-            load_slab(sA + s * TILE_ELEMS, gA, lda, kb_begin + s, tid);
-            load_slab(sB + s * TILE_ELEMS, gB, ldb, kb_begin + s, tid);
+                for (int j = 0; j < NT; j++) { v[i][j][0] = 0.0; v[i][j][1] = 0.0; }
         }
-        cp_async_commit();
+    };
+    static __device__ __forceinline__ int frag_row(int mt) {
+        return ((threadIdx.x >> 5) / WN) * (TM / WM) + mt * 8 + ((threadIdx.x & 31) >> 2);
     }
-    const int frag_off_a = (wm * 64 + (lane >> 2)) * SLD + (lane & 3);
-    const int frag_off_b = (wn * 32 + (lane >> 2)) * SLD + (lane & 3);
-    int slot = 0;
-    for (int it = 0; it < nkb; it++) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        {
-            int nx = it + STAGES - 1;
-            int nslot = slot + STAGES - 1; if (nslot >= STAGES) nslot -= STAGES;
-            if (nx < nkb) {
-                load_slab(sA + nslot * TILE_ELEMS, gA, lda, kb_begin + nx, tid);
-                load_slab(sB + nslot * TILE_ELEMS, gB, ldb, kb_begin + nx, tid);
+    static __device__ __forceinline__ int frag_col(int nt) {
+        return ((threadIdx.x >> 5) % WN) * (TN / WN) + nt * 8 + ((threadIdx.x & 3) << 1);
+    }
+
+    template <int ROWS>
+    static __device__ __forceinline__ void load_slab(double* s, const double* __restrict__ g, int ld, int kb, int tid) {
+#pragma unroll
+        for (int c = tid; c < ROWS * 8; c += THREADS) {
+            int row = c >> 3, ch = c & 7;
+            cp_async16(s + row * SLD + ch * 2, g + (size_t)row * ld + (size_t)kb * BK + ch * 2);
+        }
+    }
+
+    // gA / gB point at the first row of the operand slabs (column 0).  k-blocks [kb_begin, kb_end).
+    static __device__ __forceinline__ void mainloop(const double* __restrict__ gA, int lda, const double* __restrict__ gB,
+                                                    int ldb, int kb_begin, int kb_end, double* smem, Frag& acc) {
+        const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+        const int wm = warp / WN, wn = warp % WN;
+        double* sA = smem;
+        double* sB = smem + STAGES * A_ELEMS;
+        const int nkb = kb_end - kb_begin;
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; s++) {
+            if (s < nkb) {
+                load_slab<TM>(sA + s * A_ELEMS, gA, lda, kb_begin + s, tid);
+                load_slab<TN>(sB + s * B_ELEMS, gB, ldb, kb_begin + s, tid);
             }
             cp_async_commit();
         }
-        const double* a_s = sA + slot * TILE_ELEMS + frag_off_a;
-        const double* b_s = sB + slot * TILE_ELEMS + frag_off_b;
+        const int frag_off_a = (wm * (TM / WM) + (lane >> 2)) * SLD + (lane & 3);
+        const int frag_off_b = (wn * (TN / WN) + (lane >> 2)) * SLD + (lane & 3);
+        int slot = 0;
+        for (int it = 0; it < nkb; it++) {
+            cp_async_wait<STAGES - 2>();
+            __syncthreads();
+            {
+                int nx = it + STAGES - 1;
+                int nslot = slot + STAGES - 1; if (nslot >= STAGES) nslot -= STAGES;
+                if (nx < nkb) {
+                    load_slab<TM>(sA + nslot * A_ELEMS, gA, lda, kb_begin + nx, tid);
+                    load_slab<TN>(sB + nslot * B_ELEMS, gB, ldb, kb_begin + nx, tid);
+                }
+                cp_async_commit();
+            }
+            const double* a_s = sA + slot * A_ELEMS + frag_off_a;
+            const double* b_s = sB + slot * B_ELEMS + frag_off_b;
 #pragma unroll
-        for (int k4 = 0; k4 < BK / 4; k4++) {
-            double a[8], b[4];
+            for (int k4 = 0; k4 < BK / 4; k4++) {
+                double a[MT], b[NT];
 #pragma unroll
-            for (int mt = 0; mt < 8; mt++) a[mt] = a_s[mt * 8 * SLD + k4 * 4];
+                for (int mt = 0; mt < MT; mt++) a[mt] = a_s[mt * 8 * SLD + k4 * 4];
 #pragma unroll
-            for (int nt = 0; nt < 4; nt++) b[nt] = b_s[nt * 8 * SLD + k4 * 4];
+                for (int nt = 0; nt < NT; nt++) b[nt] = b_s[nt * 8 * SLD + k4 * 4];
 #pragma unroll
-            for (int mt = 0; mt < 8; mt++)
+                for (int mt = 0; mt < MT; mt++)
 #pragma unroll
-                for (int nt = 0; nt < 4; nt++) dmma884(acc.v[mt][nt][0], acc.v[mt][nt][1], a[mt], b[nt]);
+                    for (int nt = 0; nt < NT; nt++) dmma884(acc.v[mt][nt][0], acc.v[mt][nt][1], a[mt], b[nt]);
+            }
+            slot = (slot + 1 == STAGES) ? 0 : slot + 1;
         }
-        slot = (slot + 1 == STAGES) ? 0 : slot + 1;
+        cp_async_wait<0>();
+        __syncthreads();
     }
-    cp_async_wait<0>();
-    __syncthreads();
+};
+
+using G128 = GemmT<128, 128, 2, 4>;
+using G64 = GemmT<64, 64, 2, 2>;
+using G32 = GemmT<32, 32, 2, 2>;
+
+// ---- the default 128x128 configuration under its historical names (used by the fused kernels) ----
+constexpr int BM = 128;
+constexpr int BN = 128;
+constexpr int NTHREADS = G128::THREADS;
+constexpr int GEMM_SMEM_BYTES = G128::SMEM_BYTES;   // 122880
+constexpr int KB_PER_TILE = BM / BK;                // k-blocks per 128-wide tile (8)
+using Frag = G128::Frag;
+
+__device__ __forceinline__ int frag_row(int mt) { return G128::frag_row(mt); }
+__device__ __forceinline__ int frag_col(int nt) { return G128::frag_col(nt); }
+__device__ __forceinline__ void gemm_nt_mainloop(const double* __restrict__ gA, int lda, const double* __restrict__ gB,
+                                                 int ldb, int kb_begin, int kb_end, double* smem, Frag& acc) {
+    G128::mainloop(gA, lda, gB, ldb, kb_begin, kb_end, smem, acc);
 }
 
 // Deterministic per-row reduction of a per-thread value rowval[mt] (already summed over the thread's 8 columns):

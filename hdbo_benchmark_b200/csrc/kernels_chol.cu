@@ -11,106 +11,25 @@
 // the inverse).  Having L^-1 explicitly turns every later triangular solve on the hot path (posterior variance,
 // alpha, K^-1 for the MLL gradient) into a GEMM / matvec -- the same trade BoTorch's fast_pred_var cache makes.
 //
-// The leaf factors one 128x128 diagonal tile in shared memory (rank-1 updates in LDL^T form, one barrier per
-// column) and inverts it in place.  A non-positive pivot records info = 1-based global index (first one wins) and
-// continues with a unit pivot so the stream never hangs; the host applies the jitter schedule.
+// The leaf (leaf.cuh) factors AND inverts one 128x128 diagonal tile in a single CTA: 32x32 diagonal blocks in
+// registers with warp shuffles, panel rows by per-thread substitution, block updates with DMMA from shared memory.
+// A non-positive pivot records info = 1-based global index (first one wins) and continues with a unit pivot so the
+// stream never hangs; the host applies the jitter schedule.
 #include "gemm_core.cuh"
 #include "kernels.cuh"
+#include "leaf.cuh"
 
 namespace hdbo {
-
-constexpr int LEAF_THREADS = 512;
-constexpr int LLD = 129;
-constexpr int LEAF_SMEM_BYTES = (128 * LLD + 128 + 8) * 8;
-
-__global__ void __launch_bounds__(LEAF_THREADS, 1)
-k_leaf_chol_inv(double* __restrict__ Awork, double* __restrict__ L, double* __restrict__ Linv, double* __restrict__ Linvt,
-                int ld, long long bs, int tile, int32_t* __restrict__ info) {
-    extern __shared__ __align__(16) double sm[];
-    double* S = sm;                 // [128][129]
-    double* col = sm + 128 * LLD;   // [128] staging column
-    const int b = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;   // 16 warps
-    const size_t base = (size_t)b * bs + (size_t)tile * 128 * ld + (size_t)tile * 128;
-    const double* Ag = Awork + base;
-    for (int e = tid; e < 128 * 128; e += LEAF_THREADS) {
-        int i = e >> 7, k = e & 127;
-        S[i * LLD + k] = (k <= i) ? Ag[(size_t)i * ld + k] : 0.0;
-    }
-    // ---- factorisation: S[i][k] -= S[i][j] S[k][j] / S[j][j]  (columns stay unscaled until the end) ----
-    for (int j = 0; j < 127; j++) {
-        __syncthreads();
-        double ajj = S[j * LLD + j];
-        if (!(ajj > 0.0)) {
-            if (tid == 0) { atomicCAS(info + b, 0, tile * 128 + j + 1); }
-            __syncthreads();
-            if (tid == 0) S[j * LLD + j] = 1.0;
-            __syncthreads();
-            ajj = 1.0;
-        }
-        const double inv = 1.0 / ajj;
-        for (int i = j + 1 + warp; i < 128; i += 16) {
-            const double lij = S[i * LLD + j] * inv;
-            for (int k = j + 1 + lane; k <= i; k += 32) S[i * LLD + k] = fma(-lij, S[k * LLD + j], S[i * LLD + k]);
-        }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        double a = S[127 * LLD + 127];
-        if (!(a > 0.0)) { atomicCAS(info + b, 0, tile * 128 + 128); S[127 * LLD + 127] = 1.0; }
-    }
-    __syncthreads();
-    if (tid < 128) col[tid] = sqrt(S[tid * LLD + tid]);
-    __syncthreads();
-    for (int e = tid; e < 128 * 128; e += LEAF_THREADS) {
-        int i = e >> 7, k = e & 127;
-        if (k < i) S[i * LLD + k] = S[i * LLD + k] / col[k];
-        else if (k == i) S[i * LLD + k] = col[k];
-    }
-    __syncthreads();
-    double* Lg = L + base;
-    for (int e = tid; e < 128 * 128; e += LEAF_THREADS) {
-        int i = e >> 7, k = e & 127;
-        Lg[(size_t)i * ld + k] = S[i * LLD + k];
-    }
-    // ---- in-place inverse of the lower-triangular tile, columns right to left ----
-    // Linv[i][j] = -(sum_{k=j+1..i} Linv[i][k] L[k][j]) / L[j][j]; 4 threads per row, shuffle-combined.
-    const int row = tid >> 2, part = tid & 3;
-    for (int j = 127; j >= 0; j--) {
-        __syncthreads();
-        if (tid < 128) col[tid] = S[tid * LLD + j];   // old column j of L (rows >= j meaningful)
-        __syncthreads();
-        const double dinv = 1.0 / col[j];
-        double s = 0.0;
-        if (row > j) {
-            for (int k = j + 1 + part; k <= row; k += 4) s = fma(S[row * LLD + k], col[k], s);
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (part == 0) {
-            if (row > j) S[row * LLD + j] = -s * dinv;
-            else if (row == j) S[row * LLD + j] = dinv;
-        }
-    }
-    __syncthreads();
-    double* Lig = Linv + base;
-    double* Ltg = Linvt + base;
-    for (int e = tid; e < 128 * 128; e += LEAF_THREADS) {
-        int i = e >> 7, k = e & 127;
-        Lig[(size_t)i * ld + k] = S[i * LLD + k];
-        Ltg[(size_t)i * ld + k] = S[k * LLD + i];
-    }
-}
 
 static cudaError_t launch_leaf(double* Awork, double* L, double* Linv, double* Linvt, int ld, long long bs, int tile,
                                int32_t* info, int batch, cudaStream_t stream) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_leaf_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_leaf_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    k_leaf_chol_inv<<<batch, LEAF_THREADS, LEAF_SMEM_BYTES, stream>>>(Awork, L, Linv, Linvt, ld, bs, tile, info);
+    k_leaf_blocked<<<batch, LF_THREADS, LF_SMEM_BYTES, stream>>>(Awork, L, Linv, Linvt, ld, bs, tile, info);
     return cudaGetLastError();
 }
 

@@ -8,14 +8,15 @@
 
 namespace hdbo {
 
-__device__ __forceinline__ void krange_blocks(int mode, int bm, int bn, int kblocks, int& kb0, int& kb1) {
+// k-block range of tile (bm, bn) for tiles of TM x TN elements (kpm / kpn = k-blocks per tile edge)
+__device__ __forceinline__ void krange_blocks(int mode, int bm, int bn, int kblocks, int kpm, int kpn, int& kb0, int& kb1) {
     kb0 = 0; kb1 = kblocks;
     switch (mode) {
-        case KR_LE_N: kb1 = min(kblocks, (bn + 1) * KB_PER_TILE); break;
-        case KR_LE_M: kb1 = min(kblocks, (bm + 1) * KB_PER_TILE); break;
-        case KR_GE_N: kb0 = bn * KB_PER_TILE; break;
-        case KR_GE_M: kb0 = bm * KB_PER_TILE; break;
-        case KR_GE_MN: kb0 = max(bm, bn) * KB_PER_TILE; break;
+        case KR_LE_N: kb1 = min(kblocks, (bn + 1) * kpn); break;
+        case KR_LE_M: kb1 = min(kblocks, (bm + 1) * kpm); break;
+        case KR_GE_N: kb0 = bn * kpn; break;
+        case KR_GE_M: kb0 = bm * kpm; break;
+        case KR_GE_MN: kb0 = max(bm * kpm, bn * kpn); break;
         default: break;
     }
 }
@@ -29,25 +30,38 @@ __device__ __forceinline__ void lower_tile_decode(int t, int& bm, int& bn) {
 }
 
 // --------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 1) k_gemm_nt(GemmParams p) {
+// p.mtiles / p.ntiles count tiles of G::TM x G::TN here (the launcher rescales the 128-tile counts).
+template <class G>
+__global__ void __launch_bounds__(G::THREADS) k_gemm_nt(GemmParams p) {
     extern __shared__ __align__(16) double smem[];
     int bm, bn;
     if (p.lower_only) lower_tile_decode(blockIdx.x, bm, bn);
-    else { bm = blockIdx.x; bn = blockIdx.y; }
+    else {
+        // CTAs are dispatched in linear block order: put the tiles with the longest k-range first so the ragged
+        // triangular work drains evenly over the SMs (heavy-first list scheduling).
+        const int id = blockIdx.y * gridDim.x + blockIdx.x;
+        switch (p.krange) {
+            case KR_LE_N: bn = p.ntiles - 1 - id / p.mtiles; bm = id % p.mtiles; break;
+            case KR_GE_N: bn = id / p.mtiles; bm = id % p.mtiles; break;
+            case KR_LE_M: bm = p.mtiles - 1 - id / p.ntiles; bn = id % p.ntiles; break;
+            case KR_GE_M: case KR_GE_MN: bm = id / p.ntiles; bn = id % p.ntiles; break;
+            default: bm = blockIdx.x; bn = blockIdx.y; break;
+        }
+    }
     const int b = blockIdx.z;
     int kb0, kb1;
-    krange_blocks(p.krange, bm, bn, p.kblocks, kb0, kb1);
-    Frag acc; acc.zero();
-    gemm_nt_mainloop(p.A + b * p.bsA + (size_t)bm * BM * p.lda, p.lda, p.B + b * p.bsB + (size_t)bn * BN * p.ldb, p.ldb,
-                     kb0, kb1, smem, acc);
+    krange_blocks(p.krange, bm, bn, p.kblocks, G::KB_PER_TM, G::KB_PER_TN, kb0, kb1);
+    typename G::Frag acc; acc.zero();
+    G::mainloop(p.A + b * p.bsA + (size_t)bm * G::TM * p.lda, p.lda, p.B + b * p.bsB + (size_t)bn * G::TN * p.ldb, p.ldb,
+                kb0, kb1, smem, acc);
     double* C = p.C + b * p.bsC;
     double* Ct = p.Ct ? p.Ct + b * p.bsCt : nullptr;
 #pragma unroll
-    for (int mt = 0; mt < 8; mt++) {
-        const int i = bm * BM + frag_row(mt);
+    for (int mt = 0; mt < G::MT; mt++) {
+        const int i = bm * G::TM + G::frag_row(mt);
 #pragma unroll
-        for (int nt = 0; nt < 4; nt++) {
-            const int j = bn * BN + frag_col(nt);
+        for (int nt = 0; nt < G::NT; nt++) {
+            const int j = bn * G::TN + G::frag_col(nt);
             double2* dst = reinterpret_cast<double2*>(C + (size_t)i * p.ldc + j);
             double2 o;
             o.x = p.alpha * acc.v[mt][nt][0];
@@ -59,19 +73,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_nt(GemmParams p) {
     }
 }
 
-cudaError_t launch_gemm_nt(const GemmParams& p, int batch, cudaStream_t stream) {
+template <class G>
+static cudaError_t launch_gemm_cfg(GemmParams p, int batch, cudaStream_t stream) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_nt<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
+    p.mtiles *= 128 / G::TM;
+    p.ntiles *= 128 / G::TN;
     dim3 grid;
     if (p.lower_only) grid = dim3(p.mtiles * (p.mtiles + 1) / 2, 1, batch);
     else grid = dim3(p.mtiles, p.ntiles, batch);
     if (grid.x == 0 || grid.y == 0) return cudaSuccess;
-    k_gemm_nt<<<grid, NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
+    k_gemm_nt<G><<<grid, G::THREADS, G::SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
+}
+
+// Tile-size choice: a launch with fewer 128-tiles than SMs is latency-bound, so it is cut into 64x64 or 32x32 CTA
+// tiles (4x / 16x more CTAs, each proportionally shorter) until the grid covers the 148 SMs.
+cudaError_t launch_gemm_nt(const GemmParams& p, int batch, cudaStream_t stream) {
+    const long long t128 = (p.lower_only ? (long long)p.mtiles * (p.mtiles + 1) / 2 : (long long)p.mtiles * p.ntiles) * batch;
+    if (t128 >= 100) return launch_gemm_cfg<G128>(p, batch, stream);
+    if (t128 >= 25) return launch_gemm_cfg<G64>(p, batch, stream);
+    return launch_gemm_cfg<G32>(p, batch, stream);
 }
 
 // --------------------------------------------------------------------------------------------------------------

@@ -120,15 +120,16 @@ __global__ void __launch_bounds__(256) k_mll_G(const double* __restrict__ Kinv, 
 // T = G * Xs (as NT GEMM with B = Xs^T), epilogue: colpart[bm][k] = sum_{i in tile} Xs[i][k] (Xs[i][k] s_i - T[i][k])
 struct GxaParams {
     const double* G; const double* XsT; const double* Xs; const double* rowpart; double* colpart;
-    int ldg, ldt, ldx, n_pad, mtiles, ntiles;
+    int ldg, ldt, ldx, n_pad, mtiles, ntiles, splits;   // split-K: blockIdx.y = bn + ntiles * split
     long long bsG, bsT, bsX, bsrow, bscol;
 };
 __global__ void __launch_bounds__(NTHREADS, 1) k_gxa(GxaParams p) {
     extern __shared__ __align__(16) double smem[];
-    const int bm = blockIdx.x, bn = blockIdx.y, b = blockIdx.z;
+    const int bm = blockIdx.x, bn = blockIdx.y % p.ntiles, sp = blockIdx.y / p.ntiles, b = blockIdx.z;
+    const int kbt = p.n_pad / BK;
     Frag acc; acc.zero();
-    gemm_nt_mainloop(p.G + b * p.bsG + (size_t)bm * BM * p.ldg, p.ldg, p.XsT + b * p.bsT + (size_t)bn * BN * p.ldt, p.ldt, 0,
-                     p.n_pad / BK, smem, acc);
+    gemm_nt_mainloop(p.G + b * p.bsG + (size_t)bm * BM * p.ldg, p.ldg, p.XsT + b * p.bsT + (size_t)bn * BN * p.ldt, p.ldt,
+                     (int)((long long)kbt * sp / p.splits), (int)((long long)kbt * (sp + 1) / p.splits), smem, acc);
     const double* Xs = p.Xs + b * p.bsX;
     const double* rp = p.rowpart + b * p.bsrow;
     double colval[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
@@ -136,8 +137,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gxa(GxaParams p) {
     for (int mt = 0; mt < 8; mt++) {
         const int i = bm * BM + frag_row(mt);
         double s = 0.0;
+        if (sp == 0) {   // the x^2 s_i term is added once, by the first k-split
 #pragma unroll
-        for (int sg = 0; sg < G_NSEG; sg++) s += rp[(size_t)sg * p.n_pad + i];
+            for (int sg = 0; sg < G_NSEG; sg++) s += rp[(size_t)sg * p.n_pad + i];
+        }
 #pragma unroll
         for (int nt = 0; nt < 4; nt++)
 #pragma unroll
@@ -148,8 +151,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gxa(GxaParams p) {
             }
     }
     double r = tile_col_reduce(colval, smem);
-    if (threadIdx.x < 128) p.colpart[b * p.bscol + (size_t)bm * (p.ntiles * BN) + bn * BN + threadIdx.x] = r;
+    if (threadIdx.x < 128)
+        p.colpart[b * p.bscol + (size_t)(bm * p.splits + sp) * (p.ntiles * BN) + bn * BN + threadIdx.x] = r;
 }
+
+constexpr int GXA_MAX_SPLITS = 4;
 
 __global__ void k_mll_grad_final(const double* __restrict__ colpart, long long bscol, int mtiles, int dpt,
                                  const double* __restrict__ scalpart, int nscal, const double* __restrict__ inv_ls,
@@ -200,17 +206,22 @@ cudaError_t mll_grad(const hdbo_gp* gp, double* Kinv, double* G, double* XsT, do
     GxaParams x{};
     x.G = G; x.XsT = XsT; x.Xs = gp->Xs; x.rowpart = rowpart; x.colpart = colpart;
     x.ldg = np; x.ldt = np; x.ldx = dp; x.n_pad = np; x.mtiles = T; x.ntiles = dpt / 128;
-    x.bsG = nn; x.bsT = (long long)dpt * np; x.bsX = (long long)np * dp; x.bsrow = (long long)G_NSEG * np; x.bscol = (long long)T * dpt;
-    k_gxa<<<dim3(T, dpt / 128, B), NTHREADS, GEMM_SMEM_BYTES, st>>>(x);
+    int splits = (148 + T * (dpt / 128) * B - 1) / (T * (dpt / 128) * B);
+    splits = splits < 1 ? 1 : (splits > GXA_MAX_SPLITS ? GXA_MAX_SPLITS : splits);
+    if (splits > np / BK) splits = np / BK;
+    x.splits = splits;
+    x.bsG = nn; x.bsT = (long long)dpt * np; x.bsX = (long long)np * dp; x.bsrow = (long long)G_NSEG * np;
+    x.bscol = (long long)T * GXA_MAX_SPLITS * dpt;
+    k_gxa<<<dim3(T, (dpt / 128) * splits, B), NTHREADS, GEMM_SMEM_BYTES, st>>>(x);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    k_mll_grad_final<<<B, 256, 0, st>>>(colpart, (long long)T * dpt, T, dpt, scalpart, (np / 32) * G_NSEG, gp->inv_ls, gp->hyp,
+    k_mll_grad_final<<<B, 256, 0, st>>>(colpart, (long long)T * GXA_MAX_SPLITS * dpt, T * splits, dpt, scalpart, (np / 32) * G_NSEG, gp->inv_ls, gp->hyp,
                                         gp->scal, gp->d, grad);
     return cudaGetLastError();
 }
 
 size_t mll_grad_part_doubles(const hdbo_gp* gp) {
     const size_t np = gp->n_pad, B = gp->batch, T = np / 128, dpt = (gp->d + 127) / 128 * 128;
-    return B * (G_NSEG * np + (np / 32) * G_NSEG * 2 + T * dpt);
+    return B * (G_NSEG * np + (np / 32) * G_NSEG * 2 + T * GXA_MAX_SPLITS * dpt);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,255 @@
+// 128x128 diagonal-tile Cholesky + triangular inverse in ONE CTA (the latency-critical leaf of chol_inverse).
+//
+// Blocked 4x4 over 32x32 sub-blocks, everything resident in shared memory (row stride 132 doubles = 4 mod 16 so the
+// 8-row x 4-k DMMA fragment reads are bank-conflict free):
+//   * diagonal 32x32 block: ONE warp, the block lives in registers (lane i = row i, 32 doubles), pivots and columns are
+//     exchanged with warp shuffles -- no shared-memory round trips, no block barriers on the 32-pivot critical path;
+//   * its inverse: another warp, also in registers (lane c = column c of L^-1), overlapped with the panel solve;
+//   * panel rows below: one thread per row, right-looking substitution in registers (L_kk read as smem broadcasts);
+//   * trailing 32x32 block updates and the assembly of the tile inverse  X_ij = -(sum_k X_ik L_kj) X_jj : DMMA.8x8x4 on
+//     fragments read straight from shared memory, one 16x32 half-block per warp.
+// A non-positive pivot records info = 1-based global index (first one wins) and continues with a unit pivot.
+#pragma once
+#include "gemm_core.cuh"
+
+#ifdef LF_TIMING   /* tools/leaf_bench.cu defines `__device__ long long lf_stamps[64]` before including this file */
+#define LF_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) lf_stamps[i] = clock64(); } while (0)
+#else
+#define LF_STAMP(i) do { } while (0)
+#endif
+
+namespace hdbo {
+
+constexpr int LF_THREADS = 256;
+constexpr int LF_LD = 132;
+constexpr int LF_SMEM_DOUBLES = 128 * LF_LD + 4 * 32 * 36 + 128;
+constexpr int LF_SMEM_BYTES = LF_SMEM_DOUBLES * 8;
+constexpr unsigned LF_FULL = 0xffffffffu;
+
+// 1/sqrt(a) and sqrt(a) for a pivot on the 128-long critical path.  The two library sequences are independent and
+// overlap; a hand-rolled MUFU.RSQ seed + two FP64 Newton steps was measured SLOWER (23.1k vs 12.5k clk per 32x32
+// block, tools/leaf_bench.cu): a dependent FP64 op costs ~40 clk on B200, so the 12-op chain loses.
+__device__ __forceinline__ void lf_rsqrt_sqrt(double a, double& inv, double& d) {
+    inv = rsqrt(a);
+    d = sqrt(a);
+}
+
+// lane i holds row i (lower part) of a 32x32 SPD block; on exit row i of its Cholesky factor.  invd[j] = 1/L_jj.
+__device__ __forceinline__ int lf_warp_chol32(double (&a)[32], double* invd) {
+    const int lane = threadIdx.x & 31;
+    int bad = 0;
+    // Per-pivot dependency chain: shuffle(pivot) -> rsqrt/sqrt -> mul -> shuffle(column) -> fma, ~390 clk measured.
+    // An LDL^T variant (reciprocal in the loop, sqrt/rsqrt at the end) was measured slower (15.0k vs 12.5k clk / block).
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        double ajj = __shfl_sync(LF_FULL, a[j], j);
+        if (!(ajj > 0.0)) { if (!bad) bad = j + 1; ajj = 1.0; }
+        double inv, d;
+        lf_rsqrt_sqrt(ajj, inv, d);
+        const double l = (lane == j) ? d : a[j] * inv;
+        a[j] = l;
+        if (lane == 0) invd[j] = inv;
+#pragma unroll
+        for (int k = j + 1; k < 32; k++) {
+            const double lk = __shfl_sync(LF_FULL, l, k);
+            a[k] = fma(-l, lk, a[k]);
+        }
+    }
+    return bad;
+}
+
+// lane r holds row r of L (32x32 lower); returns in x[] column `lane` of L^-1 (x[i] = Linv[i][lane]).
+__device__ __forceinline__ void lf_warp_inv32(const double (&a)[32], const double* invd, double (&x)[32]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < 32; i++) x[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        const double xi = x[i] * invd[i];
+        x[i] = xi;
+#pragma unroll
+        for (int r = i + 1; r < 32; r++) {
+            const double lri = __shfl_sync(LF_FULL, a[i], r);
+            x[r] = fma(-lri, xi, x[r]);
+        }
+    }
+}
+
+// acc (16 rows x 32 cols, rows r0.., as 2x4 DMMA tiles) = sum over kk in [0,K) of A(r, kk) * B(kk, c)
+// fa(row, k) / fb(k, col) return shared-memory element addresses.
+template <class FA, class FB>
+__device__ __forceinline__ void lf_block_mma(double (&acc)[2][4][2], int K, FA fa, FB fb) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+#pragma unroll 4
+    for (int k4 = 0; k4 < K; k4 += 4) {
+        double a[2], b[4];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) a[mt] = *fa(mt * 8 + (lane >> 2), k4 + (lane & 3));
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) b[nt] = *fb(k4 + (lane & 3), nt * 8 + (lane >> 2));
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+    }
+}
+
+__global__ void __launch_bounds__(LF_THREADS, 1)
+k_leaf_blocked(double* __restrict__ Awork, double* __restrict__ L, double* __restrict__ Linv, double* __restrict__ Linvt,
+               int ld, long long bs, int tile, int32_t* __restrict__ info) {
+    extern __shared__ __align__(16) double sm[];
+    double* S = sm;                          // [128][132]
+    double* Dv = sm + 128 * LF_LD;           // [4][32][36] inverses of the diagonal blocks
+    double* invd = Dv + 4 * 32 * 36;         // [128] 1 / L_jj
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t base = (size_t)b * bs + (size_t)tile * 128 * ld + (size_t)tile * 128;
+    const double* Ag = Awork + base;
+    LF_STAMP(0);
+    // whole tile with 16-byte async copies, 32 in flight per thread (the strict upper part is never consumed:
+    // every store below masks it)
+#pragma unroll 8
+    for (int c = tid; c < 128 * 64; c += LF_THREADS) {
+        const int i = c >> 6, ch = c & 63;
+        cp_async16(S + i * LF_LD + ch * 2, Ag + (size_t)i * ld + ch * 2);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    LF_STAMP(1);
+
+    for (int kb = 0; kb < 4; kb++) {
+        const int o = kb * 32;
+        // ---- diagonal block: warp 0, in registers ----
+        if (warp == 0) {
+            double a[32];
+#pragma unroll
+            for (int k = 0; k < 32; k++) a[k] = S[(o + lane) * LF_LD + o + k];
+            const int bad = lf_warp_chol32(a, invd + o);
+            if (bad && lane == 0) atomicCAS(info + b, 0, tile * 128 + o + bad);
+#pragma unroll
+            for (int k = 0; k < 32; k++)
+                if (k <= lane) S[(o + lane) * LF_LD + o + k] = a[k];
+        }
+        __syncthreads();
+        LF_STAMP(2 + kb * 3);
+        // ---- warp 7: inverse of the diagonal block (registers) | threads < 32*(3-kb): panel rows below ----
+        if (warp == 7) {
+            double a[32], x[32];
+#pragma unroll
+            for (int k = 0; k < 32; k++) a[k] = S[(o + lane) * LF_LD + o + k];
+            lf_warp_inv32(a, invd + o, x);
+#pragma unroll
+            for (int i = 0; i < 32; i++) Dv[(kb * 32 + i) * 36 + lane] = (i >= lane) ? x[i] : 0.0;
+        }
+        if (tid < 32 * (3 - kb)) {
+            const int r = o + 32 + tid;
+            double acc[32];
+#pragma unroll
+            for (int c = 0; c < 32; c++) acc[c] = S[r * LF_LD + o + c];
+#pragma unroll
+            for (int k = 0; k < 32; k++) {
+                const double xk = acc[k] * invd[o + k];
+                acc[k] = xk;
+#pragma unroll
+                for (int c = k + 1; c < 32; c++) acc[c] = fma(-xk, S[(o + c) * LF_LD + o + k], acc[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < 32; c++) S[r * LF_LD + o + c] = acc[c];
+        }
+        __syncthreads();
+        LF_STAMP(3 + kb * 3);
+        // ---- trailing updates C_ib,jb -= L_ib,kb L_jb,kb^T, one 16x32 half-block per warp item ----
+        {
+            int item = 0;
+            for (int ib = kb + 1; ib < 4; ib++)
+                for (int jb = kb + 1; jb <= ib; jb++)
+                    for (int h = 0; h < 2; h++, item++) {
+                        if ((item & 7) != warp) continue;
+                        const int r0 = ib * 32 + h * 16, c0 = jb * 32;
+                        double acc[2][4][2];
+                        lf_block_mma(acc, 32,
+                                     [&](int r, int k) { return S + (r0 + r) * LF_LD + o + k; },
+                                     [&](int k, int c) { return S + (c0 + c) * LF_LD + o + k; });
+#pragma unroll
+                        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                            for (int nt = 0; nt < 4; nt++) {
+                                double* p = S + (r0 + mt * 8 + (lane >> 2)) * LF_LD + c0 + nt * 8 + (lane & 3) * 2;
+                                p[0] -= acc[mt][nt][0];
+                                p[1] -= acc[mt][nt][1];
+                            }
+                    }
+        }
+        __syncthreads();
+        LF_STAMP(4 + kb * 3);
+    }
+    // ---- L tile out; then the diagonal blocks of S become their inverses ----
+    double* Lg = L + base;
+    for (int e = tid; e < 128 * 128; e += LF_THREADS) {
+        const int i = e >> 7, k = e & 127;
+        Lg[(size_t)i * ld + k] = (k <= i) ? S[i * LF_LD + k] : 0.0;
+    }
+    __syncthreads();
+    for (int e = tid; e < 4 * 32 * 32; e += LF_THREADS) {
+        const int kb = e >> 10, i = (e >> 5) & 31, c = e & 31;
+        S[(kb * 32 + i) * LF_LD + kb * 32 + c] = Dv[(kb * 32 + i) * 36 + c];
+    }
+    __syncthreads();
+    LF_STAMP(14);
+    // ---- tile inverse, block columns right to left: X_ib,jb = -(sum_{k=jb+1..ib} X_ib,k L_k,jb) X_jb,jb ----
+    for (int jb = 2; jb >= 0; jb--) {
+        const int nitems = (3 - jb) * 2;
+        const int ib = jb + 1 + (warp >> 1), h = warp & 1;
+        const bool active = warp < nitems;
+        const int r0 = ib * 32 + h * 16, c0 = jb * 32;
+        double acc[2][4][2];
+        if (active)   // sum over the 32*(ib-jb) rows k of column block jb, starting at block row jb+1
+            lf_block_mma(acc, 32 * (ib - jb),
+                         [&](int r, int k) { return S + (r0 + r) * LF_LD + c0 + 32 + k; },
+                         [&](int k, int c) { return S + (c0 + 32 + k) * LF_LD + c0 + c; });
+        __syncthreads();
+        if (active) {
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) {
+                    double* p = S + (r0 + mt * 8 + (lane >> 2)) * LF_LD + c0 + nt * 8 + (lane & 3) * 2;
+                    p[0] = acc[mt][nt][0];
+                    p[1] = acc[mt][nt][1];
+                }
+        }
+        __syncthreads();
+        if (active)
+            lf_block_mma(acc, 32,
+                         [&](int r, int k) { return S + (r0 + r) * LF_LD + c0 + k; },
+                         [&](int k, int c) { return S + (c0 + k) * LF_LD + c0 + c; });
+        __syncthreads();
+        if (active) {
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) {
+                    double* p = S + (r0 + mt * 8 + (lane >> 2)) * LF_LD + c0 + nt * 8 + (lane & 3) * 2;
+                    p[0] = -acc[mt][nt][0];
+                    p[1] = -acc[mt][nt][1];
+                }
+        }
+        __syncthreads();
+    }
+    LF_STAMP(15);
+    double* Lig = Linv + base;
+    double* Ltg = Linvt + base;
+    for (int e = tid; e < 128 * 128; e += LF_THREADS) {
+        const int i = e >> 7, k = e & 127;
+        Lig[(size_t)i * ld + k] = (k <= i) ? S[i * LF_LD + k] : 0.0;
+        Ltg[(size_t)i * ld + k] = (k >= i) ? S[k * LF_LD + i] : 0.0;
+    }
+    LF_STAMP(16);
+}
+
+}  // namespace hdbo
