@@ -24,9 +24,7 @@
 
 namespace hdbo {
 
-constexpr int BK = 16;
-constexpr int STAGES = 3;
-constexpr int SLD = BK + 4;                  // smem row stride (doubles)
+constexpr int BK = 16;                       // k-block of the default configurations (and the unit of every kblocks argument)
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -44,9 +42,12 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-template <int TM_, int TN_, int WM_, int WN_>
+template <int TM_, int TN_, int WM_, int WN_, int BK_ = 16, int STAGES_ = 3>
 struct GemmT {
     static constexpr int TM = TM_, TN = TN_, WM = WM_, WN = WN_;
+    static constexpr int BK = BK_, STAGES = STAGES_;
+    static constexpr int SLD = BK + 4;           // smem row stride (doubles), = 4 mod 16: conflict-free fragment reads
+    static constexpr int CH = BK / 2;            // 16-byte chunks per slab row
     static constexpr int THREADS = 32 * WM * WN;
     static constexpr int MT = TM / (8 * WM);     // DMMA tiles per warp along M
     static constexpr int NT = TN / (8 * WN);     // DMMA tiles per warp along N
@@ -74,8 +75,8 @@ struct GemmT {
     template <int ROWS>
     static __device__ __forceinline__ void load_slab(double* s, const double* __restrict__ g, int ld, int kb, int tid) {
 #pragma unroll
-        for (int c = tid; c < ROWS * 8; c += THREADS) {
-            int row = c >> 3, ch = c & 7;
+        for (int q = 0; q < ROWS * CH / THREADS; q++) {
+            const int c = tid + q * THREADS, row = c / CH, ch = c % CH;
             cp_async16(s + row * SLD + ch * 2, g + (size_t)row * ld + (size_t)kb * BK + ch * 2);
         }
     }
@@ -99,32 +100,50 @@ struct GemmT {
         const int frag_off_a = (wm * (TM / WM) + (lane >> 2)) * SLD + (lane & 3);
         const int frag_off_b = (wn * (TN / WN) + (lane >> 2)) * SLD + (lane & 3);
         int slot = 0;
+        constexpr int KS = BK / 4;                       // k4 steps per k-block
+        constexpr int CPT_A = TM * CH / THREADS;         // 16-byte chunks per thread per k-block, A and B
+        constexpr int CPT_B = TN * CH / THREADS;
+        static_assert(TM * CH % THREADS == 0 && TN * CH % THREADS == 0, "slab chunks must divide evenly over the threads");
         for (int it = 0; it < nkb; it++) {
             cp_async_wait<STAGES - 2>();
             __syncthreads();
-            {
-                int nx = it + STAGES - 1;
-                int nslot = slot + STAGES - 1; if (nslot >= STAGES) nslot -= STAGES;
-                if (nx < nkb) {
-                    load_slab<TM>(sA + nslot * A_ELEMS, gA, lda, kb_begin + nx, tid);
-                    load_slab<TN>(sB + nslot * B_ELEMS, gB, ldb, kb_begin + nx, tid);
-                }
-                cp_async_commit();
-            }
+            // The cp.async for stage it+STAGES-1 are NOT issued here in one burst: measured (tools/dmma_order.cu), a burst of
+            // 8 LDGSTS per thread right after the barrier costs 10 % of DMMA throughput (32.4 vs 36.0 TFLOP/s) because all
+            // warps queue on the LSU while the tensor pipe drains.  They are spread over the k4 steps, behind the LDS.
+            const int nx = it + STAGES - 1;
+            int nslot = slot + STAGES - 1; if (nslot >= STAGES) nslot -= STAGES;
+            const bool do_load = nx < nkb;
+            double* nA = sA + nslot * A_ELEMS;
+            double* nB = sB + nslot * B_ELEMS;
             const double* a_s = sA + slot * A_ELEMS + frag_off_a;
             const double* b_s = sB + slot * B_ELEMS + frag_off_b;
 #pragma unroll
-            for (int k4 = 0; k4 < BK / 4; k4++) {
+            for (int k4 = 0; k4 < KS; k4++) {
                 double a[MT], b[NT];
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) a[mt] = a_s[mt * 8 * SLD + k4 * 4];
 #pragma unroll
                 for (int nt = 0; nt < NT; nt++) b[nt] = b_s[nt * 8 * SLD + k4 * 4];
+                if (do_load) {
+#pragma unroll
+                    for (int q = 0; q < CPT_A; q++)
+                        if (q * KS / CPT_A == k4) {
+                            const int c = tid + q * THREADS, row = c / CH, ch = c % CH;
+                            cp_async16(nA + row * SLD + ch * 2, gA + (size_t)row * lda + (size_t)(kb_begin + nx) * BK + ch * 2);
+                        }
+#pragma unroll
+                    for (int q = 0; q < CPT_B; q++)
+                        if (q * KS / CPT_B == k4) {
+                            const int c = tid + q * THREADS, row = c / CH, ch = c % CH;
+                            cp_async16(nB + row * SLD + ch * 2, gB + (size_t)row * ldb + (size_t)(kb_begin + nx) * BK + ch * 2);
+                        }
+                }
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++)
 #pragma unroll
                     for (int nt = 0; nt < NT; nt++) dmma884(acc.v[mt][nt][0], acc.v[mt][nt][1], a[mt], b[nt]);
             }
+            cp_async_commit();
             slot = (slot + 1 == STAGES) ? 0 : slot + 1;
         }
         cp_async_wait<0>();

@@ -222,12 +222,16 @@ cudaError_t launch_sym_build(const SymBuildParams& p, int batch, cudaStream_t st
 // V = K* L^-T : V[c,i] = sum_{j<=i} K*[c,j] Linv[i,j].  Column tile bn only needs k-tiles <= bn (n^2 flops per candidate,
 // not 2n^2).  Heavy column tiles are scheduled first (blockIdx.y = 0 -> last column tile).  Epilogue: per-row sum of
 // squares over this tile's 128 columns -> varpart[bn][row]; V itself is stored only for the gradient path.
+// Mainloop configuration: same 2x4 warp grid / fragment layout as G128, but 32-wide k-blocks (3 x 72 KB ring = 221 KB):
+// half the barriers; measured best of the variants in tools/var_bench.cu (35.0 vs 34.5 TFLOP/s for BK = 16).
+using GVAR = GemmT<128, 128, 2, 4, 32, 3>;
 __global__ void __launch_bounds__(NTHREADS, 1) k_var(VarParams p) {
     extern __shared__ __align__(16) double smem[];
     const int bm = blockIdx.x, bn = p.ntiles - 1 - blockIdx.y, b = blockIdx.z;
-    Frag acc; acc.zero();
-    gemm_nt_mainloop(p.Kstar + b * p.bsK + (size_t)bm * BM * p.ldk, p.ldk, p.Linv + b * p.bsL + (size_t)bn * BN * p.ldl,
-                     p.ldl, 0, (bn + 1) * KB_PER_TILE, smem, acc);
+    GVAR::Frag gacc; gacc.zero();
+    GVAR::mainloop(p.Kstar + b * p.bsK + (size_t)bm * BM * p.ldk, p.ldk, p.Linv + b * p.bsL + (size_t)bn * BN * p.ldl,
+                   p.ldl, 0, (bn + 1) * GVAR::KB_PER_TN, smem, gacc);
+    auto& acc = gacc;
     double rowval[8];
     double* V = p.V ? p.V + b * p.bsV : nullptr;
 #pragma unroll
@@ -250,12 +254,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_var(VarParams p) {
 cudaError_t launch_var(const VarParams& p, int batch, cudaStream_t stream) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_var, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_var, cudaFuncAttributeMaxDynamicSharedMemorySize, GVAR::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
     dim3 grid(p.mtiles, p.ntiles, batch);
-    k_var<<<grid, NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
+    k_var<<<grid, NTHREADS, GVAR::SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
 }
 
