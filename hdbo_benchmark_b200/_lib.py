@@ -59,6 +59,7 @@ _SIGNATURES = {
     "hdbo_dgemm_nt": (C.c_int, [_dp, C.c_int64, _dp, C.c_int64, _dp, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                 C.c_double, C.c_double, C.c_int, C.c_int, _dp]),
     "hdbo_cdist": (C.c_int, [_dp, C.c_int64, C.c_int, C.c_int, _dp, _dp, _dp, _dp]),
+    "hdbo_test_math": (C.c_int, [_dp, C.c_int64, _dp, _dp, _dp]),
     "hdbo_profile_enable": (C.c_int, [C.c_int]),
     "hdbo_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "hdbo_fp64_peak_probe": (C.c_int, [_dp, C.c_int, C.c_int, C.POINTER(C.c_double), _dp]),

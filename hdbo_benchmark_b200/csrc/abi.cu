@@ -206,6 +206,13 @@ extern "C" int hdbo_acq_elementwise(const double* mean, const double* var, int64
     return 0;
 }
 
+extern "C" int hdbo_test_math(const double* x, int64_t n, double* sqrt_out, double* exp_out, void* stream_) {
+    if (!x) return -1;
+    if (n < 0) return -2;
+    TRY_CUDA(launch_test_math(x, n, sqrt_out, exp_out, (cudaStream_t)stream_));
+    return 0;
+}
+
 extern "C" int hdbo_argmax(const double* v, int64_t m, void* work, double* out_val, int64_t* out_idx, void* stream_) {
     if (!v || m <= 0) return -1;
     if (!work) return -3;

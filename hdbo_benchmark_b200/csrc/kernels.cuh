@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "../../include/hdbo_b200.h"
+#include "fast_math.cuh"
 
 namespace hdbo {
 
@@ -36,14 +37,15 @@ struct GemmParams {
 
 // kernel value k(r^2) and derivative dk/dr^2 for unit outputscale.  kind: 0 Matern-5/2, 1 RBF.
 __device__ __forceinline__ void kernel_eval(int kind, double r2, double& k, double& dk) {
+    // branch-free sqrt / exp (fast_math.cuh) so that the unrolled epilogues interleave their independent elements
     if (kind == 0) {
-        double r = sqrt(fmax(r2, 1e-30));
-        double e = exp(-SQRT5 * r);
+        double r = sqrt_pos(fmin(fmax(r2, 1e-30), 1e30));
+        double e = exp_nonpos(-SQRT5 * r);
         double t = 1.0 + SQRT5 * r;
         k = (t + (5.0 / 3.0) * r * r) * e;
         dk = -(5.0 / 6.0) * t * e;
     } else {
-        double e = exp(-0.5 * r2);
+        double e = exp_nonpos(-0.5 * r2);
         k = e;
         dk = -0.5 * e;
     }

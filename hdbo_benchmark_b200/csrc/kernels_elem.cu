@@ -238,4 +238,17 @@ cudaError_t launch_argmax(const double* v, long long m, void* work, double* out_
     return cudaGetLastError();
 }
 
+// test hook: the branch-free sqrt / exp of fast_math.cuh evaluated on arrays (tests compare with the library functions)
+__global__ void k_test_math(const double* __restrict__ x, long long n, double* __restrict__ s, double* __restrict__ e) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (s) s[i] = sqrt_pos(fmin(fmax(x[i], 1e-30), 1e30));
+    if (e) e[i] = exp_nonpos(-fabs(x[i]));
+}
+cudaError_t launch_test_math(const double* x, long long n, double* s, double* e, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_test_math<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n, s, e);
+    return cudaGetLastError();
+}
+
 }  // namespace hdbo

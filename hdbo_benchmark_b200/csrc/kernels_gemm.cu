@@ -103,6 +103,7 @@ cudaError_t launch_gemm_nt(const GemmParams& p, int batch, cudaStream_t stream) 
 // --------------------------------------------------------------------------------------------------------------
 // K*(Z, X) tile: r2 = |z|^2 + |x|^2 - 2 z.x (clamped at 0), k(r2) * outputscale, masked beyond n; plus the partial
 // dot with alpha over this tile's 128 columns (posterior mean), written to meanpart[bn][row].
+template <int KIND>
 __global__ void __launch_bounds__(NTHREADS, 1) k_cross(CrossParams p) {
     extern __shared__ __align__(16) double smem[];
     const int bm = blockIdx.x, bn = blockIdx.y, b = blockIdx.z;
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cross(CrossParams p) {
             for (int e = 0; e < 2; e++) {
                 double r2 = fmax((znr + xnv[nt][e]) - 2.0 * acc.v[mt][nt][e], 0.0);
                 double k, dk;
-                kernel_eval(p.kind, r2, k, dk);
+                kernel_eval(KIND, r2, k, dk);
                 bool valid = ((bn * BN + c + e) < p.n) && ((bm * BM + r) < p.m);   // padding rows / columns are exact zeros
                 kv[e] = valid ? os * k : 0.0;
                 dv[e] = valid ? os * dk : 0.0;
@@ -153,12 +154,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cross(CrossParams p) {
 cudaError_t launch_cross(const CrossParams& p, int batch, cudaStream_t stream) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_cross, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_cross<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cross<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
     dim3 grid(p.mtiles, p.ntiles, batch);
-    k_cross<<<grid, NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
+    if (p.kind == 0) k_cross<0><<<grid, NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
+    else k_cross<1><<<grid, NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
 }
 

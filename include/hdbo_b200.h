@@ -141,6 +141,10 @@ int hdbo_dgemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, do
  * Xs/xn/work as produced internally: caller passes scratch Xs [n_pad][d_pad], xn [n_pad], D_pad [n_pad][n_pad]. */
 int hdbo_cdist(const double* X, int64_t ldx, int n, int d, double* Xs, double* xn, double* D_pad, void* stream);
 
+/* Test hook: sqrt_out[i] = sqrt(clamp(x[i], 1e-30, 1e30)), exp_out[i] = exp(-|x[i]|) computed with the branch-free device
+ * routines the kernel epilogues use (csrc/fast_math.cuh); either output may be NULL. */
+int hdbo_test_math(const double* x, int64_t n, double* sqrt_out, double* exp_out, void* stream);
+
 /* Opt-in profiling for bench.py: while enabled, CUDA events are recorded on the caller's stream around the two GEMM
  * phases of the posterior (class 0 = cross-kernel build, class 1 = variance contraction).  collect() synchronises on
  * the recorded events, returns total milliseconds and launch counts per class (host arrays of 2) and resets.

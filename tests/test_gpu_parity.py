@@ -150,6 +150,28 @@ def test_mll_value_and_gradient_match_oracle(cuda_device, n, d, kind, ls_mode):
     assert abs(grad[d + 2] - g_mu) < REL * max(abs(float(g_mu)), 1e-3)
 
 
+def test_branch_free_sqrt_exp_match_the_library(cuda_device):
+    """csrc/fast_math.cuh (used by every distance -> kernel epilogue) against torch's float64 sqrt / exp."""
+    from hdbo_benchmark_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(0)
+    x = torch.cat([
+        torch.rand(100000, generator=g, dtype=torch.float64) * 50.0,
+        10.0 ** (torch.rand(50000, generator=g, dtype=torch.float64) * 60.0 - 30.0),   # 1e-30 .. 1e30
+        torch.tensor([0.0, 1e-30, 1.0, 2.0, 4.0, 708.0, 739.9, 745.0, 1e4, 1e30], dtype=torch.float64),
+    ]).to(cuda_device)
+    s = torch.empty_like(x)
+    e = torch.empty_like(x)
+    _lib.check(lib.hdbo_test_math(x.data_ptr(), x.numel(), s.data_ptr(), e.data_ptr(), torch.cuda.current_stream().cuda_stream), "math")
+    want_s = x.clamp(1e-30, 1e30).sqrt()
+    assert float(((s - want_s).abs() / want_s).max()) < 4e-16
+    want_e = torch.exp(-x)
+    big = want_e > 1e-300
+    assert float(((e - want_e).abs() / want_e)[big].max()) < 1e-15
+    assert float(e[~big].abs().max()) < 1e-299 and bool((e >= 0).all())
+
+
 def test_cholesky_failure_reports_info_and_jitter_recovers(cuda_device):
     from hdbo_benchmark_b200.engine import DeviceGP, NotPSDError
 
