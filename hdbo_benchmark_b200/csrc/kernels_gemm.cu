@@ -3,6 +3,8 @@
 //   k_cross      K*(Z, X): scaled-candidate x scaled-train GEMM + distance->kernel epilogue + partial K* alpha  (A1, A4)
 //   k_sym_build  K(X, X) + noise I (lower tiles) and the squared-distance matrix                                 (A1, A2)
 //   k_var        V = K* L^-T with the triangular k-range, row sum-of-squares epilogue                            (A4)
+#include <cstdlib>
+
 #include "gemm_core.cuh"
 #include "kernels.cuh"
 
@@ -95,8 +97,10 @@ static cudaError_t launch_gemm_cfg(GemmParams p, int batch, cudaStream_t stream)
 // tiles (4x / 16x more CTAs, each proportionally shorter) until the grid covers the 148 SMs.
 cudaError_t launch_gemm_nt(const GemmParams& p, int batch, cudaStream_t stream) {
     const long long t128 = (p.lower_only ? (long long)p.mtiles * (p.mtiles + 1) / 2 : (long long)p.mtiles * p.ntiles) * batch;
-    if (t128 >= 100) return launch_gemm_cfg<G128>(p, batch, stream);
-    if (t128 >= 25) return launch_gemm_cfg<G64>(p, batch, stream);
+    static const long long t128_min = [] { const char* e = getenv("HDBO_GEMM_T128_MIN"); return e ? atoll(e) : 100LL; }();
+    static const long long t64_min = [] { const char* e = getenv("HDBO_GEMM_T64_MIN"); return e ? atoll(e) : 25LL; }();
+    if (t128 >= t128_min) return launch_gemm_cfg<G128>(p, batch, stream);
+    if (t128 >= t64_min) return launch_gemm_cfg<G64>(p, batch, stream);
     return launch_gemm_cfg<G32>(p, batch, stream);
 }
 
