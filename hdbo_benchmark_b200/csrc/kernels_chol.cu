@@ -15,6 +15,8 @@
 // registers with warp shuffles, panel rows by per-thread substitution, block updates with DMMA from shared memory.
 // A non-positive pivot records info = 1-based global index (first one wins) and continues with a unit pivot so the
 // stream never hangs; the host applies the jitter schedule.
+#include <cstdlib>
+
 #include "gemm_core.cuh"
 #include "kernels.cuh"
 #include "leaf.cuh"
@@ -23,6 +25,8 @@ namespace hdbo {
 
 static cudaError_t launch_leaf(double* Awork, double* L, double* Linv, double* Linvt, int ld, long long bs, int tile,
                                int32_t* info, int batch, cudaStream_t stream) {
+    // A warp-specialised, look-ahead ("pipelined") variant of the leaf was built and measured slower (82-104 us vs 72 us):
+    // with one CTA per SM and each role running its own long unrolled code path the warps thrash the instruction cache.
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(k_leaf_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM_BYTES);

@@ -244,6 +244,8 @@ k_leaf_blocked(double* __restrict__ Awork, double* __restrict__ L, double* __res
     LF_STAMP(15);
     double* Lig = Linv + base;
     double* Ltg = Linvt + base;
+    // (a 32-byte-per-thread vectorised write-out with lanes along the row index was measured slower: the transposed tile
+    //  then costs one 32-byte sector per thread on the store side)
     for (int e = tid; e < 128 * 128; e += LF_THREADS) {
         const int i = e >> 7, k = e & 127;
         Lig[(size_t)i * ld + k] = (k <= i) ? S[i * LF_LD + k] : 0.0;
