@@ -87,8 +87,14 @@ class DeviceGP:
         f64 = dict(dtype=torch.float64, device=self.device)
         ls = torch.as_tensor(lengthscale, **f64).detach().reshape(-1, self.d)
         self.inv_ls.copy_((1.0 / ls).expand(self.batch, self.d))
-        for col, v in enumerate((outputscale, noise, mean, jitter)):
-            self.hyp[:, col] = torch.as_tensor(v, **f64).detach().reshape(-1)
+        vals = (outputscale, noise, mean, jitter)
+        if all(torch.is_tensor(v) and v.is_cuda for v in vals[:3]):   # fit loop: already on the device, one fused write
+            cols = [v.detach().reshape(-1).expand(self.batch) for v in vals[:3]]
+            cols.append(torch.full((self.batch,), float(jitter), **f64))
+            self.hyp.copy_(torch.stack(cols, dim=1))
+        else:
+            host = torch.stack([torch.as_tensor(v, dtype=torch.float64).detach().cpu().reshape(-1).expand(self.batch) for v in vals], dim=1)
+            self.hyp.copy_(host)
         self.fitted = False
 
     # ---- A1 + A2: kernel build, Cholesky, inverse, alpha, logdet ----

@@ -77,11 +77,15 @@ def fit_gpytorch_mll_scipy(mll, options: Optional[Dict] = None, bounds=None):
     def pack():
         return np.concatenate([p.detach().to(torch.float64).cpu().numpy().reshape(-1) for _, p in params])
 
+    dev = params[0][1].device
+
     def unpack(x):
+        # one host->device copy for all parameters, then device-side slices
+        xd = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
         off = 0
         with torch.no_grad():
             for (_, p), sz in zip(params, sizes):
-                p.copy_(torch.from_numpy(x[off:off + sz]).reshape(p.shape).to(p.device))
+                p.copy_(xd[off:off + sz].view_as(p))
                 off += sz
 
     def closure(x):
@@ -94,9 +98,10 @@ def fit_gpytorch_mll_scipy(mll, options: Optional[Dict] = None, bounds=None):
             loss.backward()
         except NotPSDError:
             return float("inf"), np.zeros_like(x)
-        g = np.concatenate([(p.grad if p.grad is not None else torch.zeros_like(p)).detach().cpu().numpy().reshape(-1)
-                            for _, p in params])
-        f = float(loss.item())
+        # one device->host copy (and one sync) for the loss and every gradient
+        packed = torch.cat([loss.detach().reshape(1)] + [(p.grad if p.grad is not None else torch.zeros_like(p)).detach().reshape(-1)
+                                                          for _, p in params]).cpu().numpy()
+        f, g = float(packed[0]), packed[1:].copy()
         if not np.isfinite(f) or not np.all(np.isfinite(g)):
             return float("inf"), np.zeros_like(x)
         return f, g

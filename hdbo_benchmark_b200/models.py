@@ -383,9 +383,12 @@ def mll_gradient(gp: DeviceGP) -> torch.Tensor:
     f64 = dict(dtype=torch.float64, device=gp.device)
     B, npad = gp.batch, gp.n_pad
     dpt = _rup(gp.d, 128)
-    G = torch.empty(B, npad, npad, **f64)
-    XsT = torch.empty(B, dpt, npad, **f64)
-    part = torch.empty(gp.lib.hdbo_mll_grad_part_bytes(C.byref(gp.desc)), dtype=torch.uint8, device=gp.device)
+    scratch = getattr(gp, "_grad_scratch", None)
+    if scratch is None:   # persistent scratch: an L-BFGS fit calls this 20-100 times on the same DeviceGP
+        scratch = gp._grad_scratch = (
+            torch.empty(B, npad, npad, **f64), torch.empty(B, dpt, npad, **f64),
+            torch.empty(gp.lib.hdbo_mll_grad_part_bytes(C.byref(gp.desc)), dtype=torch.uint8, device=gp.device))
+    G, XsT, part = scratch
     grad = torch.empty(B, gp.d + 3, **f64)
     # K^-1 overwrites the Cholesky factor buffer (L itself is no longer needed once L^-1 exists)
     check(gp.lib.hdbo_mll_grad(C.byref(gp.desc), ptr(gp.L), ptr(G), ptr(XsT), ptr(part), ptr(grad), _stream()),

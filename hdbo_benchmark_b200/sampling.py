@@ -8,13 +8,45 @@ from typing import Optional
 import torch
 
 
-def draw_sobol_samples(bounds: torch.Tensor, n: int, q: int, seed: Optional[int] = None) -> torch.Tensor:
+_ENGINES = {}
+_SEEDED_POINTS = {}
+
+
+def _cached(cache: dict, key, make, limit: int = 16):
+    val = cache.get(key)
+    if val is None:
+        if len(cache) >= limit:   # bounded: callers that vary the key every iteration must not grow the cache
+            cache.pop(next(iter(cache)))
+        val = cache[key] = make()
+    return val
+
+
+def _sobol_unit_points(dim: int, n: int, seed: Optional[int], stream: Optional[int]) -> torch.Tensor:
+    """n x dim scrambled-Sobol points in the unit cube (CPU float64).
+
+    Constructing a scrambled SobolEngine costs 60-100 ms at dim >= 128 and `reset()` on a seeded one ~230 ms (measured
+    here; it was half of the wall time of a BO step at d=128), so nothing is rebuilt per call:
+      * seed given    -> the drawn points are cached by (dim, seed, n): identical points every call, as a fresh seeded
+                         engine would give;
+      * stream given  -> one engine per stream id, seeded with it and never reset: reproducible run to run, fresh points
+                         on every call (solver loops);
+      * neither       -> one unseeded engine per dimension that keeps drawing from its sequence."""
+    if stream is not None:
+        eng = _cached(_ENGINES, ("stream", dim, stream), lambda: torch.quasirandom.SobolEngine(dim, scramble=True, seed=stream))
+        return eng.draw(n, dtype=torch.float64)
+    if seed is not None:
+        return _cached(_SEEDED_POINTS, (dim, seed, n),
+                       lambda: torch.quasirandom.SobolEngine(dim, scramble=True, seed=seed).draw(n, dtype=torch.float64), limit=8)
+    eng = _cached(_ENGINES, (dim, None), lambda: torch.quasirandom.SobolEngine(dim, scramble=True))
+    return eng.draw(n, dtype=torch.float64)
+
+
+def draw_sobol_samples(bounds: torch.Tensor, n: int, q: int, seed: Optional[int] = None, stream: Optional[int] = None) -> torch.Tensor:
     """n x q x d scrambled-Sobol points inside `bounds` (2 x d); one (q*d)-dimensional engine as in BoTorch."""
     bounds = torch.as_tensor(bounds)
     d = bounds.shape[-1]
     lower, rng = bounds[0], bounds[1] - bounds[0]
-    eng = torch.quasirandom.SobolEngine(q * d, scramble=True, seed=seed)
-    u = eng.draw(n, dtype=torch.float64).reshape(n, q, d).to(bounds.device)
+    u = _sobol_unit_points(q * d, n, seed, stream).reshape(n, q, d).to(bounds.device)
     return lower.to(torch.float64) + rng.to(torch.float64) * u
 
 

@@ -109,7 +109,7 @@ class VanillaBayesianOptimization(BaseBayesianOptimization):
         acqf = self._instantiate_acquisition_function(model, best_f)
         opts = {"nonnegative": isinstance(acqf, ExpectedImprovement) and not isinstance(acqf, LogExpectedImprovement)}
         if self.seed is not None:
-            opts["seed"] = self.seed + self.iteration
+            opts["sobol_stream"] = self.seed   # one cached scrambled-Sobol sequence per solver: reproducible, fresh points each step
         cand, _ = optimize_acqf(acqf, self.bounds, q=1, num_restarts=self.num_restarts, raw_samples=self.raw_samples, options=opts)
         return cand.detach().cpu().numpy().reshape(1, -1)
 

@@ -81,10 +81,11 @@ def test_priors_match_torch_distributions():
     from hdbo_benchmark_b200 import gp_modules as G
 
     x = torch.tensor([0.3, 1.7, 4.0], dtype=torch.float64)
-    torch.testing.assert_close(G.GammaPrior(3.0, 6.0).log_prob(x), torch.distributions.Gamma(3.0, 6.0).log_prob(x))
-    torch.testing.assert_close(G.LogNormalPrior(1.2, 0.8).log_prob(x), torch.distributions.LogNormal(1.2, 0.8).log_prob(x))
-    torch.testing.assert_close(G.NormalPrior(0.2, 1.5).log_prob(x), torch.distributions.Normal(0.2, 1.5).log_prob(x))
-    torch.testing.assert_close(G.HalfCauchyPrior(0.1).log_prob(x), torch.distributions.HalfCauchy(0.1).log_prob(x))
+    f = lambda v: torch.tensor(v, dtype=torch.float64)   # independent of the process-wide default dtype
+    torch.testing.assert_close(G.GammaPrior(3.0, 6.0).log_prob(x), torch.distributions.Gamma(f(3.0), f(6.0)).log_prob(x))
+    torch.testing.assert_close(G.LogNormalPrior(1.2, 0.8).log_prob(x), torch.distributions.LogNormal(f(1.2), f(0.8)).log_prob(x))
+    torch.testing.assert_close(G.NormalPrior(0.2, 1.5).log_prob(x), torch.distributions.Normal(f(0.2), f(1.5)).log_prob(x))
+    torch.testing.assert_close(G.HalfCauchyPrior(0.1).log_prob(x), torch.distributions.HalfCauchy(f(0.1)).log_prob(x))
     assert abs(float(G.LogNormalPrior(1.0, 0.5).mode) - math.exp(1.0 - 0.25)) < 1e-12
     assert abs(float(G.GammaPrior(3.0, 6.0).mode) - 2.0 / 6.0) < 1e-12
 
