@@ -73,7 +73,7 @@ def test_float32_callers_and_host_tensors(cuda_device):
     X, y, ls, *_ = O.synthetic_problem(60, 6)
     model = SingleTaskGP(X.float(), y.float().unsqueeze(-1))
     model.eval()
-    Z = torch.rand(7, 1, 6)
+    Z = torch.rand(7, 1, 6, dtype=torch.float32)   # explicit: other test modules change the process-wide default dtype
     post = model.posterior(Z)
     assert post.mean.dtype == torch.float32 and post.mean.device.type == "cpu" and post.mean.shape == (7, 1, 1)
     acq = A.LogExpectedImprovement(model, best_f=float(y.max()))(Z)
