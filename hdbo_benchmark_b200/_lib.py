@@ -46,6 +46,11 @@ _SIGNATURES = {
     "hdbo_posterior_workspace_bytes": (C.c_size_t, [C.POINTER(HdboGp), C.c_int64, C.c_int]),
     "hdbo_posterior_acq": (C.c_int, [C.POINTER(HdboGp), _dp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_double,
                                      _dp, _dp, _dp, C.c_int64, _dp, C.c_size_t, _dp]),
+    "hdbo_i8_state_bytes": (C.c_size_t, [C.POINTER(HdboGp)]),
+    "hdbo_gp_slice_linv": (C.c_int, [C.POINTER(HdboGp), _dp, _dp]),
+    "hdbo_posterior_acq_i8": (C.c_int, [C.POINTER(HdboGp), _dp, _dp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_double,
+                                        _dp, _dp, _dp, C.c_int64, _dp, C.c_size_t, _dp]),
+    "hdbo_i8_state_flag": (C.c_void_p, [C.POINTER(HdboGp), _dp]),
     "hdbo_posterior_fwd": (C.c_int, [C.POINTER(HdboGp), _dp, C.c_int64, C.c_int64, C.c_int, _dp, _dp, C.c_int64,
                                      _dp, C.c_size_t, _dp]),
     "hdbo_posterior_joint_cov": (C.c_int, [C.POINTER(HdboGp), C.c_int64, C.c_int, C.c_int, _dp, C.c_int64, _dp,

@@ -4,6 +4,7 @@
 #include "kernels.cuh"
 #include "elem.cuh"
 #include "grad.cuh"
+#include "i8.cuh"
 
 #include <vector>
 
@@ -62,7 +63,7 @@ extern "C" int hdbo_gp_fit_downdated(const hdbo_gp* gp, int need_r2, const doubl
 // ------------------------------------------------------------------------------------------------------------
 // ---- opt-in profiling: CUDA events around the GEMM phases of the posterior, recorded on the caller's stream ----
 namespace {
-constexpr int PROF_CLASSES = 2;   // 0 = cross-kernel build (k_cross), 1 = variance contraction (k_var)
+constexpr int PROF_CLASSES = 2;   // 0 = cross-kernel build (k_cross), 1 = variance contraction (k_var / k_var_i8)
 struct Prof {
     bool on = false;
     std::vector<cudaEvent_t> ev[PROF_CLASSES];   // pairs: start, stop
@@ -114,7 +115,7 @@ PostWs carve(const hdbo_gp* gp, int64_t rows, int keep, void* base) {
     w.zn = take(B * rows);
     w.Kstar = take(B * rows * np);
     w.meanpart = take(B * nt * rows);
-    w.varpart = take(B * nt * rows);
+    w.varpart = take(B * 2 * nt * rows);   // the int8 variance kernel works on 64-column tiles: twice the partials
     if (keep) {
         w.DK = take(B * rows * np);
         w.V = take(B * rows * np);
@@ -125,9 +126,27 @@ PostWs carve(const hdbo_gp* gp, int64_t rows, int keep, void* base) {
     return w;
 }
 
-// scale -> cross -> var for `mc` candidates starting at Z (rows_alloc = row capacity of the workspace arrays)
+// state of the exact int8 variance path, carved from the caller's buffer (hdbo_i8_state_bytes)
+struct I8State {
+    int8_t* digits;   // [I8_S][n_pad][n_pad] digit planes of the row-scaled L^-1
+    double* scale;    // [n_pad] power-of-two row scales
+    int32_t* flag;    // barrier-timeout flag of k_var_i8 (0 = healthy)
+    size_t bytes;
+};
+I8State carve_i8(const hdbo_gp* gp, void* base) {
+    const size_t np = gp->n_pad;
+    I8State s{};
+    s.digits = (int8_t*)base;
+    s.scale = (double*)((char*)base + (size_t)I8_S * np * np);
+    s.flag = (int32_t*)((char*)s.scale + np * sizeof(double));
+    s.bytes = (size_t)I8_S * np * np + np * sizeof(double) + 16;
+    return s;
+}
+
+// scale -> cross -> var for `mc` candidates starting at Z (rows_alloc = row capacity of the workspace arrays).
+// i8 != nullptr: K* leaves k_cross as int8 digit planes (in the Kstar slab) and the variance runs on tcgen05 (kernels_i8.cu).
 cudaError_t posterior_chunk(const hdbo_gp* gp, const PostWs& w, int64_t rows_alloc, const double* Z, int64_t ldz,
-                            int64_t mc, int keep, cudaStream_t st) {
+                            int64_t mc, int keep, cudaStream_t st, const I8State* i8 = nullptr) {
     const int np = gp->n_pad, dp = gp->d_pad, B = gp->batch;
     const int rp = (int)rup(mc, 128), mt = rp / 128, nt = np / 128;
     cudaError_t e;
@@ -141,15 +160,22 @@ cudaError_t posterior_chunk(const hdbo_gp* gp, const PostWs& w, int64_t rows_all
     c.bsZ = (long long)rows_alloc * dp; c.bsX = (long long)np * dp; c.bszn = rows_alloc; c.bsxn = np; c.bsalpha = np;
     c.bsK = (long long)rows_alloc * np; c.bsmp = (long long)nt * rows_alloc;
     c.m = (int)mc; c.n = gp->n; c.mtiles = mt; c.ntiles = nt; c.kblocks = dp / BK; c.kind = gp->kind;
+    if (i8) { c.Adig = reinterpret_cast<int8_t*>(w.Kstar); c.dig_plane = (long long)rows_alloc * np; }
     prof_mark(0, st);
     e = launch_cross(c, B, st);
     prof_mark(0, st);
     if (e != cudaSuccess) return e;
+    if (i8) {
+        prof_mark(1, st);
+        e = launch_var_i8(c.Adig, (int)rows_alloc, rp, i8->digits, i8->scale, gp->hyp, np, w.varpart, i8->flag, st);
+        prof_mark(1, st);
+        return e;
+    }
     VarParams v{};
     v.Kstar = w.Kstar; v.Linv = gp->Linv; v.V = keep ? w.V : nullptr; v.varpart = w.varpart;
     v.ldk = np; v.ldl = np; v.ldv = np;
     v.bsK = (long long)rows_alloc * np; v.bsL = (long long)np * np; v.bsV = (long long)rows_alloc * np;
-    v.bsvp = (long long)nt * rows_alloc; v.mtiles = mt; v.ntiles = nt;
+    v.bsvp = 2LL * nt * rows_alloc; v.mtiles = mt; v.ntiles = nt;
     prof_mark(1, st);
     e = launch_var(v, B, st);
     prof_mark(1, st);
@@ -167,9 +193,9 @@ extern "C" double* hdbo_posterior_workspace_V(const hdbo_gp* gp, int64_t rows, v
     return carve(gp, rows, 1, workspace).V;
 }
 
-extern "C" int hdbo_posterior_acq(const hdbo_gp* gp, const double* Z, int64_t ldz, int64_t m, int observation_noise,
-                                  int acq_kind, double acq_param, double* mean, double* var, double* acq, int64_t bso,
-                                  void* workspace, size_t workspace_bytes, void* stream_) {
+static int posterior_acq_impl(const hdbo_gp* gp, const I8State* i8, const double* Z, int64_t ldz, int64_t m, int observation_noise,
+                              int acq_kind, double acq_param, double* mean, double* var, double* acq, int64_t bso,
+                              void* workspace, size_t workspace_bytes, void* stream_) {
     if (int e = check_gp(gp)) return e;
     if (m < 0) return -4;
     if (m == 0) return 0;   /* empty pool: nothing to do (Z may be NULL) */
@@ -189,12 +215,53 @@ extern "C" int hdbo_posterior_acq(const hdbo_gp* gp, const double* Z, int64_t ld
     const int nt = gp->n_pad / 128, B = gp->batch;
     for (int64_t off = 0; off < m; off += rows) {
         const int64_t mc = (m - off < rows) ? (m - off) : rows;
-        TRY_CUDA(posterior_chunk(gp, w, rows, Z + off * ldz, ldz, mc, 0, st));
-        TRY_CUDA(launch_finalize_acq(w.meanpart, w.varpart, (long long)nt * rows, nt, (int)rup(mc, 128), (int)mc, gp->hyp,
+        TRY_CUDA(posterior_chunk(gp, w, rows, Z + off * ldz, ldz, mc, 0, st, i8));
+        TRY_CUDA(launch_finalize_acq(w.meanpart, w.varpart, (long long)nt * rows, nt, i8 ? 2 * nt : nt, (int)rup(mc, 128), (int)mc, gp->hyp,
                                      observation_noise, acq_kind, acq_param, mean ? mean + off : nullptr,
                                      var ? var + off : nullptr, (acq && acq_kind >= 0) ? acq + off : nullptr, bso, B, st));
     }
     return 0;
+}
+
+extern "C" int hdbo_posterior_acq(const hdbo_gp* gp, const double* Z, int64_t ldz, int64_t m, int observation_noise,
+                                  int acq_kind, double acq_param, double* mean, double* var, double* acq, int64_t bso,
+                                  void* workspace, size_t workspace_bytes, void* stream_) {
+    return posterior_acq_impl(gp, nullptr, Z, ldz, m, observation_noise, acq_kind, acq_param, mean, var, acq, bso, workspace,
+                              workspace_bytes, stream_);
+}
+
+// ---- exact int8 (tcgen05) variance path: digit planes of L^-1 once per fit, then the pool evaluation ----
+extern "C" size_t hdbo_i8_state_bytes(const hdbo_gp* gp) {
+    if (check_gp(gp) || gp->batch != 1) return 0;
+    return carve_i8(gp, nullptr).bytes;
+}
+
+extern "C" int32_t* hdbo_i8_state_flag(const hdbo_gp* gp, void* i8_state) {
+    if (check_gp(gp) || gp->batch != 1 || !i8_state) return nullptr;
+    return carve_i8(gp, i8_state).flag;
+}
+
+extern "C" int hdbo_gp_slice_linv(const hdbo_gp* gp, void* i8_state, void* stream_) {
+    if (int e = check_gp(gp)) return e;
+    if (gp->batch != 1) return -1;
+    if (!i8_state || ((uintptr_t)i8_state & 127)) return -2;
+    cudaStream_t st = (cudaStream_t)stream_;
+    I8State s = carve_i8(gp, i8_state);
+    TRY_CUDA(cudaMemsetAsync(s.flag, 0, 16, st));
+    TRY_CUDA(launch_slice_linv(gp->Linv, gp->n_pad, gp->n_pad, s.digits, s.scale, st));
+    return 0;
+}
+
+extern "C" int hdbo_posterior_acq_i8(const hdbo_gp* gp, void* i8_state, const double* Z, int64_t ldz, int64_t m,
+                                     int observation_noise, int acq_kind, double acq_param, double* mean, double* var, double* acq,
+                                     int64_t bso, void* workspace, size_t workspace_bytes, void* stream_) {
+    if (int e = check_gp(gp)) return e;
+    if (gp->batch != 1) return -1;
+    if (!i8_state || ((uintptr_t)i8_state & 127)) return -2;
+    if (workspace && ((uintptr_t)workspace & 127)) return -13;
+    I8State s = carve_i8(gp, i8_state);
+    return posterior_acq_impl(gp, &s, Z, ldz, m, observation_noise, acq_kind, acq_param, mean, var, acq, bso, workspace,
+                              workspace_bytes, stream_);
 }
 
 extern "C" int hdbo_acq_elementwise(const double* mean, const double* var, int64_t m, int acq_kind, double acq_param,
@@ -266,7 +333,7 @@ extern "C" int hdbo_posterior_fwd(const hdbo_gp* gp, const double* Z, int64_t ld
     PostWs w = carve(gp, rows, 1, workspace);
     const int nt = gp->n_pad / 128;
     TRY_CUDA(posterior_chunk(gp, w, rows, Z, ldz, m, 1, st));
-    TRY_CUDA(launch_finalize_acq(w.meanpart, w.varpart, (long long)nt * rows, nt, (int)rows, (int)m, gp->hyp,
+    TRY_CUDA(launch_finalize_acq(w.meanpart, w.varpart, (long long)nt * rows, nt, nt, (int)rows, (int)m, gp->hyp,
                                  observation_noise, HDBO_ACQ_NONE, 0.0, mean, var, nullptr, bso, gp->batch, st));
     return 0;
 }

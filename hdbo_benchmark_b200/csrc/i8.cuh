@@ -1,0 +1,31 @@
+// Digit slicing shared by the producers (k_cross epilogue, L^-1 slicing) and the consumer (k_var_i8) of the exact int8 path.
+// A value x in [-1, 1] is held as a 49-bit fixed-point integer X = rint(x 2^48) and split into S = 7 balanced base-128
+// digits d_t in [-64, 64]:  x = sum_t d_t 2^-(7t+6).  Products of two digit planes with s + t = g share the weight 2^-(7g+12).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hdbo {
+
+constexpr int I8_S = 7;
+constexpr int I8_FRAC_BITS = 48;
+
+__device__ __forceinline__ void i8_digits(long long x, signed char (&d)[I8_S]) {
+#pragma unroll
+    for (int t = I8_S - 1; t >= 1; t--) {
+        const int r = (int)((x + 64) & 127) - 64;   // balanced remainder in [-64, 63]
+        d[t] = (signed char)r;
+        x = (x - r) >> 7;
+    }
+    d[0] = (signed char)x;                          // |x| <= 64 for |value| <= 1
+}
+
+__device__ __forceinline__ double i8_group_weight(int g) {   // 2^-(7g+12)
+    return __longlong_as_double((long long)(1023 - (7 * g + 12)) << 52);
+}
+
+cudaError_t launch_slice_linv(const double* Linv, int ld, int n_pad, int8_t* planes, double* scale, cudaStream_t st);
+cudaError_t launch_var_i8(const int8_t* Adig, int rows_alloc, int rows_pad, const int8_t* Bdig, const double* colscale, const double* hyp,
+                          int n_pad, double* varpart, int* flag, cudaStream_t st);
+
+}  // namespace hdbo

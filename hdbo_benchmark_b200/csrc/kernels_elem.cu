@@ -122,17 +122,15 @@ cudaError_t launch_fit_scalars(const double* L, int ld, long long bsL, const dou
 // Per candidate: mean = m0 + sum_t meanpart[t][i]; var = outputscale - sum_t varpart[t][i] (+ noise);
 // acquisition value (A5) and, if requested, d acq / d mean and d acq / d var.
 __global__ void k_finalize_acq(const double* __restrict__ meanpart, const double* __restrict__ varpart, long long bsp,
-                               int ntiles, int rows_pad, int m, const double* __restrict__ hyp, int observation_noise,
+                               int ntiles, int ntiles_var, int rows_pad, int m, const double* __restrict__ hyp, int observation_noise,
                                int acq_kind, double acq_param, double* __restrict__ mean_out,
                                double* __restrict__ var_out, double* __restrict__ acq_out, long long bso) {
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     double sm = 0.0, sv = 0.0;
-    for (int t = 0; t < ntiles; t++) {
-        sm += meanpart[b * bsp + (size_t)t * rows_pad + i];
-        sv += varpart[b * bsp + (size_t)t * rows_pad + i];
-    }
+    for (int t = 0; t < ntiles; t++) sm += meanpart[b * bsp + (size_t)t * rows_pad + i];
+    for (int t = 0; t < ntiles_var; t++) sv += varpart[b * 2 * bsp + (size_t)t * rows_pad + i];
     const double os = hyp[b * 4 + 0], noise = hyp[b * 4 + 1], m0 = hyp[b * 4 + 2];
     const double mean = m0 + sm;
     double var = os - sv;
@@ -146,12 +144,12 @@ __global__ void k_finalize_acq(const double* __restrict__ meanpart, const double
     }
 }
 
-cudaError_t launch_finalize_acq(const double* meanpart, const double* varpart, long long bsp, int ntiles, int rows_pad,
+cudaError_t launch_finalize_acq(const double* meanpart, const double* varpart, long long bsp, int ntiles, int ntiles_var, int rows_pad,
                                 int m, const double* hyp, int observation_noise, int acq_kind, double acq_param,
                                 double* mean_out, double* var_out, double* acq_out, long long bso, int batch,
                                 cudaStream_t stream) {
     dim3 grid((m + 255) / 256, batch);
-    k_finalize_acq<<<grid, 256, 0, stream>>>(meanpart, varpart, bsp, ntiles, rows_pad, m, hyp, observation_noise,
+    k_finalize_acq<<<grid, 256, 0, stream>>>(meanpart, varpart, bsp, ntiles, ntiles_var, rows_pad, m, hyp, observation_noise,
                                             acq_kind, acq_param, mean_out, var_out, acq_out, bso);
     return cudaGetLastError();
 }

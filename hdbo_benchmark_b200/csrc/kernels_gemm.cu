@@ -7,6 +7,7 @@
 
 #include "gemm_core.cuh"
 #include "kernels.cuh"
+#include "i8.cuh"
 
 namespace hdbo {
 
@@ -108,7 +109,13 @@ cudaError_t launch_gemm_nt(const GemmParams& p, int batch, cudaStream_t stream) 
 // --------------------------------------------------------------------------------------------------------------
 // K*(Z, X) tile: r2 = |z|^2 + |x|^2 - 2 z.x (clamped at 0), k(r2) * outputscale, masked beyond n; plus the partial
 // dot with alpha over this tile's 128 columns (posterior mean), written to meanpart[bn][row].
-template <int KIND>
+// DIG: instead of the FP64 K* slab, emit the 7 int8 digit planes of K*/outputscale for the tcgen05 variance kernel
+// (kernels_i8.cu).  The digits come from one FP64 multiply + integer shifts/masks per element (no extra FP64 pipe work) and are
+// staged through shared memory (row stride 144 B: conflict-free 2-byte fragment writes) so the global stores are 16-byte coalesced.
+constexpr int CROSS_DIG_LD = 144;
+constexpr int CROSS_DIG_OFF = 4096;   // the first 4 KB stay free for tile_row_reduce
+constexpr int CROSS_DIG_SMEM = CROSS_DIG_OFF + I8_S * 128 * CROSS_DIG_LD;   // 133,120 B
+template <int KIND, bool DIG>
 __global__ void __launch_bounds__(NTHREADS, 1) k_cross(CrossParams p) {
     extern __shared__ __align__(16) double smem[];
     const int bm = blockIdx.x, bn = blockIdx.y, b = blockIdx.z;
@@ -135,38 +142,68 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cross(CrossParams p) {
 #pragma unroll
         for (int nt = 0; nt < 4; nt++) {
             const int c = frag_col(nt);
-            double kv[2], dv[2];
+            double kv[2], dv[2], kq[2];
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 double r2 = fmax((znr + xnv[nt][e]) - 2.0 * acc.v[mt][nt][e], 0.0);
                 double k, dk;
                 kernel_eval(KIND, r2, k, dk);
                 bool valid = ((bn * BN + c + e) < p.n) && ((bm * BM + r) < p.m);   // padding rows / columns are exact zeros
+                kq[e] = valid ? k : 0.0;                                           // unit-outputscale kernel value in [0, 1]
                 kv[e] = valid ? os * k : 0.0;
                 dv[e] = valid ? os * dk : 0.0;
                 s += kv[e] * alv[nt][e];
             }
-            size_t off = (size_t)(bm * BM + r) * p.ldk + bn * BN + c;
-            *reinterpret_cast<double2*>(Kst + off) = make_double2(kv[0], kv[1]);
-            if (DK) *reinterpret_cast<double2*>(DK + off) = make_double2(dv[0], dv[1]);
+            if constexpr (DIG) {
+                long long x0 = __double2ll_rn(kq[0] * 281474976710656.0);   // (K*/outputscale) 2^48, in [0, 2^48]
+                long long x1 = __double2ll_rn(kq[1] * 281474976710656.0);
+                unsigned char* sd = reinterpret_cast<unsigned char*>(smem) + CROSS_DIG_OFF + r * CROSS_DIG_LD + c;
+#pragma unroll
+                for (int t = I8_S - 1; t >= 1; t--) {               // balanced base-128 digits, least significant first (i8.cuh)
+                    const int r0 = (int)((x0 + 64) & 127) - 64, r1 = (int)((x1 + 64) & 127) - 64;
+                    *reinterpret_cast<char2*>(sd + t * 128 * CROSS_DIG_LD) = make_char2((signed char)r0, (signed char)r1);
+                    x0 = (x0 - r0) >> 7;
+                    x1 = (x1 - r1) >> 7;
+                }
+                *reinterpret_cast<char2*>(sd) = make_char2((signed char)x0, (signed char)x1);
+            } else {
+                size_t off = (size_t)(bm * BM + r) * p.ldk + bn * BN + c;
+                *reinterpret_cast<double2*>(Kst + off) = make_double2(kv[0], kv[1]);
+                if (DK) *reinterpret_cast<double2*>(DK + off) = make_double2(dv[0], dv[1]);
+            }
         }
         rowval[mt] = s;
     }
     double r = tile_row_reduce(rowval, smem);
     if (threadIdx.x < 128) p.meanpart[b * p.bsmp + (size_t)bn * (p.mtiles * BM) + bm * BM + threadIdx.x] = r;
+    if constexpr (DIG) {   // (tile_row_reduce ends with a barrier: every digit is in shared memory)
+        const unsigned char* sd = reinterpret_cast<const unsigned char*>(smem) + CROSS_DIG_OFF;
+        for (int q = threadIdx.x; q < I8_S * 128 * 8; q += NTHREADS) {
+            const int t = q >> 10, rr = (q >> 3) & 127, ch = q & 7;
+            const int4 v = *reinterpret_cast<const int4*>(sd + (t * 128 + rr) * CROSS_DIG_LD + ch * 16);
+            *reinterpret_cast<int4*>(p.Adig + (size_t)t * p.dig_plane + (size_t)(bm * BM + rr) * p.ldk + bn * BN + ch * 16) = v;
+        }
+    }
 }
 
 cudaError_t launch_cross(const CrossParams& p, int batch, cudaStream_t stream) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_cross<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cross<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_cross<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cross<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cross<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CROSS_DIG_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cross<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CROSS_DIG_SMEM);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
     dim3 grid(p.mtiles, p.ntiles, batch);
-    if (p.kind == 0) k_cross<0><<<grid, NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
-    else k_cross<1><<<grid, NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
+    if (p.Adig) {
+        if (p.kind == 0) k_cross<0, true><<<grid, NTHREADS, CROSS_DIG_SMEM, stream>>>(p);
+        else k_cross<1, true><<<grid, NTHREADS, CROSS_DIG_SMEM, stream>>>(p);
+    } else {
+        if (p.kind == 0) k_cross<0, false><<<grid, NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
+        else k_cross<1, false><<<grid, NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 

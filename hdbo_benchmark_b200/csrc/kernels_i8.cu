@@ -1,0 +1,257 @@
+// Exact digit-sliced ("Ozaki") variance contraction on the 5th-generation tensor cores.
+//
+// tcgen05 has no f64 kind, and the FP64 DMMA path of k_var already runs at 95 % of its 37 TFLOP/s ceiling.  The n^2
+// contraction V = K* L^-T is therefore ALSO available as an exact integer computation on tcgen05.mma kind::i8:
+//   K*[c,j] / outputscale = sum_s A_s[c,j] 2^-(7s+6)          (S = 7 balanced base-128 digits, |digit| <= 64, int8)
+//   L^-1[i,j] / 2^e_i     = sum_t B_t[i,j] 2^-(7t+6)          (e_i: per-row power-of-two scale)
+//   V[c,i] = outputscale 2^e_i  sum_g 2^-(7g+12)  sum_{s+t=g} A_s[c,:] . B_t[i,:]      (pairs with s + t <= S-1: 28 int8 GEMMs)
+// Each inner product is EXACT in int32 (|d d'| <= 2^12, K <= 2^15, <= 7 pairs per weight group), the 7 weight groups are
+// accumulated simultaneously in TMEM (7 x 64 columns), and only the final recombination is rounded (FP64).  Measured on the
+// real problem (tests + /tmp simulation recorded in DESIGN.md): posterior-variance error 1e-10 relative, far inside the 1e-6 bar.
+//
+// Kernel: one CTA per (128 candidates x 64 columns of V) tile, 192 threads: warp 0 = TMA producer (two 3-D bulk-tensor copies
+// per 64-byte k-block bring ALL 7+7 digit planes, 64B swizzle), warp 1 = MMA issuer (56 tcgen05.mma per k-block), warps 2-5 =
+// epilogue (tcgen05.ld, FP64 recombination, column scale, row sum of squares).  Triangular k-range (only k-blocks <= column tile),
+// heavy tiles first.  SASS: UTCIMMA / UTMALDG.3D / LDTM / UTCBAR.
+#include <cuda.h>
+
+#include "kernels.cuh"
+#include "i8.cuh"
+
+namespace hdbo {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// digit planes of L^-1 (once per fit): one warp per row.  planes [S][n_pad][n_pad] int8, scale[i] = 2^e_i
+__global__ void k_slice_linv(const double* __restrict__ Linv, int ld, int n_pad, int8_t* __restrict__ planes, double* __restrict__ scale) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n_pad) return;
+    const double* src = Linv + (size_t)row * ld;
+    double mx = 0.0;
+    for (int j = lane; j <= row; j += 32) mx = fmax(mx, fabs(src[j]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    int ex = 0;
+    if (mx > 0.0) frexp(mx, &ex);                       // mx = f 2^ex, f in [0.5, 1)  ->  |x| 2^-ex < 1
+    const double down = ldexp(1.0, I8_FRAC_BITS - ex);  // x -> fixed point with 48 fractional bits
+    if (lane == 0) scale[row] = ldexp(1.0, ex);
+    const size_t plane = (size_t)n_pad * n_pad;
+    for (int j = lane; j < n_pad; j += 32) {
+        long long x = (j <= row) ? __double2ll_rn(src[j] * down) : 0LL;
+        signed char d[I8_S];
+        i8_digits(x, d);
+#pragma unroll
+        for (int t = 0; t < I8_S; t++) planes[t * plane + (size_t)row * n_pad + j] = d[t];
+    }
+}
+
+cudaError_t launch_slice_linv(const double* Linv, int ld, int n_pad, int8_t* planes, double* scale, cudaStream_t st) {
+    k_slice_linv<<<(n_pad + 7) / 8, 256, 0, st>>>(Linv, ld, n_pad, planes, scale);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+#ifndef HDBO_I8_KB
+#define HDBO_I8_KB 32
+#endif
+constexpr int VT_M = 128, VT_N = 64, VT_KB = HDBO_I8_KB;          // k-block = one swizzle row: 32 B (SWIZZLE_32B) or 64 B (SWIZZLE_64B)
+constexpr int VT_STAGES = 128 / VT_KB;                            // 172 KB of operand ring either way; KB = 32 gives the deeper pipeline
+constexpr int VT_A_STAGE = I8_S * VT_M * VT_KB;
+constexpr int VT_B_STAGE = I8_S * VT_N * VT_KB;
+constexpr int VT_GN = 16;   // rasterisation: a wave of 148 CTAs covers ~9 row tiles x 16 column tiles (see launch_var_i8)
+constexpr int VT_SMEM = VT_STAGES * (VT_A_STAGE + VT_B_STAGE) + 256 + 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug becomes a NaN result (flag) instead of a hung GPU
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* flag) {
+    for (long i = 0; i < 200000000L; i++) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    atomicExch(flag, 1);
+    return false;
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// K-major operand whose rows are exactly one swizzle span (VT_KB bytes): 8-row groups 8 VT_KB bytes apart (SBO, in 16 B units),
+// LBO = 1, descriptor version 1 (sm_100), layout type 6 = SWIZZLE_32B / 4 = SWIZZLE_64B
+__device__ __forceinline__ uint64_t make_desc_sw(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(8 * VT_KB / 16) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(VT_KB == 32 ? 6 : 4) << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+                 "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                   "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                   "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+}  // namespace
+
+struct VarI8Params {
+    const double* colscale;   // [n_pad] 2^e_i of the L^-1 row = column of V
+    const double* hyp;        // outputscale at [0]
+    double* varpart;          // [ntiles64][rows_pad]
+    int rows_pad, ntiles64, mtiles;
+    int* flag;                // set when a barrier wait timed out (results are then poisoned with NaN)
+};
+
+__global__ void __launch_bounds__(192, 1) k_var_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, VarI8Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* As = base;
+    uint8_t* Bs = base + VT_STAGES * VT_A_STAGE;
+    uint64_t* bars = (uint64_t*)(base + VT_STAGES * (VT_A_STAGE + VT_B_STAGE));
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + VT_STAGES), accum = smem_u32(bars + 2 * VT_STAGES);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * VT_STAGES + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // Rasterisation: consecutive CTAs (one wave of 148) cover VT_GN column tiles x ~9 row tiles, so every A (K* digit) tile is
+    // fetched from DRAM once per VT_GN column tiles instead of once per column tile (the A planes of a chunk are 4x the L2).
+    // Column-tile groups with the longest k-range come first (heavy-first).
+    const int per_group = p.mtiles * VT_GN;
+    const int grp = blockIdx.x / per_group, rem = blockIdx.x - grp * per_group;
+    const int bm = rem / VT_GN, bn = p.ntiles64 - 1 - (grp * VT_GN + rem % VT_GN);
+    if (bn < 0) return;                                             // (ntiles64 not a multiple of VT_GN: grid is rounded up)
+    const int kblocks = (bn + 1) * (VT_N / VT_KB);                  // L^-1 is lower triangular: k <= column tile
+    if (tid == 0) {
+        for (int s = 0; s < VT_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    // M = 128, N = 64, A/B signed 8-bit K-major, D = S32
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(VT_N >> 3) << 17) | ((uint32_t)(VT_M >> 4) << 24);
+
+    if (warp == 0 && lane == 0) {            // ---- TMA producer ----
+        for (int kb = 0; kb < kblocks; kb++) {
+            const int s = kb % VT_STAGES, ph = (kb / VT_STAGES) & 1;
+            if (!mbar_wait(empty0 + 8 * s, ph ^ 1, p.flag)) break;
+            mbar_expect_tx(full0 + 8 * s, VT_A_STAGE + VT_B_STAGE);
+            tma_load_3d(smem_u32(As + s * VT_A_STAGE), &tmA, full0 + 8 * s, kb * VT_KB, bm * VT_M, 0);
+            tma_load_3d(smem_u32(Bs + s * VT_B_STAGE), &tmB, full0 + 8 * s, kb * VT_KB, bn * VT_N, 0);
+        }
+    } else if (warp == 1 && lane == 0) {     // ---- MMA issuer: 28 digit pairs x 2 k-steps per k-block, one TMEM accumulator per weight group ----
+        for (int kb = 0; kb < kblocks; kb++) {
+            const int s = kb % VT_STAGES, ph = (kb / VT_STAGES) & 1;
+            if (!mbar_wait(full0 + 8 * s, ph, p.flag)) break;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a0 = smem_u32(As + s * VT_A_STAGE), b0 = smem_u32(Bs + s * VT_B_STAGE);
+#pragma unroll
+            for (int g = 0; g < I8_S; g++) {
+#pragma unroll
+                for (int sa = 0; sa <= g; sa++) {
+                    const uint64_t ad = make_desc_sw(a0 + sa * VT_M * VT_KB), bd = make_desc_sw(b0 + (g - sa) * VT_N * VT_KB);
+#pragma unroll
+                    for (int k = 0; k < VT_KB / 32; k++) umma_i8(tmem_base + g * VT_N, ad + 2 * k, bd + 2 * k, idesc, (kb | sa | k) != 0);
+                }
+            }
+            umma_commit(empty0 + 8 * s);
+        }
+        umma_commit(accum);
+    }
+    __syncwarp();
+    if (warp >= 2) {                         // ---- epilogue: FP64 recombination of the 7 weight groups, column scale, row sum of squares ----
+        const bool ok = mbar_wait(accum, 0, p.flag);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;              // TMEM lane quarter this warp may access
+        const double os = p.hyp[0];
+        double ssq = 0.0;
+#pragma unroll
+        for (int ch = 0; ch < VT_N / 32; ch++) {
+            double v[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = 0.0;
+#pragma unroll
+            for (int g = I8_S - 1; g >= 0; g--) {      // smallest weights first
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + g * VT_N + ch * 32, r);
+                const double w = i8_group_weight(g);
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = fma(w, (double)(int32_t)r[j], v[j]);
+            }
+            const double* cs = p.colscale + bn * VT_N + ch * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j++) { const double x = v[j] * (os * cs[j]); ssq = fma(x, x, ssq); }
+        }
+        if (!ok) ssq = __longlong_as_double(0x7ff8000000000000LL);
+        p.varpart[(size_t)bn * p.rows_pad + bm * VT_M + q * 32 + lane] = ssq;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn get_encode() {
+    static EncodeFn fn = [] {
+        void* p = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+        return (EncodeFn)p;
+    }();
+    return fn;
+}
+
+// digit planes [S][rows][kbytes] -> 3-D map, box {64 bytes of K, box_rows, S planes}, 64B swizzle
+static bool make_map3(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t kbytes, uint32_t box_rows) {
+    EncodeFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {kbytes, rows, (cuuint64_t)I8_S};
+    cuuint64_t strides[2] = {kbytes, kbytes * rows};
+    cuuint32_t box[3] = {VT_KB, box_rows, (cuuint32_t)I8_S};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               VT_KB == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Adig: [S][rows_alloc][n_pad] int8 digit planes of K*/outputscale (rows_pad of them used); Bdig: [S][n_pad][n_pad] of scaled L^-1
+cudaError_t launch_var_i8(const int8_t* Adig, int rows_alloc, int rows_pad, const int8_t* Bdig, const double* colscale, const double* hyp,
+                          int n_pad, double* varpart, int* flag, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_var_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    CUtensorMap ta, tb;
+    if (!make_map3(&ta, Adig, rows_alloc, n_pad, VT_M) || !make_map3(&tb, Bdig, n_pad, n_pad, VT_N)) return cudaErrorInvalidValue;
+    const int mt = rows_pad / VT_M, nt = n_pad / VT_N, groups = (nt + VT_GN - 1) / VT_GN;
+    VarI8Params p{colscale, hyp, varpart, rows_pad, nt, mt, flag};
+    k_var_i8<<<mt * VT_GN * groups, 192, VT_SMEM, st>>>(ta, tb, p);
+    return cudaGetLastError();
+}
+
+}  // namespace hdbo

@@ -13,6 +13,7 @@ Data layout in HBM (all FP64, row-major, padded: n_pad = roundup(n,128), d_pad =
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -38,7 +39,10 @@ def _stream() -> int:
 
 
 class DeviceGP:
-    def __init__(self, X: torch.Tensor, y: torch.Tensor, kind: int, batch: int = 1, keep_r2: bool = False):
+    def __init__(self, X: torch.Tensor, y: torch.Tensor, kind: int, batch: int = 1, keep_r2: bool = False,
+                 var_mode: Optional[str] = None):
+        """var_mode: "f64" (FP64 DMMA variance contraction, the default) or "i8" (exact digit-sliced int8 contraction on the
+        tcgen05 tensor cores for the no-grad pool evaluation; batch == 1).  Default from $HDBO_VAR_MODE."""
         if not X.is_cuda:
             raise _lib.HdboError("DeviceGP needs CUDA tensors: the hot path has no CPU implementation")
         self.lib = _lib.load()
@@ -73,6 +77,12 @@ class DeviceGP:
         self._argmax_work = torch.zeros(8192, dtype=torch.uint8, device=self.device)
         self.fitted = False
         self.jitter_used = 0.0
+        self.var_mode = (var_mode or os.environ.get("HDBO_VAR_MODE", "f64")).lower()
+        if self.var_mode not in ("f64", "i8"):
+            raise ValueError(f"var_mode must be 'f64' or 'i8', got {self.var_mode!r}")
+        if self.batch != 1:
+            self.var_mode = "f64"
+        self._i8_state: Optional[torch.Tensor] = None
         self.desc = HdboGp(
             n=self.n, d=self.d, n_pad=npad, d_pad=dpad, kind=self.kind, batch=B,
             X=ptr(self.X), ldx=self.X.stride(0), y=ptr(self.y), center=ptr(self.center), inv_ls=ptr(self.inv_ls),
@@ -119,7 +129,34 @@ class DeviceGP:
             self.hyp[:, 3] = 0.0
         self.fitted = True
         self.jitter_used = jitter
+        if self.var_mode == "i8":
+            self.slice_linv()
         return jitter
+
+    # ---- exact int8 variance mode: digit planes of L^-1, once per fit ----
+    def slice_linv(self) -> None:
+        if self._i8_state is None:
+            need = self.lib.hdbo_i8_state_bytes(C.byref(self.desc))
+            if need == 0:
+                raise _lib.HdboError("hdbo_i8_state_bytes rejected its arguments")
+            self._i8_state = torch.empty(need, dtype=torch.uint8, device=self.device)
+        check(self.lib.hdbo_gp_slice_linv(C.byref(self.desc), ptr(self._i8_state), _stream()), "hdbo_gp_slice_linv")
+
+    def i8_flag(self) -> int:
+        """Non-zero if a pipeline wait of the int8 variance kernel ever timed out (its outputs are then NaN).  Host sync."""
+        if self._i8_state is None:
+            return 0
+        return int(self._i8_state[-16:-12].view(torch.int32).item())
+
+    def _pool_call(self, Zptr, ldz, m, observation_noise, acq_kind, acq_param, mean, var, acq, bso, ws, stream) -> None:
+        if self.var_mode == "i8" and self._i8_state is not None:
+            check(self.lib.hdbo_posterior_acq_i8(C.byref(self.desc), ptr(self._i8_state), Zptr, ldz, m, int(observation_noise),
+                                                 acq_kind, float(acq_param), mean, var, acq, bso, ptr(ws), ws.numel(), stream),
+                  "hdbo_posterior_acq_i8")
+        else:
+            check(self.lib.hdbo_posterior_acq(C.byref(self.desc), Zptr, ldz, m, int(observation_noise), acq_kind,
+                                              float(acq_param), mean, var, acq, bso, ptr(ws), ws.numel(), stream),
+                  "hdbo_posterior_acq")
 
     # ---- workspace ----
     def workspace(self, rows: int, keep: bool = False) -> torch.Tensor:
@@ -150,9 +187,8 @@ class DeviceGP:
         mean = out.get("mean") if "mean" in out else (torch.empty(self.batch, m, **f64) if want_mean else None)
         var = out.get("var") if "var" in out else (torch.empty(self.batch, m, **f64) if want_var else None)
         acq = out.get("acq") if "acq" in out else (torch.empty(self.batch, m, **f64) if acq_kind >= 0 else None)
-        check(self.lib.hdbo_posterior_acq(C.byref(self.desc), ptr(Z), Z.stride(0), m, int(observation_noise), acq_kind,
-                                          float(acq_param), ptr(mean), ptr(var), ptr(acq), m, ptr(ws), ws.numel(),
-                                          _stream()), "hdbo_posterior_acq")
+        self._pool_call(ptr(Z), Z.stride(0), m, observation_noise, acq_kind, acq_param, ptr(mean), ptr(var), ptr(acq), m, ws,
+                        _stream())
         return mean, var, acq
 
     def posterior_acq_host(self, Z_host: torch.Tensor, acq_kind: int, acq_param: float, out_host: Optional[torch.Tensor] = None,
@@ -185,9 +221,8 @@ class DeviceGP:
                 slab[:mc].copy_(Z_host[off:off + mc], non_blocking=True)
                 ready[i % 2].record(self._copy_stream)
             main.wait_event(ready[i % 2])
-            check(self.lib.hdbo_posterior_acq(C.byref(self.desc), ptr(slab), slab.stride(0), mc, 0, acq_kind, float(acq_param),
-                                              0, 0, acq.data_ptr() + off * 8, m, ptr(ws), ws.numel(), main.cuda_stream),
-                  "hdbo_posterior_acq")
+            self._pool_call(ptr(slab), slab.stride(0), mc, 0, acq_kind, acq_param, 0, 0, acq.data_ptr() + off * 8, m, ws,
+                            main.cuda_stream)
             free[i % 2].record(main)
         val, idx = self.argmax(acq)
         if out_host is not None:

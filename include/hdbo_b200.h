@@ -100,6 +100,21 @@ int hdbo_posterior_acq(const hdbo_gp* gp, const double* Z, int64_t ldz, int64_t 
                        double acq_param, double* mean, double* var, double* acq, int64_t bso, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* Exact int8 variance mode (batch == 1): the same call as hdbo_posterior_acq, with the n^2 contraction V = K* L^-T computed
+ * on the tcgen05 tensor cores from base-128 digit planes (7 x 7 digits, 28 exact int8 GEMMs accumulated in TMEM, FP64
+ * recombination; csrc/kernels_i8.cu) instead of FP64 DMMA.  Results agree with hdbo_posterior_acq to ~1e-10 of the prior
+ * variance (tests/test_gpu_i8.py).
+ *   hdbo_i8_state_bytes     size of the caller-owned state buffer (128-byte aligned): digit planes of L^-1 + row scales + flag
+ *   hdbo_gp_slice_linv      after every hdbo_gp_fit: slices gp->Linv into the state
+ *   hdbo_posterior_acq_i8   pool evaluation; `workspace` as for hdbo_posterior_acq (keep_grad_state = 0), 128-byte aligned
+ *   hdbo_i8_state_flag      device int32 inside the state: non-zero if a pipeline wait timed out (outputs are then NaN) */
+size_t hdbo_i8_state_bytes(const hdbo_gp* gp);
+int hdbo_gp_slice_linv(const hdbo_gp* gp, void* i8_state, void* stream);
+int hdbo_posterior_acq_i8(const hdbo_gp* gp, void* i8_state, const double* Z, int64_t ldz, int64_t m, int observation_noise,
+                          int acq_kind, double acq_param, double* mean, double* var, double* acq, int64_t bso, void* workspace,
+                          size_t workspace_bytes, void* stream);
+int32_t* hdbo_i8_state_flag(const hdbo_gp* gp, void* i8_state);
+
 /* Forward of the differentiable posterior for m <= rows candidates, keeping Kstar, dKstar_dr2 and V in the workspace
  * (layout fixed by hdbo_posterior_workspace_bytes(keep_grad_state=1)) for hdbo_posterior_bwd.
  * Replaces: model.posterior(X) under autograd. */
