@@ -128,7 +128,7 @@ PostWs carve(const hdbo_gp* gp, int64_t rows, int keep, void* base) {
 
 // state of the exact int8 variance path, carved from the caller's buffer (hdbo_i8_state_bytes)
 struct I8State {
-    int8_t* digits;   // [I8_S][n_pad][n_pad] digit planes of the row-scaled L^-1
+    int8_t* digits;   // I8_S n_pad^2 bytes: digit images of the row-scaled L^-1 (layout: kernels_i8.cu)
     double* scale;    // [n_pad] power-of-two row scales
     int32_t* flag;    // barrier-timeout flag of k_var_i8 (0 = healthy)
     size_t bytes;
@@ -160,14 +160,14 @@ cudaError_t posterior_chunk(const hdbo_gp* gp, const PostWs& w, int64_t rows_all
     c.bsZ = (long long)rows_alloc * dp; c.bsX = (long long)np * dp; c.bszn = rows_alloc; c.bsxn = np; c.bsalpha = np;
     c.bsK = (long long)rows_alloc * np; c.bsmp = (long long)nt * rows_alloc;
     c.m = (int)mc; c.n = gp->n; c.mtiles = mt; c.ntiles = nt; c.kblocks = dp / BK; c.kind = gp->kind;
-    if (i8) { c.Adig = reinterpret_cast<int8_t*>(w.Kstar); c.dig_plane = (long long)rows_alloc * np; }
+    if (i8) c.Adig = reinterpret_cast<int8_t*>(w.Kstar);   // tile images: 7 bytes per element of the 8-byte K* slab
     prof_mark(0, st);
     e = launch_cross(c, B, st);
     prof_mark(0, st);
     if (e != cudaSuccess) return e;
     if (i8) {
         prof_mark(1, st);
-        e = launch_var_i8(c.Adig, (int)rows_alloc, rp, i8->digits, i8->scale, gp->hyp, np, w.varpart, i8->flag, st);
+        e = launch_var_i8(c.Adig, rp, i8->digits, i8->scale, gp->hyp, np, w.varpart, i8->flag, st);
         prof_mark(1, st);
         return e;
     }

@@ -9,6 +9,8 @@ namespace hdbo {
 
 constexpr int I8_S = 7;
 constexpr int I8_FRAC_BITS = 48;
+constexpr int I8_A_IMAGE = I8_S * 128 * 32;   // bytes of one K* tile image (128 candidates x 32 k) -- layout in kernels_i8.cu
+constexpr int I8_B_IMAGE = I8_S * 64 * 32;    // bytes of one L^-1 tile image (64 rows x 32 k)
 
 __device__ __forceinline__ void i8_digits(long long x, signed char (&d)[I8_S]) {
 #pragma unroll
@@ -25,7 +27,7 @@ __device__ __forceinline__ double i8_group_weight(int g) {   // 2^-(7g+12)
 }
 
 cudaError_t launch_slice_linv(const double* Linv, int ld, int n_pad, int8_t* planes, double* scale, cudaStream_t st);
-cudaError_t launch_var_i8(const int8_t* Adig, int rows_alloc, int rows_pad, const int8_t* Bdig, const double* colscale, const double* hyp,
+cudaError_t launch_var_i8(const int8_t* Aimg, int rows_pad, const int8_t* Bimg, const double* colscale, const double* hyp,
                           int n_pad, double* varpart, int* flag, cudaStream_t st);
 
 }  // namespace hdbo

@@ -109,7 +109,7 @@ cudaError_t launch_gemm_nt(const GemmParams& p, int batch, cudaStream_t stream) 
 // --------------------------------------------------------------------------------------------------------------
 // K*(Z, X) tile: r2 = |z|^2 + |x|^2 - 2 z.x (clamped at 0), k(r2) * outputscale, masked beyond n; plus the partial
 // dot with alpha over this tile's 128 columns (posterior mean), written to meanpart[bn][row].
-// DIG: instead of the FP64 K* slab, emit the 7 int8 digit planes of K*/outputscale for the tcgen05 variance kernel
+// DIG: instead of the FP64 K* slab, emit the int8 digit images of K*/outputscale for the tcgen05 variance kernel
 // (kernels_i8.cu).  The digits come from one FP64 multiply + integer shifts/masks per element (no extra FP64 pipe work) and are
 // staged through shared memory (row stride 144 B: conflict-free 2-byte fragment writes) so the global stores are 16-byte coalesced.
 constexpr int CROSS_DIG_LD = 144;
@@ -177,11 +177,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cross(CrossParams p) {
     double r = tile_row_reduce(rowval, smem);
     if (threadIdx.x < 128) p.meanpart[b * p.bsmp + (size_t)bn * (p.mtiles * BM) + bm * BM + threadIdx.x] = r;
     if constexpr (DIG) {   // (tile_row_reduce ends with a barrier: every digit is in shared memory)
+        // This tile covers 4 k-blocks of the variance contraction: write their images (layout: kernels_i8.cu) -- each image is
+        // 28 KB contiguous, consecutive threads write consecutive 16-byte pieces.
         const unsigned char* sd = reinterpret_cast<const unsigned char*>(smem) + CROSS_DIG_OFF;
-        for (int q = threadIdx.x; q < I8_S * 128 * 8; q += NTHREADS) {
-            const int t = q >> 10, rr = (q >> 3) & 127, ch = q & 7;
-            const int4 v = *reinterpret_cast<const int4*>(sd + (t * 128 + rr) * CROSS_DIG_LD + ch * 16);
-            *reinterpret_cast<int4*>(p.Adig + (size_t)t * p.dig_plane + (size_t)(bm * BM + rr) * p.ldk + bn * BN + ch * 16) = v;
+        const int nkb = p.ldk >> 5;
+        int8_t* dst0 = p.Adig + ((size_t)bm * nkb + bn * 4) * I8_A_IMAGE;
+        constexpr int PIECES = I8_A_IMAGE / 16;   // 1792 per image
+        for (int q = threadIdx.x; q < 4 * PIECES; q += NTHREADS) {
+            const int kbl = q / PIECES, w = q - kbl * PIECES;
+            const int t = w >> 8, rr = (w >> 1) & 127, c = (w & 1) ^ ((rr >> 2) & 1);   // SWIZZLE_32B: halves of rows 4..7 swapped
+            const int4 v = *reinterpret_cast<const int4*>(sd + (t * 128 + rr) * CROSS_DIG_LD + kbl * 32 + c * 16);
+            *reinterpret_cast<int4*>(dst0 + (size_t)kbl * I8_A_IMAGE + w * 16) = v;
         }
     }
 }

@@ -13,16 +13,19 @@
 // per 64-byte k-block bring ALL 7+7 digit planes, 64B swizzle), warp 1 = MMA issuer (56 tcgen05.mma per k-block), warps 2-5 =
 // epilogue (tcgen05.ld, FP64 recombination, column scale, row sum of squares).  Triangular k-range (only k-blocks <= column tile),
 // heavy tiles first.  SASS: UTCIMMA / UTMALDG.3D / LDTM / UTCBAR.
-#include <cuda.h>
-
 #include "kernels.cuh"
 #include "i8.cuh"
 
 namespace hdbo {
 
-// ---------------------------------------------------------------------------------------------------------------------
-// digit planes of L^-1 (once per fit): one warp per row.  planes [S][n_pad][n_pad] int8, scale[i] = 2^e_i
-__global__ void k_slice_linv(const double* __restrict__ Linv, int ld, int n_pad, int8_t* __restrict__ planes, double* __restrict__ scale) {
+// Operand layout ("tile images").  Both digit operands are stored in global memory exactly as the tensor core wants them in shared
+// memory, so one 1-D bulk copy (cp.async.bulk, full 128-byte lines) per operand and k-block fills a pipeline stage:
+//   image(tile, kb) = [S planes][ROWS rows][32 bytes of k], SWIZZLE_32B applied (16-byte halves of rows 4..7 of every 8 swapped),
+//   stored at ((tile * nkb + kb) * S * ROWS * 32), nkb = n_pad / 32;  ROWS = 128 for K* (A), 64 for L^-1 (B).
+// (A 3-D tensor map over plain [S][rows][n_pad] planes works too -- first version -- but its 32-byte box rows are one L2 request
+// each and the L1->XBAR request path saturated at 75 %, ncu profiles/r01_i8_v1.)
+// digit images of L^-1 (once per fit): one warp per row.  scale[i] = 2^e_i
+__global__ void k_slice_linv(const double* __restrict__ Linv, int ld, int n_pad, int8_t* __restrict__ img, double* __restrict__ scale) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= n_pad) return;
@@ -35,13 +38,16 @@ __global__ void k_slice_linv(const double* __restrict__ Linv, int ld, int n_pad,
     if (mx > 0.0) frexp(mx, &ex);                       // mx = f 2^ex, f in [0.5, 1)  ->  |x| 2^-ex < 1
     const double down = ldexp(1.0, I8_FRAC_BITS - ex);  // x -> fixed point with 48 fractional bits
     if (lane == 0) scale[row] = ldexp(1.0, ex);
-    const size_t plane = (size_t)n_pad * n_pad;
-    for (int j = lane; j < n_pad; j += 32) {
+    const int nkb = n_pad >> 5, bn = row >> 6, r = row & 63;
+    const int inrow = (((lane >> 4) ^ ((r >> 2) & 1)) << 4) | (lane & 15);   // SWIZZLE_32B position of k = lane inside the 32-byte row
+    for (int kb = 0; kb < nkb; kb++) {
+        const int j = kb * 32 + lane;
         long long x = (j <= row) ? __double2ll_rn(src[j] * down) : 0LL;
         signed char d[I8_S];
         i8_digits(x, d);
+        int8_t* dst = img + ((size_t)bn * nkb + kb) * (I8_S * 64 * 32) + r * 32 + inrow;
 #pragma unroll
-        for (int t = 0; t < I8_S; t++) planes[t * plane + (size_t)row * n_pad + j] = d[t];
+        for (int t = 0; t < I8_S; t++) dst[t * 64 * 32] = d[t];
     }
 }
 
@@ -52,15 +58,13 @@ cudaError_t launch_slice_linv(const double* Linv, int ld, int n_pad, int8_t* pla
 
 // ---------------------------------------------------------------------------------------------------------------------
 namespace {
-#ifndef HDBO_I8_KB
-#define HDBO_I8_KB 32
-#endif
-constexpr int VT_M = 128, VT_N = 64, VT_KB = HDBO_I8_KB;          // k-block = one swizzle row: 32 B (SWIZZLE_32B) or 64 B (SWIZZLE_64B)
-constexpr int VT_STAGES = 128 / VT_KB;                            // 172 KB of operand ring either way; KB = 32 gives the deeper pipeline
-constexpr int VT_A_STAGE = I8_S * VT_M * VT_KB;
-constexpr int VT_B_STAGE = I8_S * VT_N * VT_KB;
-constexpr int VT_GN = 16;   // rasterisation: a wave of 148 CTAs covers ~9 row tiles x 16 column tiles (see launch_var_i8)
+constexpr int VT_M = 128, VT_N = 64, VT_KB = 32;                  // k-block = one 32-byte swizzle row = one MMA k-step
+constexpr int VT_STAGES = 4;
+constexpr int VT_A_STAGE = I8_S * VT_M * VT_KB;                   // 28672
+constexpr int VT_B_STAGE = I8_S * VT_N * VT_KB;                   // 14336
+constexpr int VT_GN = 16;   // rasterisation: a wave of 148 CTAs covers ~9 row tiles x 16 column tiles (see k_var_i8)
 constexpr int VT_SMEM = VT_STAGES * (VT_A_STAGE + VT_B_STAGE) + 256 + 1024;
+static_assert(VT_A_STAGE == I8_A_IMAGE && VT_B_STAGE == I8_B_IMAGE, "image sizes");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
@@ -78,20 +82,24 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* fl
     atomicExch(flag, 1);
     return false;
 }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-// K-major operand whose rows are exactly one swizzle span (VT_KB bytes): 8-row groups 8 VT_KB bytes apart (SBO, in 16 B units),
-// LBO = 1, descriptor version 1 (sm_100), layout type 6 = SWIZZLE_32B / 4 = SWIZZLE_64B
-__device__ __forceinline__ uint64_t make_desc_sw(uint32_t saddr) {
+// K-major operand with 32-byte rows, SWIZZLE_32B (layout type 6): 8-row groups 256 B apart (SBO = 16 x 16 B), LBO = 1,
+// descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_desc_sw32(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(8 * VT_KB / 16) << 32;
+    d |= (uint64_t)16 << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)(VT_KB == 32 ? 6 : 4) << 61;
+    d |= (uint64_t)6 << 61;
     return d;
+}
+// M = 128, N = n, A/B signed 8-bit K-major, D = S32
+__device__ __forceinline__ constexpr uint32_t idesc_i8(int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(VT_M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_i8(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
@@ -113,14 +121,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }  // namespace
 
 struct VarI8Params {
+    const int8_t* Aimg;       // K* digit images, tile = 128 candidates
+    const int8_t* Bimg;       // L^-1 digit images, tile = 64 rows of L^-1 (= columns of V)
     const double* colscale;   // [n_pad] 2^e_i of the L^-1 row = column of V
     const double* hyp;        // outputscale at [0]
     double* varpart;          // [ntiles64][rows_pad]
-    int rows_pad, ntiles64, mtiles;
+    int rows_pad, ntiles64, mtiles, nkb;
     int* flag;                // set when a barrier wait timed out (results are then poisoned with NaN)
 };
 
-__global__ void __launch_bounds__(192, 1) k_var_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, VarI8Params p) {
+__global__ void __launch_bounds__(192, 1) k_var_i8(VarI8Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* As = base;
@@ -150,32 +160,40 @@ __global__ void __launch_bounds__(192, 1) k_var_i8(const __grid_constant__ CUten
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    // M = 128, N = 64, A/B signed 8-bit K-major, D = S32
-    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(VT_N >> 3) << 17) | ((uint32_t)(VT_M >> 4) << 24);
 
-    if (warp == 0 && lane == 0) {            // ---- TMA producer ----
+    if (warp == 0 && lane == 0) {            // ---- producer: two bulk copies per k-block ----
+        const int8_t* asrc = p.Aimg + (size_t)bm * p.nkb * VT_A_STAGE;
+        const int8_t* bsrc = p.Bimg + (size_t)bn * p.nkb * VT_B_STAGE;
         for (int kb = 0; kb < kblocks; kb++) {
             const int s = kb % VT_STAGES, ph = (kb / VT_STAGES) & 1;
             if (!mbar_wait(empty0 + 8 * s, ph ^ 1, p.flag)) break;
             mbar_expect_tx(full0 + 8 * s, VT_A_STAGE + VT_B_STAGE);
-            tma_load_3d(smem_u32(As + s * VT_A_STAGE), &tmA, full0 + 8 * s, kb * VT_KB, bm * VT_M, 0);
-            tma_load_3d(smem_u32(Bs + s * VT_B_STAGE), &tmB, full0 + 8 * s, kb * VT_KB, bn * VT_N, 0);
+            bulk_load(smem_u32(As + s * VT_A_STAGE), asrc + (size_t)kb * VT_A_STAGE, VT_A_STAGE, full0 + 8 * s);
+            bulk_load(smem_u32(Bs + s * VT_B_STAGE), bsrc + (size_t)kb * VT_B_STAGE, VT_B_STAGE, full0 + 8 * s);
         }
-    } else if (warp == 1 && lane == 0) {     // ---- MMA issuer: 28 digit pairs x 2 k-steps per k-block, one TMEM accumulator per weight group ----
+    } else if (warp == 1 && lane == 0) {     // ---- MMA issuer ----
+        // The B planes t0..t0+c-1 of a stage are contiguous (64 rows x 32 B each), i.e. ONE K-major operand with N = 64 c rows, and the
+        // accumulators of the weight groups g = s + t are adjacent 64-column blocks of TMEM: digit plane s of A against planes
+        // t0.. of B is a single MMA with N = 64 c writing groups s+t0...  10 MMAs (N <= 256) instead of 28 per k-block: the
+        // 4 KB A plane is read from shared memory 10 instead of 28 times (SS-mode operand reads were the limiter: 192 B/clk needed
+        // for N = 64 against 128 B/clk of shared-memory bandwidth).
         for (int kb = 0; kb < kblocks; kb++) {
             const int s = kb % VT_STAGES, ph = (kb / VT_STAGES) & 1;
             if (!mbar_wait(full0 + 8 * s, ph, p.flag)) break;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a0 = smem_u32(As + s * VT_A_STAGE), b0 = smem_u32(Bs + s * VT_B_STAGE);
-#pragma unroll
-            for (int g = 0; g < I8_S; g++) {
-#pragma unroll
-                for (int sa = 0; sa <= g; sa++) {
-                    const uint64_t ad = make_desc_sw(a0 + sa * VT_M * VT_KB), bd = make_desc_sw(b0 + (g - sa) * VT_N * VT_KB);
-#pragma unroll
-                    for (int k = 0; k < VT_KB / 32; k++) umma_i8(tmem_base + g * VT_N, ad + 2 * k, bd + 2 * k, idesc, (kb | sa | k) != 0);
-                }
-            }
+            const uint32_t acc = kb != 0;
+#define HDBO_I8_MMA(SA, T0, CNT, ACC)                                                                                         \
+            umma_i8(tmem_base + ((SA) + (T0)) * VT_N, make_desc_sw32(a0 + (SA) * VT_M * VT_KB),                                \
+                    make_desc_sw32(b0 + (T0) * VT_N * VT_KB), idesc_i8((CNT) * VT_N), (ACC))
+            HDBO_I8_MMA(0, 0, 4, acc); HDBO_I8_MMA(0, 4, 3, acc);      // plane 0 of A initialises all 7 groups at kb = 0
+            HDBO_I8_MMA(1, 0, 4, 1u);  HDBO_I8_MMA(1, 4, 2, 1u);
+            HDBO_I8_MMA(2, 0, 4, 1u);  HDBO_I8_MMA(2, 4, 1, 1u);
+            HDBO_I8_MMA(3, 0, 4, 1u);
+            HDBO_I8_MMA(4, 0, 3, 1u);
+            HDBO_I8_MMA(5, 0, 2, 1u);
+            HDBO_I8_MMA(6, 0, 1, 1u);
+#undef HDBO_I8_MMA
             umma_commit(empty0 + 8 * s);
         }
         umma_commit(accum);
@@ -213,32 +231,8 @@ __global__ void __launch_bounds__(192, 1) k_var_i8(const __grid_constant__ CUten
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeFn get_encode() {
-    static EncodeFn fn = [] {
-        void* p = nullptr; cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
-        return (EncodeFn)p;
-    }();
-    return fn;
-}
-
-// digit planes [S][rows][kbytes] -> 3-D map, box {64 bytes of K, box_rows, S planes}, 64B swizzle
-static bool make_map3(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t kbytes, uint32_t box_rows) {
-    EncodeFn enc = get_encode();
-    if (!enc) return false;
-    cuuint64_t dims[3] = {kbytes, rows, (cuuint64_t)I8_S};
-    cuuint64_t strides[2] = {kbytes, kbytes * rows};
-    cuuint32_t box[3] = {VT_KB, box_rows, (cuuint32_t)I8_S};
-    cuuint32_t estr[3] = {1, 1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               VT_KB == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-// Adig: [S][rows_alloc][n_pad] int8 digit planes of K*/outputscale (rows_pad of them used); Bdig: [S][n_pad][n_pad] of scaled L^-1
-cudaError_t launch_var_i8(const int8_t* Adig, int rows_alloc, int rows_pad, const int8_t* Bdig, const double* colscale, const double* hyp,
+// Aimg: K* digit images for rows_pad / 128 row tiles; Bimg: L^-1 digit images (layout at the top of this file)
+cudaError_t launch_var_i8(const int8_t* Aimg, int rows_pad, const int8_t* Bimg, const double* colscale, const double* hyp,
                           int n_pad, double* varpart, int* flag, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
@@ -246,11 +240,9 @@ cudaError_t launch_var_i8(const int8_t* Adig, int rows_alloc, int rows_pad, cons
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    CUtensorMap ta, tb;
-    if (!make_map3(&ta, Adig, rows_alloc, n_pad, VT_M) || !make_map3(&tb, Bdig, n_pad, n_pad, VT_N)) return cudaErrorInvalidValue;
     const int mt = rows_pad / VT_M, nt = n_pad / VT_N, groups = (nt + VT_GN - 1) / VT_GN;
-    VarI8Params p{colscale, hyp, varpart, rows_pad, nt, mt, flag};
-    k_var_i8<<<mt * VT_GN * groups, 192, VT_SMEM, st>>>(ta, tb, p);
+    VarI8Params p{Aimg, Bimg, colscale, hyp, varpart, rows_pad, nt, mt, n_pad / VT_KB, flag};
+    k_var_i8<<<mt * VT_GN * groups, 192, VT_SMEM, st>>>(p);
     return cudaGetLastError();
 }
 
