@@ -12,6 +12,9 @@ constexpr int I8_FRAC_BITS = 48;
 constexpr int I8_A_IMAGE = I8_S * 128 * 32;   // bytes of one K* tile image (128 candidates x 32 k) -- layout in kernels_i8.cu
 constexpr int I8_B_IMAGE = I8_S * 64 * 32;    // bytes of one L^-1 tile image (64 rows x 32 k)
 
+// sum_{t=1..6} 64 128^(6-t): adding it to a NON-NEGATIVE fixed-point value makes its 6 low balanced digits plain 7-bit fields + 64
+constexpr long long I8_LOW_BIAS = 0x20408102040LL;
+
 __device__ __forceinline__ void i8_digits(long long x, signed char (&d)[I8_S]) {
 #pragma unroll
     for (int t = I8_S - 1; t >= 1; t--) {

@@ -155,17 +155,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cross(CrossParams p) {
                 s += kv[e] * alv[nt][e];
             }
             if constexpr (DIG) {
-                long long x0 = __double2ll_rn(kq[0] * 281474976710656.0);   // (K*/outputscale) 2^48, in [0, 2^48]
-                long long x1 = __double2ll_rn(kq[1] * 281474976710656.0);
+                // balanced base-128 digits (i8.cuh) without a carry chain: adding 64 to each of the 6 low digits turns them into plain
+                // 7-bit fields f_t of y, and d_t = f_t - 64 is the 7-bit value f_t ^ 0x40 sign-extended; done on byte pairs.
+                const unsigned long long y0 = (unsigned long long)(__double2ll_rn(kq[0] * 281474976710656.0) + I8_LOW_BIAS);
+                const unsigned long long y1 = (unsigned long long)(__double2ll_rn(kq[1] * 281474976710656.0) + I8_LOW_BIAS);
+                const unsigned lo0 = (unsigned)y0, hi0 = (unsigned)(y0 >> 32), lo1 = (unsigned)y1, hi1 = (unsigned)(y1 >> 32);
                 unsigned char* sd = reinterpret_cast<unsigned char*>(smem) + CROSS_DIG_OFF + r * CROSS_DIG_LD + c;
+                unsigned v[I8_S];
+                v[6] = (lo0 & 127u) | ((lo1 & 127u) << 8);
+                v[5] = ((lo0 >> 7) & 127u) | (((lo1 >> 7) & 127u) << 8);
+                v[4] = ((lo0 >> 14) & 127u) | (((lo1 >> 14) & 127u) << 8);
+                v[3] = ((lo0 >> 21) & 127u) | (((lo1 >> 21) & 127u) << 8);
+                v[2] = (__funnelshift_r(lo0, hi0, 28) & 127u) | ((__funnelshift_r(lo1, hi1, 28) & 127u) << 8);
+                v[1] = ((hi0 >> 3) & 127u) | (((hi1 >> 3) & 127u) << 8);
+                v[0] = (hi0 >> 10) | ((hi1 >> 10) << 8);                       // top digit: 0..65, no bias
 #pragma unroll
-                for (int t = I8_S - 1; t >= 1; t--) {               // balanced base-128 digits, least significant first (i8.cuh)
-                    const int r0 = (int)((x0 + 64) & 127) - 64, r1 = (int)((x1 + 64) & 127) - 64;
-                    *reinterpret_cast<char2*>(sd + t * 128 * CROSS_DIG_LD) = make_char2((signed char)r0, (signed char)r1);
-                    x0 = (x0 - r0) >> 7;
-                    x1 = (x1 - r1) >> 7;
-                }
-                *reinterpret_cast<char2*>(sd) = make_char2((signed char)x0, (signed char)x1);
+                for (int t = 1; t < I8_S; t++) { v[t] ^= 0x4040u; v[t] |= (v[t] & 0x4040u) << 1; }
+#pragma unroll
+                for (int t = 0; t < I8_S; t++) *reinterpret_cast<unsigned short*>(sd + t * 128 * CROSS_DIG_LD) = (unsigned short)v[t];
             } else {
                 size_t off = (size_t)(bm * BM + r) * p.ldk + bn * BN + c;
                 *reinterpret_cast<double2*>(Kst + off) = make_double2(kv[0], kv[1]);
