@@ -46,6 +46,8 @@ def parse():
     p.add_argument("--cpu-sample", type=int, default=8192, help="candidates per CPU-baseline batch")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--var-mode", default="i8", choices=["i8", "f64"],
+                   help="variance contraction: exact int8 digit slices on tcgen05 (default) or FP64 DMMA")
     return p.parse_args()
 
 
@@ -55,7 +57,8 @@ def workload_config(args, world):
                     f"-candidate scrambled-Sobol pool per GPU (BASELINE.json configs[2])",
         "n_train": args.n, "d": args.d, "pool_per_gpu": args.pool, "pool_total": args.pool * world,
         "acquisition": "LogExpectedImprovement", "kernel": "matern52_ard", "noise": 1e-3,
-        "parallelism": f"pool-shard x{world}", "cache": "inputs larger than L2 (K* chunk 620 MB per launch, L^-1 67 MB; 126 MB L2)",
+        "parallelism": f"pool-shard x{world}", "var_mode": getattr(args, "var_mode", "f64"),
+        "cache": "inputs larger than L2 (per launch: K* chunk 620 MB FP64 / 543 MB int8 digit images, L^-1 67 MB / 117 MB; 126 MB L2)",
     }
 
 
@@ -165,6 +168,14 @@ def run_reference(args):
     }))
 
 
+def _measured_bf16x2():
+    try:
+        pk = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        return {"burst": 2 * pk["bf16_tflops"], "sustained": 2 * pk["bf16_tflops_sustained"]}
+    except Exception:
+        return {"burst": None, "sustained": None}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -190,7 +201,7 @@ def main():
     n, d, m = args.n, args.d, args.pool
     X, y, ls, os_, nz, mu = O.synthetic_problem(n, d)
     best_f = float(y.max())
-    gp = DeviceGP(X.to(dev), y.to(dev), _lib.KERNEL_MATERN52, keep_r2=True)
+    gp = DeviceGP(X.to(dev), y.to(dev), _lib.KERNEL_MATERN52, keep_r2=True, var_mode=args.var_mode)
     gp.set_hyper(ls.to(dev), os_, nz, mu)
     gp.fit()
 
@@ -256,6 +267,33 @@ def main():
         e1.record(); torch.cuda.synchronize()
         peak = max(peak, fl.value / e0.elapsed_time(e1) / 1e9)
 
+    # ---- int8 tensor ceiling, measured live, and the in-run parity guard of the int8 mode against the FP64 DMMA mode ----
+    i8_peak, mode_check, f64_mode = None, None, None
+    if args.var_mode == "i8":
+        flag = torch.zeros(4, dtype=torch.int32, device=dev)
+        ops = C.c_double(0.0)
+        i8_peak = 0.0
+        for _ in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(lib.hdbo_i8_peak_probe(flag.data_ptr(), 4096, sms, C.byref(ops), torch.cuda.current_stream().cuda_stream), "i8 peak")
+            e1.record(); torch.cuda.synchronize()
+            i8_peak = max(i8_peak, ops.value / e0.elapsed_time(e1) / 1e9)
+        assert int(flag[0].item()) == 0, "int8 peak probe timed out"
+        Zc = Z_dev[: 1 << 14]
+        _, var_i8, acq_i8 = gp.posterior_acq(Zc, _lib.ACQ_LOGEI, best_f, want_mean=False)
+        gp.var_mode = "f64"
+        _, var_f64, acq_f64 = gp.posterior_acq(Zc, _lib.ACQ_LOGEI, best_f, want_mean=False)
+        step_resident()
+        ms_f64, _ = timed(step_resident, 1)
+        gp.var_mode = "i8"
+        f64_mode = {"value": m * world / (ms_f64 / 1e3), "unit": UNIT, "steps": 1}
+        mode_check = {"candidates": int(Zc.shape[0]),
+                      "max_abs_var_diff_over_outputscale": float((var_i8 - var_f64).abs().max() / float(os_)),
+                      "max_rel_var_diff": float(((var_i8 - var_f64).abs() / var_f64.abs()).max()),
+                      "same_argmax": bool(int(acq_i8[0].argmax()) == int(acq_f64[0].argmax())), "timeout_flag": gp.i8_flag()}
+        assert mode_check["max_rel_var_diff"] < 1e-6 and mode_check["same_argmax"] and mode_check["timeout_flag"] == 0, mode_check
+
     for _ in range(args.warmup):
         step_resident()
     clocks = ClockSampler(local)
@@ -286,20 +324,38 @@ def main():
         cross_ms = prof_ms[0]
         alg_var = float(args.steps) * m * float(n) * n  # n^2 flops per candidate (triangular V = K* L^-T)
         alg_cross = float(args.steps) * m * 2.0 * n * d
-        achieved = alg_var / (var_ms / 1e3) / 1e12 if var_ms > 0 else None
         traffic = None
         ncu_path = ROOT / "profiles" / "ncu_summary.json"
+        key = "k_var_i8" if args.var_mode == "i8" else "k_var"
         if ncu_path.exists():
             try:
-                traffic = json.loads(ncu_path.read_text()).get("k_var", {}).get("dram_bytes_per_launch")
+                traffic = json.loads(ncu_path.read_text()).get(key, {}).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(args, world), "clocks": clk,
-            "gpu_launches": launches * args.steps, "argmax_index": int(best_i),
-            "roofline": {
+        cross = {"achieved": alg_cross / (cross_ms / 1e3) / 1e12 if cross_ms > 0 else None, "unit": "TFLOP/s (FP64 DMMA)",
+                 "peak": peak, "share_of_step": cross_ms / ms_total}
+        whole = args.steps * m * (2.0 * n * d + float(n) * n + 2 * n) / (ms_total / 1e3) / 1e12
+        if args.var_mode == "i8":
+            # 28 digit-pair products of the triangular contraction, 2 integer ops per multiply-accumulate
+            alg_ops = 28.0 * alg_var
+            achieved = alg_ops / (var_ms / 1e3) / 1e12 if var_ms > 0 else None
+            roof = {
+                "kernel": "k_var_i8 (V = K* L^-T as 28 exact int8 digit-pair GEMMs on tcgen05.mma kind::i8, TMEM accumulators, "
+                          "triangular k-range, FP64 recombination)",
+                "bound": "tensor", "achieved": achieved, "peak": i8_peak, "unit": "TOP/s (int8 tensor ops, 2 per MAC)",
+                "frac": (achieved / i8_peak) if achieved else None, "traffic": traffic, "launches": int(var_n),
+                "avg_launch_ms": var_ms / max(int(var_n), 1), "share_of_step": var_ms / ms_total,
+                "algorithmic_ops_per_launch": alg_ops / max(int(var_n), 1),
+                "fp64_equivalent_tflops": alg_var / (var_ms / 1e3) / 1e12 if var_ms > 0 else None,
+                "fp64_dmma_peak_tflops": peak,
+                "peak_source": "tcgen05.mma kind::i8 issue ceiling measured live by hdbo_i8_peak_probe (resident operands, M128 N256 "
+                               "K32); MEASURED_PEAKS.json has no int8 entry -- for context 2 x its bf16 figures: "
+                               + json.dumps(_measured_bf16x2()),
+                "cross_kernel": cross, "whole_step_fp64_equivalent_tflops": whole,
+            }
+        else:
+            achieved = alg_var / (var_ms / 1e3) / 1e12 if var_ms > 0 else None
+            roof = {
                 "kernel": "k_var (V = K* L^-T, triangular k-range, DMMA.8x8x4)", "bound": "tensor",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": traffic, "launches": int(var_n), "avg_launch_ms": var_ms / max(int(var_n), 1),
@@ -307,12 +363,20 @@ def main():
                 "algorithmic_flops_per_launch": alg_var / max(int(var_n), 1),
                 "peak_source": "FP64 DMMA.8x8x4 issue ceiling measured live by hdbo_fp64_peak_probe (MEASURED_PEAKS.json has "
                                "no FP64 entry; tcgen05 has no f64 kind, so the bf16 figure there does not bound this path)",
-                "cross_kernel": {"achieved": alg_cross / (cross_ms / 1e3) / 1e12 if cross_ms > 0 else None,
-                                 "share_of_step": cross_ms / ms_total},
-                "whole_step_tflops": args.steps * m * (2.0 * n * d + float(n) * n + 2 * n) / (ms_total / 1e3) / 1e12,
-            },
+                "cross_kernel": cross, "whole_step_tflops": whole,
+            }
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if args.var_mode == "f64" else "f64 (variance contraction: exact int8 digit slices on tcgen05, FP64 recombination)",
+            "data": "synthetic", "config": workload_config(args, world), "clocks": clk,
+            "gpu_launches": launches * args.steps, "argmax_index": int(best_i),
+            "roofline": roof,
             "mll_fit_grad_ms": min(mll_ms),
         }
+        if mode_check is not None:
+            out["var_mode_check"] = mode_check
+            out["fp64_dmma_mode"] = f64_mode
         if e2e is not None:
             out["e2e"] = e2e
         if not args.no_cpu_baseline:

@@ -50,6 +50,7 @@ _SIGNATURES = {
     "hdbo_gp_slice_linv": (C.c_int, [C.POINTER(HdboGp), _dp, _dp]),
     "hdbo_posterior_acq_i8": (C.c_int, [C.POINTER(HdboGp), _dp, _dp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_double,
                                         _dp, _dp, _dp, C.c_int64, _dp, C.c_size_t, _dp]),
+    "hdbo_i8_peak_probe": (C.c_int, [_dp, C.c_int, C.c_int, C.POINTER(C.c_double), _dp]),
     "hdbo_i8_state_flag": (C.c_void_p, [C.POINTER(HdboGp), _dp]),
     "hdbo_posterior_fwd": (C.c_int, [C.POINTER(HdboGp), _dp, C.c_int64, C.c_int64, C.c_int, _dp, _dp, C.c_int64,
                                      _dp, C.c_size_t, _dp]),

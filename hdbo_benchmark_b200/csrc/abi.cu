@@ -264,6 +264,12 @@ extern "C" int hdbo_posterior_acq_i8(const hdbo_gp* gp, void* i8_state, const do
                               workspace_bytes, stream_);
 }
 
+extern "C" int hdbo_i8_peak_probe(int32_t* flag, int iters, int sms, double* ops_out, void* stream_) {
+    if (!flag || iters <= 0 || sms <= 0) return -1;
+    TRY_CUDA(launch_i8_peak(iters, sms, flag, ops_out, (cudaStream_t)stream_));
+    return 0;
+}
+
 extern "C" int hdbo_acq_elementwise(const double* mean, const double* var, int64_t m, int acq_kind, double acq_param,
                                     double* acq, double* dmean, double* dvar, void* stream_) {
     if (!mean || !var) return -1;

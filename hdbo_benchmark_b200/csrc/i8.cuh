@@ -33,4 +33,6 @@ cudaError_t launch_slice_linv(const double* Linv, int ld, int n_pad, int8_t* pla
 cudaError_t launch_var_i8(const int8_t* Aimg, int rows_pad, const int8_t* Bimg, const double* colscale, const double* hyp,
                           int n_pad, double* varpart, int* flag, cudaStream_t st);
 
+cudaError_t launch_i8_peak(int iters, int sms, int* flag, double* ops_out, cudaStream_t st);
+
 }  // namespace hdbo

@@ -231,6 +231,47 @@ __global__ void __launch_bounds__(192, 1) k_var_i8(VarI8Params p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------------------
+// int8 tensor-pipe ceiling, measured live (bench.py roofline denominator): every CTA issues `iters` x 8 resident-operand MMAs
+// (M = 128, N = 256, K = 32, pseudo-random digits in shared memory, no global traffic) and waits for the last commit.
+__global__ void __launch_bounds__(128, 1) k_i8_peak(int iters, int* flag) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bar = (uint64_t*)(base + 16384);
+    uint32_t* tmem_slot = (uint32_t*)(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 4096; i += 128) ((uint32_t*)base)[i] = (uint32_t)(i * 2654435761u) & 0x3f3f3f3fu;   // digits in [0, 63]
+    if (tid == 0) { mbar_init(smem_u32(bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes above -> visible to the tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) {
+        const uint64_t ad = make_desc_sw32(smem_u32(base)), bd = make_desc_sw32(smem_u32(base + 4096));
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) umma_i8(tmem_base + (j & 1) * 256, ad, bd, idesc_i8(256), (uint32_t)(it != 0));
+        }
+        umma_commit(smem_u32(bar));
+        mbar_wait(smem_u32(bar), 0, flag);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+cudaError_t launch_i8_peak(int iters, int sms, int* flag, double* ops_out, cudaStream_t st) {
+    constexpr int SM = 16384 + 64 + 1024;
+    k_i8_peak<<<sms, 128, SM, st>>>(iters, flag);
+    if (ops_out) *ops_out = 2.0 * 128 * 256 * 32 * 8.0 * iters * sms;
+    return cudaGetLastError();
+}
+
 // Aimg: K* digit images for rows_pad / 128 row tiles; Bimg: L^-1 digit images (layout at the top of this file)
 cudaError_t launch_var_i8(const int8_t* Aimg, int rows_pad, const int8_t* Bimg, const double* colscale, const double* hyp,
                           int n_pad, double* varpart, int* flag, cudaStream_t st) {

@@ -171,6 +171,10 @@ int hdbo_profile_collect(double* ms_by_class, int64_t* launches_by_class);
  * writes the flops it performs to *flops_out (HOST pointer).  Timed by the caller: measured FP64 tensor peak. */
 int hdbo_fp64_peak_probe(double* scratch, int iters, int sms, double* flops_out, void* stream);
 
+/* Same for the int8 tensor pipe: `sms` CTAs issue resident-operand tcgen05.mma kind::i8 (M128 N256 K32) only; *ops_out (HOST) =
+ * integer operations performed (2 per multiply-accumulate).  flag: device int32, set if the completion wait timed out. */
+int hdbo_i8_peak_probe(int32_t* flag, int iters, int sms, double* ops_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
