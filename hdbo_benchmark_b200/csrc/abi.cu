@@ -6,6 +6,7 @@
 #include "grad.cuh"
 #include "i8.cuh"
 
+#include <cstdlib>
 #include <vector>
 
 using namespace hdbo;
@@ -104,6 +105,8 @@ extern "C" int hdbo_profile_collect(double* ms_by_class, int64_t* launches_by_cl
 namespace {
 struct PostWs {
     double *Zs, *zn, *Kstar, *meanpart, *varpart, *DK, *V, *T, *XsT;
+    double* zscale;   // int8 mode: power-of-two row scales of the candidate digit images
+    int8_t* Zdig;     // int8 mode: candidate digit images
     size_t bytes;
 };
 PostWs carve(const hdbo_gp* gp, int64_t rows, int keep, void* base) {
@@ -114,8 +117,10 @@ PostWs carve(const hdbo_gp* gp, int64_t rows, int keep, void* base) {
     w.Zs = take(B * rows * dp);
     w.zn = take(B * rows);
     w.Kstar = take(B * rows * np);
-    w.meanpart = take(B * nt * rows);
-    w.varpart = take(B * 2 * nt * rows);   // the int8 variance kernel works on 64-column tiles: twice the partials
+    w.meanpart = take(B * 2 * nt * rows);  // the int8 kernels work on 64-column tiles: twice the partials
+    w.varpart = take(B * 2 * nt * rows);
+    w.zscale = take(rows);
+    w.Zdig = reinterpret_cast<int8_t*>(take((size_t)I8_S * rows * rup(gp->d, 32) / 8));
     if (keep) {
         w.DK = take(B * rows * np);
         w.V = take(B * rows * np);
@@ -129,17 +134,22 @@ PostWs carve(const hdbo_gp* gp, int64_t rows, int keep, void* base) {
 // state of the exact int8 variance path, carved from the caller's buffer (hdbo_i8_state_bytes)
 struct I8State {
     int8_t* digits;   // I8_S n_pad^2 bytes: digit images of the row-scaled L^-1 (layout: kernels_i8.cu)
-    double* scale;    // [n_pad] power-of-two row scales
-    int32_t* flag;    // barrier-timeout flag of k_var_i8 (0 = healthy)
+    double* scale;    // [n_pad] power-of-two row scales of L^-1
+    int8_t* Xdig;     // I8_S n_pad roundup(d,32) bytes: digit images of the centred, scaled training inputs
+    double* xscale;   // [n_pad] their row scales
+    int32_t* flag;    // barrier-timeout flag of the tcgen05 kernels (0 = healthy)
     size_t bytes;
 };
 I8State carve_i8(const hdbo_gp* gp, void* base) {
-    const size_t np = gp->n_pad;
+    const size_t np = gp->n_pad, d32 = rup(gp->d, 32);
     I8State s{};
-    s.digits = (int8_t*)base;
-    s.scale = (double*)((char*)base + (size_t)I8_S * np * np);
-    s.flag = (int32_t*)((char*)s.scale + np * sizeof(double));
-    s.bytes = (size_t)I8_S * np * np + np * sizeof(double) + 16;
+    char* p = (char*)base;
+    s.digits = (int8_t*)p;  p += (size_t)I8_S * np * np;
+    s.scale = (double*)p;   p += np * sizeof(double);
+    s.Xdig = (int8_t*)p;    p += (size_t)I8_S * np * d32;
+    s.xscale = (double*)p;  p += np * sizeof(double);
+    s.flag = (int32_t*)p;   p += 16;
+    s.bytes = (size_t)(p - (char*)base);
     return s;
 }
 
@@ -150,9 +160,6 @@ cudaError_t posterior_chunk(const hdbo_gp* gp, const PostWs& w, int64_t rows_all
     const int np = gp->n_pad, dp = gp->d_pad, B = gp->batch;
     const int rp = (int)rup(mc, 128), mt = rp / 128, nt = np / 128;
     cudaError_t e;
-    e = launch_scale_inputs(Z, (int)ldz, 0, (int)mc, gp->d, gp->center, gp->inv_ls, gp->d, w.Zs, dp, rp,
-                            (long long)rows_alloc * dp, w.zn, rows_alloc, B, st);
-    if (e != cudaSuccess) return e;
     CrossParams c{};
     c.Zs = w.Zs; c.Xs = gp->Xs; c.zn = w.zn; c.xn = gp->xn; c.alpha = gp->alpha; c.hyp = gp->hyp;
     c.Kstar = w.Kstar; c.DK = keep ? w.DK : nullptr; c.meanpart = w.meanpart;
@@ -160,7 +167,26 @@ cudaError_t posterior_chunk(const hdbo_gp* gp, const PostWs& w, int64_t rows_all
     c.bsZ = (long long)rows_alloc * dp; c.bsX = (long long)np * dp; c.bszn = rows_alloc; c.bsxn = np; c.bsalpha = np;
     c.bsK = (long long)rows_alloc * np; c.bsmp = (long long)nt * rows_alloc;
     c.m = (int)mc; c.n = gp->n; c.mtiles = mt; c.ntiles = nt; c.kblocks = dp / BK; c.kind = gp->kind;
-    if (i8) c.Adig = reinterpret_cast<int8_t*>(w.Kstar);   // tile images: 7 bytes per element of the 8-byte K* slab
+    static const bool i8_cross = [] { const char* e = getenv("HDBO_I8_CROSS"); return !e || atoi(e) != 0; }();
+    if (i8 && i8_cross) {
+        // whole chunk on the int8 tensor cores: candidate digit images -> K* digit images + mean partials -> variance partials
+        int8_t* Kimg = reinterpret_cast<int8_t*>(w.Kstar);   // tile images: 7 bytes per element of the 8-byte K* slab
+        e = launch_slice_rows(128, Z, ldz, (int)mc, rp, gp->d, gp->center, gp->inv_ls, w.Zdig, w.zscale, w.zn, st);
+        if (e != cudaSuccess) return e;
+        prof_mark(0, st);
+        e = launch_cross_i8(gp->kind, w.Zdig, i8->Xdig, w.zscale, i8->xscale, w.zn, gp->xn, gp->alpha, gp->hyp, Kimg, w.meanpart,
+                            (int)mc, gp->n, rp, np, gp->d, i8->flag, st);
+        prof_mark(0, st);
+        if (e != cudaSuccess) return e;
+        prof_mark(1, st);
+        e = launch_var_i8(Kimg, rp, i8->digits, i8->scale, gp->hyp, np, w.varpart, i8->flag, st);
+        prof_mark(1, st);
+        return e;
+    }
+    e = launch_scale_inputs(Z, (int)ldz, 0, (int)mc, gp->d, gp->center, gp->inv_ls, gp->d, w.Zs, dp, rp,
+                            (long long)rows_alloc * dp, w.zn, rows_alloc, B, st);
+    if (e != cudaSuccess) return e;
+    if (i8) c.Adig = reinterpret_cast<int8_t*>(w.Kstar);   // HDBO_I8_CROSS=0: FP64 DMMA cross kernel with the digit epilogue
     prof_mark(0, st);
     e = launch_cross(c, B, st);
     prof_mark(0, st);
@@ -216,7 +242,8 @@ static int posterior_acq_impl(const hdbo_gp* gp, const I8State* i8, const double
     for (int64_t off = 0; off < m; off += rows) {
         const int64_t mc = (m - off < rows) ? (m - off) : rows;
         TRY_CUDA(posterior_chunk(gp, w, rows, Z + off * ldz, ldz, mc, 0, st, i8));
-        TRY_CUDA(launch_finalize_acq(w.meanpart, w.varpart, (long long)nt * rows, nt, i8 ? 2 * nt : nt, (int)rup(mc, 128), (int)mc, gp->hyp,
+        const bool i8c = i8 && (!getenv("HDBO_I8_CROSS") || atoi(getenv("HDBO_I8_CROSS")) != 0);
+        TRY_CUDA(launch_finalize_acq(w.meanpart, w.varpart, (long long)nt * rows, i8c ? 2 * nt : nt, i8 ? 2 * nt : nt, (int)rup(mc, 128), (int)mc, gp->hyp,
                                      observation_noise, acq_kind, acq_param, mean ? mean + off : nullptr,
                                      var ? var + off : nullptr, (acq && acq_kind >= 0) ? acq + off : nullptr, bso, B, st));
     }
@@ -249,6 +276,7 @@ extern "C" int hdbo_gp_slice_linv(const hdbo_gp* gp, void* i8_state, void* strea
     I8State s = carve_i8(gp, i8_state);
     TRY_CUDA(cudaMemsetAsync(s.flag, 0, 16, st));
     TRY_CUDA(launch_slice_linv(gp->Linv, gp->n_pad, gp->n_pad, s.digits, s.scale, st));
+    TRY_CUDA(launch_slice_rows(64, gp->X, gp->ldx, gp->n, gp->n_pad, gp->d, gp->center, gp->inv_ls, s.Xdig, s.xscale, nullptr, st));
     return 0;
 }
 

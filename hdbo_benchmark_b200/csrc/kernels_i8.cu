@@ -118,7 +118,90 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
                  : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 }  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Pipeline shared by k_var_i8 and k_cross_i8: 192 threads, warp 0 = producer, warp 1 = MMA issuer, warps 2-5 = epilogue.
+struct I8Pipe {
+    uint8_t *As, *Bs;
+    uint32_t full0, empty0, accum, tmem_base;
+};
+
+__device__ __forceinline__ I8Pipe i8_pipe_setup(uint8_t* smem_raw) {
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    I8Pipe pp;
+    pp.As = base;
+    pp.Bs = base + VT_STAGES * VT_A_STAGE;
+    uint64_t* bars = (uint64_t*)(base + VT_STAGES * (VT_A_STAGE + VT_B_STAGE));
+    pp.full0 = smem_u32(bars); pp.empty0 = smem_u32(bars + VT_STAGES); pp.accum = smem_u32(bars + 2 * VT_STAGES);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * VT_STAGES + 1);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < VT_STAGES; s++) { mbar_init(pp.full0 + 8 * s, 1); mbar_init(pp.empty0 + 8 * s, 1); }
+        mbar_init(pp.accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if ((threadIdx.x >> 5) == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    pp.tmem_base = *tmem_slot;
+    return pp;
+}
+
+__device__ __forceinline__ void i8_pipe_teardown(const I8Pipe& pp) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(pp.tmem_base), "r"(512) : "memory");
+}
+
+// producer (one thread): two bulk copies per k-block, images asrc[kb], bsrc[kb]
+__device__ __forceinline__ void i8_pipe_produce(const I8Pipe& pp, const int8_t* asrc, const int8_t* bsrc, int kblocks, int* flag) {
+    for (int kb = 0; kb < kblocks; kb++) {
+        const int s = kb % VT_STAGES, ph = (kb / VT_STAGES) & 1;
+        if (!mbar_wait(pp.empty0 + 8 * s, ph ^ 1, flag)) break;
+        mbar_expect_tx(pp.full0 + 8 * s, VT_A_STAGE + VT_B_STAGE);
+        bulk_load(smem_u32(pp.As + s * VT_A_STAGE), asrc + (size_t)kb * VT_A_STAGE, VT_A_STAGE, pp.full0 + 8 * s);
+        bulk_load(smem_u32(pp.Bs + s * VT_B_STAGE), bsrc + (size_t)kb * VT_B_STAGE, VT_B_STAGE, pp.full0 + 8 * s);
+    }
+}
+
+// MMA issuer (one thread).  The B planes t0..t0+c-1 of a stage are contiguous (64 rows x 32 B each), i.e. ONE K-major operand with
+// N = 64 c rows, and the accumulators of the weight groups g = s + t are adjacent 64-column blocks of TMEM: digit plane s of A
+// against planes t0.. of B is a single MMA with N = 64 c writing groups s+t0...  10 MMAs (N <= 256) instead of 28 per k-block: the
+// 4 KB A plane is read from shared memory 10 instead of 28 times (SS-mode operand reads were the limiter: 192 B/clk needed for
+// N = 64 against 128 B/clk of shared-memory bandwidth).
+__device__ __forceinline__ void i8_pipe_mma(const I8Pipe& pp, int kblocks, int* flag) {
+    for (int kb = 0; kb < kblocks; kb++) {
+        const int s = kb % VT_STAGES, ph = (kb / VT_STAGES) & 1;
+        if (!mbar_wait(pp.full0 + 8 * s, ph, flag)) break;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a0 = smem_u32(pp.As + s * VT_A_STAGE), b0 = smem_u32(pp.Bs + s * VT_B_STAGE);
+        const uint32_t acc = kb != 0;
+#define HDBO_I8_MMA(SA, T0, CNT, ACC)                                                                                         \
+        umma_i8(pp.tmem_base + ((SA) + (T0)) * VT_N, make_desc_sw32(a0 + (SA) * VT_M * VT_KB),                                 \
+                make_desc_sw32(b0 + (T0) * VT_N * VT_KB), idesc_i8((CNT) * VT_N), (ACC))
+        HDBO_I8_MMA(0, 0, 4, acc); HDBO_I8_MMA(0, 4, 3, acc);      // plane 0 of A initialises all 7 groups at kb = 0
+        HDBO_I8_MMA(1, 0, 4, 1u);  HDBO_I8_MMA(1, 4, 2, 1u);
+        HDBO_I8_MMA(2, 0, 4, 1u);  HDBO_I8_MMA(2, 4, 1, 1u);
+        HDBO_I8_MMA(3, 0, 4, 1u);
+        HDBO_I8_MMA(4, 0, 3, 1u);
+        HDBO_I8_MMA(5, 0, 2, 1u);
+        HDBO_I8_MMA(6, 0, 1, 1u);
+#undef HDBO_I8_MMA
+        umma_commit(pp.empty0 + 8 * s);
+    }
+    umma_commit(pp.accum);
+}
 
 struct VarI8Params {
     const int8_t* Aimg;       // K* digit images, tile = 128 candidates
@@ -132,12 +215,6 @@ struct VarI8Params {
 
 __global__ void __launch_bounds__(192, 1) k_var_i8(VarI8Params p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* As = base;
-    uint8_t* Bs = base + VT_STAGES * VT_A_STAGE;
-    uint64_t* bars = (uint64_t*)(base + VT_STAGES * (VT_A_STAGE + VT_B_STAGE));
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + VT_STAGES), accum = smem_u32(bars + 2 * VT_STAGES);
-    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * VT_STAGES + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // Rasterisation: consecutive CTAs (one wave of 148) cover VT_GN column tiles x ~9 row tiles, so every A (K* digit) tile is
     // fetched from DRAM once per VT_GN column tiles instead of once per column tile (the A planes of a chunk are 4x the L2).
@@ -147,57 +224,12 @@ __global__ void __launch_bounds__(192, 1) k_var_i8(VarI8Params p) {
     const int bm = rem / VT_GN, bn = p.ntiles64 - 1 - (grp * VT_GN + rem % VT_GN);
     if (bn < 0) return;                                             // (ntiles64 not a multiple of VT_GN: grid is rounded up)
     const int kblocks = (bn + 1) * (VT_N / VT_KB);                  // L^-1 is lower triangular: k <= column tile
-    if (tid == 0) {
-        for (int s = 0; s < VT_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        mbar_init(accum, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0 && lane == 0) {            // ---- producer: two bulk copies per k-block ----
-        const int8_t* asrc = p.Aimg + (size_t)bm * p.nkb * VT_A_STAGE;
-        const int8_t* bsrc = p.Bimg + (size_t)bn * p.nkb * VT_B_STAGE;
-        for (int kb = 0; kb < kblocks; kb++) {
-            const int s = kb % VT_STAGES, ph = (kb / VT_STAGES) & 1;
-            if (!mbar_wait(empty0 + 8 * s, ph ^ 1, p.flag)) break;
-            mbar_expect_tx(full0 + 8 * s, VT_A_STAGE + VT_B_STAGE);
-            bulk_load(smem_u32(As + s * VT_A_STAGE), asrc + (size_t)kb * VT_A_STAGE, VT_A_STAGE, full0 + 8 * s);
-            bulk_load(smem_u32(Bs + s * VT_B_STAGE), bsrc + (size_t)kb * VT_B_STAGE, VT_B_STAGE, full0 + 8 * s);
-        }
-    } else if (warp == 1 && lane == 0) {     // ---- MMA issuer ----
-        // The B planes t0..t0+c-1 of a stage are contiguous (64 rows x 32 B each), i.e. ONE K-major operand with N = 64 c rows, and the
-        // accumulators of the weight groups g = s + t are adjacent 64-column blocks of TMEM: digit plane s of A against planes
-        // t0.. of B is a single MMA with N = 64 c writing groups s+t0...  10 MMAs (N <= 256) instead of 28 per k-block: the
-        // 4 KB A plane is read from shared memory 10 instead of 28 times (SS-mode operand reads were the limiter: 192 B/clk needed
-        // for N = 64 against 128 B/clk of shared-memory bandwidth).
-        for (int kb = 0; kb < kblocks; kb++) {
-            const int s = kb % VT_STAGES, ph = (kb / VT_STAGES) & 1;
-            if (!mbar_wait(full0 + 8 * s, ph, p.flag)) break;
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a0 = smem_u32(As + s * VT_A_STAGE), b0 = smem_u32(Bs + s * VT_B_STAGE);
-            const uint32_t acc = kb != 0;
-#define HDBO_I8_MMA(SA, T0, CNT, ACC)                                                                                         \
-            umma_i8(tmem_base + ((SA) + (T0)) * VT_N, make_desc_sw32(a0 + (SA) * VT_M * VT_KB),                                \
-                    make_desc_sw32(b0 + (T0) * VT_N * VT_KB), idesc_i8((CNT) * VT_N), (ACC))
-            HDBO_I8_MMA(0, 0, 4, acc); HDBO_I8_MMA(0, 4, 3, acc);      // plane 0 of A initialises all 7 groups at kb = 0
-            HDBO_I8_MMA(1, 0, 4, 1u);  HDBO_I8_MMA(1, 4, 2, 1u);
-            HDBO_I8_MMA(2, 0, 4, 1u);  HDBO_I8_MMA(2, 4, 1, 1u);
-            HDBO_I8_MMA(3, 0, 4, 1u);
-            HDBO_I8_MMA(4, 0, 3, 1u);
-            HDBO_I8_MMA(5, 0, 2, 1u);
-            HDBO_I8_MMA(6, 0, 1, 1u);
-#undef HDBO_I8_MMA
-            umma_commit(empty0 + 8 * s);
-        }
-        umma_commit(accum);
-    }
+    const I8Pipe pp = i8_pipe_setup(smem_raw);
+    const uint32_t tmem_base = pp.tmem_base, accum = pp.accum;
+    if (warp == 0 && lane == 0)
+        i8_pipe_produce(pp, p.Aimg + (size_t)bm * p.nkb * VT_A_STAGE, p.Bimg + (size_t)bn * p.nkb * VT_B_STAGE, kblocks, p.flag);
+    else if (warp == 1 && lane == 0)
+        i8_pipe_mma(pp, kblocks, p.flag);
     __syncwarp();
     if (warp >= 2) {                         // ---- epilogue: FP64 recombination of the 7 weight groups, column scale, row sum of squares ----
         const bool ok = mbar_wait(accum, 0, p.flag);
@@ -225,12 +257,169 @@ __global__ void __launch_bounds__(192, 1) k_var_i8(VarI8Params p) {
         if (!ok) ssq = __longlong_as_double(0x7ff8000000000000LL);
         p.varpart[(size_t)bn * p.rows_pad + bm * VT_M + q * 32 + lane] = ssq;
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    i8_pipe_teardown(pp);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Digit images of centred, lengthscale-scaled input rows (candidates: ROWS = 128 per tile, the A side; training points:
+// ROWS = 64, the B side).  One warp per row: zs_j = (x_j - c_j) / l_j, row scale 2^e >= max |zs|, digits of zs 2^-e; the
+// k-range is padded with zeros to a multiple of 32.  norms (optional) = sum_j zs_j^2 in FP64.
+template <int ROWS>
+__global__ void k_slice_rows(const double* __restrict__ X, long long ldx, int rows_valid, int rows_pad, int d,
+                             const double* __restrict__ center, const double* __restrict__ inv_ls, int8_t* __restrict__ img,
+                             double* __restrict__ scale, double* __restrict__ norms) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows_pad) return;
+    const int nkb = (d + 31) >> 5, tile = row / ROWS, r = row % ROWS;
+    const bool live = row < rows_valid;
+    const double* src = X + (size_t)row * ldx;
+    double mx = 0.0, ss = 0.0;
+    if (live)
+        for (int j = lane; j < d; j += 32) { const double z = (src[j] - center[j]) * inv_ls[j]; mx = fmax(mx, fabs(z)); ss = fma(z, z, ss); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+    int ex = 0;
+    if (mx > 0.0) frexp(mx, &ex);
+    const double down = ldexp(1.0, I8_FRAC_BITS - ex);
+    if (lane == 0) { scale[row] = ldexp(1.0, ex); if (norms) norms[row] = ss; }
+    const int inrow = (((lane >> 4) ^ ((r >> 2) & 1)) << 4) | (lane & 15);   // SWIZZLE_32B position of k = lane inside the 32-byte row
+    for (int kb = 0; kb < nkb; kb++) {
+        const int j = kb * 32 + lane;
+        long long x = 0;
+        if (live && j < d) x = __double2ll_rn((src[j] - center[j]) * inv_ls[j] * down);
+        signed char dg[I8_S];
+        i8_digits(x, dg);
+        int8_t* dst = img + ((size_t)tile * nkb + kb) * (I8_S * ROWS * 32) + r * 32 + inrow;
+#pragma unroll
+        for (int t = 0; t < I8_S; t++) dst[t * ROWS * 32] = dg[t];
+    }
+}
+
+cudaError_t launch_slice_rows(int rows_per_tile, const double* X, long long ldx, int rows_valid, int rows_pad, int d, const double* center,
+                              const double* inv_ls, int8_t* img, double* scale, double* norms, cudaStream_t st) {
+    if (rows_pad == 0) return cudaSuccess;
+    const int grid = (rows_pad + 7) / 8;
+    if (rows_per_tile == 128) k_slice_rows<128><<<grid, 256, 0, st>>>(X, ldx, rows_valid, rows_pad, d, center, inv_ls, img, scale, norms);
+    else k_slice_rows<64><<<grid, 256, 0, st>>>(X, ldx, rows_valid, rows_pad, d, center, inv_ls, img, scale, norms);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K*(Z, X) on the int8 tensor cores: the scaled-candidate x scaled-train inner products as 28 exact digit-pair GEMMs (same
+// pipeline as k_var_i8, K = roundup(d, 32)), then per element  r2 = |z|^2 + |x|^2 - 2 z.x  ->  k(r2)  ->  the 7 digits of
+// k (the A operand of k_var_i8, written straight into its tile images: a thread owns one candidate row, i.e. whole 16-byte
+// halves of image rows) and the partial posterior mean over this tile's 64 training points.
+struct CrossI8Params {
+    const int8_t* Zimg;       // candidate digit images (tile = 128 rows), nkb_d k-blocks
+    const int8_t* Ximg;       // training-point digit images (tile = 64 rows)
+    const double *zscale, *xscale, *zn, *xn, *alpha, *hyp;
+    int8_t* Kimg;             // out: K*/outputscale digit images (tile = 128 rows, n_pad / 32 k-blocks)
+    double* meanpart;         // out: [ntiles64][rows_pad]
+    int m, n, rows_pad, ntiles64, nkb_d, nkb_n;
+    int* flag;
+};
+
+// 320 threads: warp 0 producer, warp 1 MMA issuer, warps 2-9 epilogue (two warps per TMEM lane quarter, 32 columns each: the
+// FP64-heavy epilogue needs two warps per scheduler to hide its dependent-issue latency).
+template <int KIND>
+__global__ void __launch_bounds__(320, 1) k_cross_i8(CrossI8Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ double s_xn[VT_N], s_xs[VT_N], s_al[VT_N], s_ms[VT_M];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int bn = blockIdx.x % p.ntiles64, bm = blockIdx.x / p.ntiles64;
+    if (tid >= 64 && tid < 64 + VT_N) {
+        const int c = bn * VT_N + tid - 64;
+        s_xn[tid - 64] = p.xn[c]; s_xs[tid - 64] = p.xscale[c]; s_al[tid - 64] = p.alpha[c];
+    }
+    const I8Pipe pp = i8_pipe_setup(smem_raw);   // (contains the __syncthreads that publishes s_xn / s_xs / s_al)
+    if (warp == 0 && lane == 0)
+        i8_pipe_produce(pp, p.Zimg + (size_t)bm * p.nkb_d * VT_A_STAGE, p.Ximg + (size_t)bn * p.nkb_d * VT_B_STAGE, p.nkb_d, p.flag);
+    else if (warp == 1 && lane == 0)
+        i8_pipe_mma(pp, p.nkb_d, p.flag);
+    __syncwarp();
+    if (warp >= 2) {
+        const bool ok = mbar_wait(pp.accum, 0, p.flag);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3, half = (warp - 2) >> 2, row = q * 32 + lane, grow = bm * VT_M + row;
+        const double os = p.hyp[0], znr = p.zn[grow], m2sz = -2.0 * p.zscale[grow];
+        const bool rowvalid = grow < p.m;
+        const int swz = (row >> 2) & 1;
+        double msum = 0.0;
+#pragma unroll 1
+        for (int gi = 2 * half; gi < 2 * half + 2; gi++) {   // 16 columns at a time = one 16-byte half of an image row per plane
+            double v[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[j] = 0.0;
+#pragma unroll
+            for (int g = I8_S - 1; g >= 0; g--) {          // smallest weights first
+                uint32_t rr[16];
+                tmem_ld16(pp.tmem_base + ((uint32_t)(q * 32) << 16) + g * VT_N + gi * 16, rr);
+                const double w = i8_group_weight(g);
+#pragma unroll
+                for (int j = 0; j < 16; j++) v[j] = fma(w, (double)(int32_t)rr[j], v[j]);
+            }
+            uint32_t dg[I8_S][4];
+#pragma unroll
+            for (int t = 0; t < I8_S; t++)
+#pragma unroll
+                for (int w4 = 0; w4 < 4; w4++) dg[t][w4] = 0u;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int cl = gi * 16 + j;
+                const double r2 = fmax(fma(v[j] * m2sz, s_xs[cl], znr + s_xn[cl]), 0.0);
+                double k, dk;
+                kernel_eval(KIND, r2, k, dk);
+                const bool valid = rowvalid && (bn * VT_N + cl) < p.n;      // padding rows / columns are exact zeros
+                const double kq = valid ? k : 0.0;
+                msum = fma(os * kq, s_al[cl], msum);
+                const unsigned long long y = (unsigned long long)(__double2ll_rn(kq * 281474976710656.0) + I8_LOW_BIAS);
+                const unsigned lo = (unsigned)y, hi = (unsigned)(y >> 32);
+                const int sh = (j & 3) * 8;
+                dg[6][j >> 2] |= (lo & 127u) << sh;
+                dg[5][j >> 2] |= ((lo >> 7) & 127u) << sh;
+                dg[4][j >> 2] |= ((lo >> 14) & 127u) << sh;
+                dg[3][j >> 2] |= ((lo >> 21) & 127u) << sh;
+                dg[2][j >> 2] |= (__funnelshift_r(lo, hi, 28) & 127u) << sh;
+                dg[1][j >> 2] |= ((hi >> 3) & 127u) << sh;
+                dg[0][j >> 2] |= (hi >> 10) << sh;
+            }
+            int8_t* dst = p.Kimg + ((size_t)bm * p.nkb_n + bn * 2 + (gi >> 1)) * VT_A_STAGE + row * 32 + (((gi & 1) ^ swz) << 4);
+#pragma unroll
+            for (int t = 0; t < I8_S; t++) {
+                uint4 o = make_uint4(dg[t][0], dg[t][1], dg[t][2], dg[t][3]);
+                if (t) {                                   // d_t = f_t - 64: the 7-bit field ^ 0x40, sign-extended (see k_cross)
+                    o.x ^= 0x40404040u; o.x |= (o.x & 0x40404040u) << 1;  o.y ^= 0x40404040u; o.y |= (o.y & 0x40404040u) << 1;
+                    o.z ^= 0x40404040u; o.z |= (o.z & 0x40404040u) << 1;  o.w ^= 0x40404040u; o.w |= (o.w & 0x40404040u) << 1;
+                }
+                *reinterpret_cast<uint4*>(dst + t * VT_M * 32) = o;
+            }
+        }
+        if (!ok) msum = __longlong_as_double(0x7ff8000000000000LL);
+        if (half) s_ms[row] = msum;
+        asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 epilogue warps
+        if (!half) p.meanpart[(size_t)bn * p.rows_pad + grow] = msum + s_ms[row];
+    }
+    i8_pipe_teardown(pp);
+}
+
+cudaError_t launch_cross_i8(int kind, const int8_t* Zimg, const int8_t* Ximg, const double* zscale, const double* xscale, const double* zn,
+                            const double* xn, const double* alpha, const double* hyp, int8_t* Kimg, double* meanpart, int m, int n,
+                            int rows_pad, int n_pad, int d, int* flag, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_cross_i8<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cross_i8<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    CrossI8Params p{Zimg, Ximg, zscale, xscale, zn, xn, alpha, hyp, Kimg, meanpart, m, n, rows_pad, n_pad / VT_N, (d + 31) / 32, n_pad / VT_KB, flag};
+    const int grid = (rows_pad / VT_M) * (n_pad / VT_N);
+    if (kind == 0) k_cross_i8<0><<<grid, 320, VT_SMEM, st>>>(p);
+    else k_cross_i8<1><<<grid, 320, VT_SMEM, st>>>(p);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // int8 tensor-pipe ceiling, measured live (bench.py roofline denominator): every CTA issues `iters` x 8 resident-operand MMAs
 // (M = 128, N = 256, K = 32, pseudo-random digits in shared memory, no global traffic) and waits for the last commit.

@@ -57,7 +57,7 @@ def test_i8_mode_matches_oracle_and_f64_mode(cuda_device, n, d, m, kind, ls_mode
     assert float((mean - m_o).abs().max()) < REL * float(m_o.abs().max())
     assert float(((var - v_o).abs() / v_o.abs()).max()) < REL
     assert float((var - out["f64"][1]).abs().max()) < ABS_VS_F64 * float(os_)
-    assert torch.equal(mean, out["f64"][0])          # the mean does not go through the int8 path
+    assert float((mean - out["f64"][0]).abs().max()) < 1e-9 * float(m_o.abs().max())
     assert int(acq.argmax()) == int(a_o.argmax())
     assert float((acq - a_o).abs().max()) < REL * max(1.0, float(a_o.abs().max()))
 
@@ -140,7 +140,7 @@ def test_i8_c_abi_argument_checks(cuda_device):
     assert lib.hdbo_i8_state_bytes(C.byref(gpb.desc)) == 0
     gp = _gp(X, y, O.MATERN52, (ls, os_, nz, mu), cuda_device, "i8")
     need = lib.hdbo_i8_state_bytes(C.byref(gp.desc))
-    assert need == 7 * 128 * 128 + 8 * 128 + 16
+    assert need == 7 * 128 * 128 + 8 * 128 + 7 * 128 * 32 + 8 * 128 + 16   # L^-1 images + scales, X images + scales, flag
     state = torch.empty(need + 256, dtype=torch.uint8, device=cuda_device)
     assert lib.hdbo_gp_slice_linv(C.byref(gp.desc), state.data_ptr() + 8, 0) == -2      # misaligned state
     assert lib.hdbo_gp_slice_linv(C.byref(gp.desc), 0, 0) == -2
@@ -171,7 +171,7 @@ def test_i8_full_size_against_f64_mode(cuda_device):
         res[mode] = (mean[0].clone(), var[0].clone(), acq[0].clone())
         assert gp.i8_flag() == 0
         del gp
-    assert torch.equal(res["i8"][0], res["f64"][0])
+    assert float((res["i8"][0] - res["f64"][0]).abs().max()) < 1e-9 * float(res["f64"][0].abs().max())
     assert float((res["i8"][1] - res["f64"][1]).abs().max()) < ABS_VS_F64 * float(os_)
     assert float(((res["i8"][1] - res["f64"][1]).abs() / res["f64"][1].abs()).max()) < REL
     assert int(res["i8"][2].argmax()) == int(res["f64"][2].argmax())
