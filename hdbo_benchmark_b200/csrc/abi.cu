@@ -154,23 +154,15 @@ I8State carve_i8(const hdbo_gp* gp, void* base) {
 }
 
 // scale -> cross -> var for `mc` candidates starting at Z (rows_alloc = row capacity of the workspace arrays).
-// i8 != nullptr: K* leaves k_cross as int8 digit planes (in the Kstar slab) and the variance runs on tcgen05 (kernels_i8.cu).
+// i8 != nullptr: both GEMMs run as exact int8 digit-pair products on tcgen05 (kernels_i8.cu); K* only exists as digit images.
 cudaError_t posterior_chunk(const hdbo_gp* gp, const PostWs& w, int64_t rows_alloc, const double* Z, int64_t ldz,
                             int64_t mc, int keep, cudaStream_t st, const I8State* i8 = nullptr) {
     const int np = gp->n_pad, dp = gp->d_pad, B = gp->batch;
     const int rp = (int)rup(mc, 128), mt = rp / 128, nt = np / 128;
     cudaError_t e;
-    CrossParams c{};
-    c.Zs = w.Zs; c.Xs = gp->Xs; c.zn = w.zn; c.xn = gp->xn; c.alpha = gp->alpha; c.hyp = gp->hyp;
-    c.Kstar = w.Kstar; c.DK = keep ? w.DK : nullptr; c.meanpart = w.meanpart;
-    c.ldz = dp; c.ldx = dp; c.ldk = np;
-    c.bsZ = (long long)rows_alloc * dp; c.bsX = (long long)np * dp; c.bszn = rows_alloc; c.bsxn = np; c.bsalpha = np;
-    c.bsK = (long long)rows_alloc * np; c.bsmp = (long long)nt * rows_alloc;
-    c.m = (int)mc; c.n = gp->n; c.mtiles = mt; c.ntiles = nt; c.kblocks = dp / BK; c.kind = gp->kind;
-    static const bool i8_cross = [] { const char* e = getenv("HDBO_I8_CROSS"); return !e || atoi(e) != 0; }();
-    if (i8 && i8_cross) {
+    if (i8) {
         // whole chunk on the int8 tensor cores: candidate digit images -> K* digit images + mean partials -> variance partials
-        int8_t* Kimg = reinterpret_cast<int8_t*>(w.Kstar);   // tile images: 7 bytes per element of the 8-byte K* slab
+        int8_t* Kimg = reinterpret_cast<int8_t*>(w.Kstar);   // tile images: 6 bytes per element of the 8-byte K* slab
         e = launch_slice_rows(128, Z, ldz, (int)mc, rp, gp->d, gp->center, gp->inv_ls, w.Zdig, w.zscale, w.zn, st);
         if (e != cudaSuccess) return e;
         prof_mark(0, st);
@@ -183,20 +175,20 @@ cudaError_t posterior_chunk(const hdbo_gp* gp, const PostWs& w, int64_t rows_all
         prof_mark(1, st);
         return e;
     }
+    CrossParams c{};
+    c.Zs = w.Zs; c.Xs = gp->Xs; c.zn = w.zn; c.xn = gp->xn; c.alpha = gp->alpha; c.hyp = gp->hyp;
+    c.Kstar = w.Kstar; c.DK = keep ? w.DK : nullptr; c.meanpart = w.meanpart;
+    c.ldz = dp; c.ldx = dp; c.ldk = np;
+    c.bsZ = (long long)rows_alloc * dp; c.bsX = (long long)np * dp; c.bszn = rows_alloc; c.bsxn = np; c.bsalpha = np;
+    c.bsK = (long long)rows_alloc * np; c.bsmp = (long long)nt * rows_alloc;
+    c.m = (int)mc; c.n = gp->n; c.mtiles = mt; c.ntiles = nt; c.kblocks = dp / BK; c.kind = gp->kind;
     e = launch_scale_inputs(Z, (int)ldz, 0, (int)mc, gp->d, gp->center, gp->inv_ls, gp->d, w.Zs, dp, rp,
                             (long long)rows_alloc * dp, w.zn, rows_alloc, B, st);
     if (e != cudaSuccess) return e;
-    if (i8) c.Adig = reinterpret_cast<int8_t*>(w.Kstar);   // HDBO_I8_CROSS=0: FP64 DMMA cross kernel with the digit epilogue
     prof_mark(0, st);
     e = launch_cross(c, B, st);
     prof_mark(0, st);
     if (e != cudaSuccess) return e;
-    if (i8) {
-        prof_mark(1, st);
-        e = launch_var_i8(c.Adig, rp, i8->digits, i8->scale, gp->hyp, np, w.varpart, i8->flag, st);
-        prof_mark(1, st);
-        return e;
-    }
     VarParams v{};
     v.Kstar = w.Kstar; v.Linv = gp->Linv; v.V = keep ? w.V : nullptr; v.varpart = w.varpart;
     v.ldk = np; v.ldl = np; v.ldv = np;
@@ -242,8 +234,7 @@ static int posterior_acq_impl(const hdbo_gp* gp, const I8State* i8, const double
     for (int64_t off = 0; off < m; off += rows) {
         const int64_t mc = (m - off < rows) ? (m - off) : rows;
         TRY_CUDA(posterior_chunk(gp, w, rows, Z + off * ldz, ldz, mc, 0, st, i8));
-        const bool i8c = i8 && (!getenv("HDBO_I8_CROSS") || atoi(getenv("HDBO_I8_CROSS")) != 0);
-        TRY_CUDA(launch_finalize_acq(w.meanpart, w.varpart, (long long)nt * rows, i8c ? 2 * nt : nt, i8 ? 2 * nt : nt, (int)rup(mc, 128), (int)mc, gp->hyp,
+        TRY_CUDA(launch_finalize_acq(w.meanpart, w.varpart, (long long)nt * rows, i8 ? 2 * nt : nt, i8 ? 2 * nt : nt, (int)rup(mc, 128), (int)mc, gp->hyp,
                                      observation_noise, acq_kind, acq_param, mean ? mean + off : nullptr,
                                      var ? var + off : nullptr, (acq && acq_kind >= 0) ? acq + off : nullptr, bso, B, st));
     }
@@ -259,7 +250,7 @@ extern "C" int hdbo_posterior_acq(const hdbo_gp* gp, const double* Z, int64_t ld
 
 // ---- exact int8 (tcgen05) variance path: digit planes of L^-1 once per fit, then the pool evaluation ----
 extern "C" size_t hdbo_i8_state_bytes(const hdbo_gp* gp) {
-    if (check_gp(gp) || gp->batch != 1) return 0;
+    if (check_gp(gp) || gp->batch != 1 || gp->n_pad > I8_MAX_N_PAD) return 0;   // int32 group sums: see i8.cuh
     return carve_i8(gp, nullptr).bytes;
 }
 
@@ -270,7 +261,7 @@ extern "C" int32_t* hdbo_i8_state_flag(const hdbo_gp* gp, void* i8_state) {
 
 extern "C" int hdbo_gp_slice_linv(const hdbo_gp* gp, void* i8_state, void* stream_) {
     if (int e = check_gp(gp)) return e;
-    if (gp->batch != 1) return -1;
+    if (gp->batch != 1 || gp->n_pad > I8_MAX_N_PAD) return -1;
     if (!i8_state || ((uintptr_t)i8_state & 127)) return -2;
     cudaStream_t st = (cudaStream_t)stream_;
     I8State s = carve_i8(gp, i8_state);
@@ -284,7 +275,7 @@ extern "C" int hdbo_posterior_acq_i8(const hdbo_gp* gp, void* i8_state, const do
                                      int observation_noise, int acq_kind, double acq_param, double* mean, double* var, double* acq,
                                      int64_t bso, void* workspace, size_t workspace_bytes, void* stream_) {
     if (int e = check_gp(gp)) return e;
-    if (gp->batch != 1) return -1;
+    if (gp->batch != 1 || gp->n_pad > I8_MAX_N_PAD) return -1;
     if (!i8_state || ((uintptr_t)i8_state & 127)) return -2;
     if (workspace && ((uintptr_t)workspace & 127)) return -13;
     I8State s = carve_i8(gp, i8_state);

@@ -61,7 +61,6 @@ cudaError_t launch_scale_inputs(const double* X, int ldx, long long bsX, int nro
 struct CrossParams {
     const double* Zs; const double* Xs; const double* zn; const double* xn; const double* alpha; const double* hyp;
     double* Kstar; double* DK; double* meanpart;
-    int8_t* Adig;     // int8 digit tile images of K*/outputscale (exact tcgen05 path, layout in kernels_i8.cu) or NULL
     int ldz, ldx, ldk;
     long long bsZ, bsX, bszn, bsxn, bsalpha, bsK, bsmp;
     int m, n, mtiles, ntiles, kblocks, kind;

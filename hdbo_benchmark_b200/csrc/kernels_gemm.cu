@@ -7,7 +7,6 @@
 
 #include "gemm_core.cuh"
 #include "kernels.cuh"
-#include "i8.cuh"
 
 namespace hdbo {
 
@@ -109,13 +108,7 @@ cudaError_t launch_gemm_nt(const GemmParams& p, int batch, cudaStream_t stream) 
 // --------------------------------------------------------------------------------------------------------------
 // K*(Z, X) tile: r2 = |z|^2 + |x|^2 - 2 z.x (clamped at 0), k(r2) * outputscale, masked beyond n; plus the partial
 // dot with alpha over this tile's 128 columns (posterior mean), written to meanpart[bn][row].
-// DIG: instead of the FP64 K* slab, emit the int8 digit images of K*/outputscale for the tcgen05 variance kernel
-// (kernels_i8.cu).  The digits come from one FP64 multiply + integer shifts/masks per element (no extra FP64 pipe work) and are
-// staged through shared memory (row stride 144 B: conflict-free 2-byte fragment writes) so the global stores are 16-byte coalesced.
-constexpr int CROSS_DIG_LD = 144;
-constexpr int CROSS_DIG_OFF = 4096;   // the first 4 KB stay free for tile_row_reduce
-constexpr int CROSS_DIG_SMEM = CROSS_DIG_OFF + I8_S * 128 * CROSS_DIG_LD;   // 133,120 B
-template <int KIND, bool DIG>
+template <int KIND>
 __global__ void __launch_bounds__(NTHREADS, 1) k_cross(CrossParams p) {
     extern __shared__ __align__(16) double smem[];
     const int bm = blockIdx.x, bn = blockIdx.y, b = blockIdx.z;
@@ -142,38 +135,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cross(CrossParams p) {
 #pragma unroll
         for (int nt = 0; nt < 4; nt++) {
             const int c = frag_col(nt);
-            double kv[2], dv[2], kq[2];
+            double kv[2], dv[2];
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 double r2 = fmax((znr + xnv[nt][e]) - 2.0 * acc.v[mt][nt][e], 0.0);
                 double k, dk;
                 kernel_eval(KIND, r2, k, dk);
                 bool valid = ((bn * BN + c + e) < p.n) && ((bm * BM + r) < p.m);   // padding rows / columns are exact zeros
-                kq[e] = valid ? k : 0.0;                                           // unit-outputscale kernel value in [0, 1]
                 kv[e] = valid ? os * k : 0.0;
                 dv[e] = valid ? os * dk : 0.0;
                 s += kv[e] * alv[nt][e];
             }
-            if constexpr (DIG) {
-                // balanced base-128 digits (i8.cuh) without a carry chain: adding 64 to each of the 6 low digits turns them into plain
-                // 7-bit fields f_t of y, and d_t = f_t - 64 is the 7-bit value f_t ^ 0x40 sign-extended; done on byte pairs.
-                const unsigned long long y0 = (unsigned long long)(__double2ll_rn(kq[0] * 281474976710656.0) + I8_LOW_BIAS);
-                const unsigned long long y1 = (unsigned long long)(__double2ll_rn(kq[1] * 281474976710656.0) + I8_LOW_BIAS);
-                const unsigned lo0 = (unsigned)y0, hi0 = (unsigned)(y0 >> 32), lo1 = (unsigned)y1, hi1 = (unsigned)(y1 >> 32);
-                unsigned char* sd = reinterpret_cast<unsigned char*>(smem) + CROSS_DIG_OFF + r * CROSS_DIG_LD + c;
-                unsigned v[I8_S];
-                v[6] = (lo0 & 127u) | ((lo1 & 127u) << 8);
-                v[5] = ((lo0 >> 7) & 127u) | (((lo1 >> 7) & 127u) << 8);
-                v[4] = ((lo0 >> 14) & 127u) | (((lo1 >> 14) & 127u) << 8);
-                v[3] = ((lo0 >> 21) & 127u) | (((lo1 >> 21) & 127u) << 8);
-                v[2] = (__funnelshift_r(lo0, hi0, 28) & 127u) | ((__funnelshift_r(lo1, hi1, 28) & 127u) << 8);
-                v[1] = ((hi0 >> 3) & 127u) | (((hi1 >> 3) & 127u) << 8);
-                v[0] = (hi0 >> 10) | ((hi1 >> 10) << 8);                       // top digit: 0..65, no bias
-#pragma unroll
-                for (int t = 1; t < I8_S; t++) { v[t] ^= 0x4040u; v[t] |= (v[t] & 0x4040u) << 1; }
-#pragma unroll
-                for (int t = 0; t < I8_S; t++) *reinterpret_cast<unsigned short*>(sd + t * 128 * CROSS_DIG_LD) = (unsigned short)v[t];
-            } else {
+            {
                 size_t off = (size_t)(bm * BM + r) * p.ldk + bn * BN + c;
                 *reinterpret_cast<double2*>(Kst + off) = make_double2(kv[0], kv[1]);
                 if (DK) *reinterpret_cast<double2*>(DK + off) = make_double2(dv[0], dv[1]);
@@ -183,40 +156,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cross(CrossParams p) {
     }
     double r = tile_row_reduce(rowval, smem);
     if (threadIdx.x < 128) p.meanpart[b * p.bsmp + (size_t)bn * (p.mtiles * BM) + bm * BM + threadIdx.x] = r;
-    if constexpr (DIG) {   // (tile_row_reduce ends with a barrier: every digit is in shared memory)
-        // This tile covers 4 k-blocks of the variance contraction: write their images (layout: kernels_i8.cu) -- each image is
-        // 28 KB contiguous, consecutive threads write consecutive 16-byte pieces.
-        const unsigned char* sd = reinterpret_cast<const unsigned char*>(smem) + CROSS_DIG_OFF;
-        const int nkb = p.ldk >> 5;
-        int8_t* dst0 = p.Adig + ((size_t)bm * nkb + bn * 4) * I8_A_IMAGE;
-        constexpr int PIECES = I8_A_IMAGE / 16;   // 1792 per image
-        for (int q = threadIdx.x; q < 4 * PIECES; q += NTHREADS) {
-            const int kbl = q / PIECES, w = q - kbl * PIECES;
-            const int t = w >> 8, rr = (w >> 1) & 127, c = (w & 1) ^ ((rr >> 2) & 1);   // SWIZZLE_32B: halves of rows 4..7 swapped
-            const int4 v = *reinterpret_cast<const int4*>(sd + (t * 128 + rr) * CROSS_DIG_LD + kbl * 32 + c * 16);
-            *reinterpret_cast<int4*>(dst0 + (size_t)kbl * I8_A_IMAGE + w * 16) = v;
-        }
-    }
 }
 
 cudaError_t launch_cross(const CrossParams& p, int batch, cudaStream_t stream) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_cross<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cross<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cross<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CROSS_DIG_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cross<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CROSS_DIG_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(k_cross<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cross<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
     dim3 grid(p.mtiles, p.ntiles, batch);
-    if (p.Adig) {
-        if (p.kind == 0) k_cross<0, true><<<grid, NTHREADS, CROSS_DIG_SMEM, stream>>>(p);
-        else k_cross<1, true><<<grid, NTHREADS, CROSS_DIG_SMEM, stream>>>(p);
-    } else {
-        if (p.kind == 0) k_cross<0, false><<<grid, NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
-        else k_cross<1, false><<<grid, NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
-    }
+    if (p.kind == 0) k_cross<0><<<grid, NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
+    else k_cross<1><<<grid, NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -1,29 +1,32 @@
-// Exact digit-sliced ("Ozaki") variance contraction on the 5th-generation tensor cores.
+// Exact digit-sliced ("Ozaki"-style) GEMMs of the posterior on the 5th-generation tensor cores.
 //
-// tcgen05 has no f64 kind, and the FP64 DMMA path of k_var already runs at 95 % of its 37 TFLOP/s ceiling.  The n^2
-// contraction V = K* L^-T is therefore ALSO available as an exact integer computation on tcgen05.mma kind::i8:
-//   K*[c,j] / outputscale = sum_s A_s[c,j] 2^-(7s+6)          (S = 7 balanced base-128 digits, |digit| <= 64, int8)
-//   L^-1[i,j] / 2^e_i     = sum_t B_t[i,j] 2^-(7t+6)          (e_i: per-row power-of-two scale)
-//   V[c,i] = outputscale 2^e_i  sum_g 2^-(7g+12)  sum_{s+t=g} A_s[c,:] . B_t[i,:]      (pairs with s + t <= S-1: 28 int8 GEMMs)
-// Each inner product is EXACT in int32 (|d d'| <= 2^12, K <= 2^15, <= 7 pairs per weight group), the 7 weight groups are
-// accumulated simultaneously in TMEM (7 x 64 columns), and only the final recombination is rounded (FP64).  Measured on the
-// real problem (tests + /tmp simulation recorded in DESIGN.md): posterior-variance error 1e-10 relative, far inside the 1e-6 bar.
+// tcgen05 has no f64 kind, and the FP64 DMMA kernels (kernels_gemm.cu) already run at 95 % of the 37 TFLOP/s DMMA ceiling.  The two
+// GEMMs of the no-grad pool evaluation are therefore ALSO available as exact integer computations on tcgen05.mma kind::i8:
+//   k_cross_i8   G = Zs Xs^T (scaled candidates x scaled training points, K = d)   ->  r2 -> k(r2) -> digits of K*, mean partials
+//   k_var_i8     V = K* L^-T (K = n, triangular)                                   ->  row sums of squares (variance partials)
+// Both operands are split into 6 base-256 digit planes (i8.cuh); the 21 plane pairs with s + t <= 5 are exact int8 GEMMs with
+// int32 accumulation, the 6 weight groups g = s + t live side by side in TMEM (6 x 64 columns), and only the final recombination
+// sum_g 2^-(8g+c) acc_g is rounded (FP64).  Measured against the FP64 path: variance within 1e-12 of the prior variance, mean
+// within 1e-11 relative (tests/test_gpu_i8.py).
 //
-// Kernel: one CTA per (128 candidates x 64 columns of V) tile, 192 threads: warp 0 = TMA producer (two 3-D bulk-tensor copies
-// per 64-byte k-block bring ALL 7+7 digit planes, 64B swizzle), warp 1 = MMA issuer (56 tcgen05.mma per k-block), warps 2-5 =
-// epilogue (tcgen05.ld, FP64 recombination, column scale, row sum of squares).  Triangular k-range (only k-blocks <= column tile),
-// heavy tiles first.  SASS: UTCIMMA / UTMALDG.3D / LDTM / UTCBAR.
+// Kernel shape (both): one CTA per (128 candidates x 64 columns) tile; warp 0 = producer (two 1-D bulk copies per 32-byte k-block
+// bring all 6+6 digit planes), warp 1 = MMA issuer (8 merged MMAs per k-block), remaining warps = epilogue from TMEM.
+// SASS: UTCIMMA / UBLKCP / LDTM / UTCBAR.
 #include "kernels.cuh"
 #include "i8.cuh"
 
 namespace hdbo {
 
-// Operand layout ("tile images").  Both digit operands are stored in global memory exactly as the tensor core wants them in shared
+// Operand layout ("tile images").  Digit operands are stored in global memory exactly as the tensor core wants them in shared
 // memory, so one 1-D bulk copy (cp.async.bulk, full 128-byte lines) per operand and k-block fills a pipeline stage:
 //   image(tile, kb) = [S planes][ROWS rows][32 bytes of k], SWIZZLE_32B applied (16-byte halves of rows 4..7 of every 8 swapped),
-//   stored at ((tile * nkb + kb) * S * ROWS * 32), nkb = n_pad / 32;  ROWS = 128 for K* (A), 64 for L^-1 (B).
-// (A 3-D tensor map over plain [S][rows][n_pad] planes works too -- first version -- but its 32-byte box rows are one L2 request
-// each and the L1->XBAR request path saturated at 75 %, ncu profiles/r01_i8_v1.)
+//   stored at ((tile * nkb + kb) * S * ROWS * 32);  ROWS = 128 for the A side (candidates), 64 for the B side.
+// (A 3-D tensor map over plain [S][rows][K] planes works too -- first version -- but its 32-byte box rows are one L2 request each
+// and the L1->XBAR request path saturated at 75 %: profiles/r01_ncu_i8_v1.txt.)
+
+// position of k-byte `lane` (0..31) of row r inside its 32-byte image row
+__device__ __forceinline__ int img_inrow(int r, int lane) { return (((lane >> 4) ^ ((r >> 2) & 1)) << 4) | (lane & 15); }
+
 // digit images of L^-1 (once per fit): one warp per row.  scale[i] = 2^e_i
 __global__ void k_slice_linv(const double* __restrict__ Linv, int ld, int n_pad, int8_t* __restrict__ img, double* __restrict__ scale) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -34,37 +37,80 @@ __global__ void k_slice_linv(const double* __restrict__ Linv, int ld, int n_pad,
     for (int j = lane; j <= row; j += 32) mx = fmax(mx, fabs(src[j]));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    int ex = 0;
-    if (mx > 0.0) frexp(mx, &ex);                       // mx = f 2^ex, f in [0.5, 1)  ->  |x| 2^-ex < 1
-    const double down = ldexp(1.0, I8_FRAC_BITS - ex);  // x -> fixed point with 48 fractional bits
+    const int ex = i8_row_exponent(mx);
+    const double down = ldexp(1.0, I8_SIGNED_FRAC_BITS - ex);
     if (lane == 0) scale[row] = ldexp(1.0, ex);
     const int nkb = n_pad >> 5, bn = row >> 6, r = row & 63;
-    const int inrow = (((lane >> 4) ^ ((r >> 2) & 1)) << 4) | (lane & 15);   // SWIZZLE_32B position of k = lane inside the 32-byte row
+    const int inrow = img_inrow(r, lane);
     for (int kb = 0; kb < nkb; kb++) {
         const int j = kb * 32 + lane;
-        long long x = (j <= row) ? __double2ll_rn(src[j] * down) : 0LL;
-        signed char d[I8_S];
-        i8_digits(x, d);
-        int8_t* dst = img + ((size_t)bn * nkb + kb) * (I8_S * 64 * 32) + r * 32 + inrow;
+        const long long x = (j <= row) ? __double2ll_rn(src[j] * down) : 0LL;
+        unsigned dg[I8_S];
+        i8_signed_digits(x, dg);
+        int8_t* dst = img + ((size_t)bn * nkb + kb) * I8_B_IMAGE + r * 32 + inrow;
 #pragma unroll
-        for (int t = 0; t < I8_S; t++) dst[t * 64 * 32] = d[t];
+        for (int t = 0; t < I8_S; t++) dst[t * 64 * 32] = (int8_t)dg[t];
     }
 }
 
-cudaError_t launch_slice_linv(const double* Linv, int ld, int n_pad, int8_t* planes, double* scale, cudaStream_t st) {
-    k_slice_linv<<<(n_pad + 7) / 8, 256, 0, st>>>(Linv, ld, n_pad, planes, scale);
+cudaError_t launch_slice_linv(const double* Linv, int ld, int n_pad, int8_t* img, double* scale, cudaStream_t st) {
+    k_slice_linv<<<(n_pad + 7) / 8, 256, 0, st>>>(Linv, ld, n_pad, img, scale);
+    return cudaGetLastError();
+}
+
+// Digit images of centred, lengthscale-scaled input rows (candidates: ROWS = 128 per tile, the A side; training points:
+// ROWS = 64, the B side).  One warp per row: zs_j = (x_j - c_j) / l_j, row scale 2^e, digits of zs 2^-e; the k-range is
+// padded with zeros to a multiple of 32.  norms (optional) = sum_j zs_j^2 in FP64.
+template <int ROWS>
+__global__ void k_slice_rows(const double* __restrict__ X, long long ldx, int rows_valid, int rows_pad, int d,
+                             const double* __restrict__ center, const double* __restrict__ inv_ls, int8_t* __restrict__ img,
+                             double* __restrict__ scale, double* __restrict__ norms) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows_pad) return;
+    const int nkb = (d + 31) >> 5, tile = row / ROWS, r = row % ROWS;
+    const bool live = row < rows_valid;
+    const double* src = X + (size_t)row * ldx;
+    double mx = 0.0, ss = 0.0;
+    if (live)
+        for (int j = lane; j < d; j += 32) { const double z = (src[j] - center[j]) * inv_ls[j]; mx = fmax(mx, fabs(z)); ss = fma(z, z, ss); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+    const int ex = i8_row_exponent(mx);
+    const double down = ldexp(1.0, I8_SIGNED_FRAC_BITS - ex);
+    if (lane == 0) { scale[row] = ldexp(1.0, ex); if (norms) norms[row] = ss; }
+    const int inrow = img_inrow(r, lane);
+    for (int kb = 0; kb < nkb; kb++) {
+        const int j = kb * 32 + lane;
+        long long x = 0;
+        if (live && j < d) x = __double2ll_rn((src[j] - center[j]) * inv_ls[j] * down);
+        unsigned dg[I8_S];
+        i8_signed_digits(x, dg);
+        int8_t* dst = img + ((size_t)tile * nkb + kb) * (I8_S * ROWS * 32) + r * 32 + inrow;
+#pragma unroll
+        for (int t = 0; t < I8_S; t++) dst[t * ROWS * 32] = (int8_t)dg[t];
+    }
+}
+
+cudaError_t launch_slice_rows(int rows_per_tile, const double* X, long long ldx, int rows_valid, int rows_pad, int d, const double* center,
+                              const double* inv_ls, int8_t* img, double* scale, double* norms, cudaStream_t st) {
+    if (rows_pad == 0) return cudaSuccess;
+    const int grid = (rows_pad + 7) / 8;
+    if (rows_per_tile == 128) k_slice_rows<128><<<grid, 256, 0, st>>>(X, ldx, rows_valid, rows_pad, d, center, inv_ls, img, scale, norms);
+    else k_slice_rows<64><<<grid, 256, 0, st>>>(X, ldx, rows_valid, rows_pad, d, center, inv_ls, img, scale, norms);
     return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 namespace {
 constexpr int VT_M = 128, VT_N = 64, VT_KB = 32;                  // k-block = one 32-byte swizzle row = one MMA k-step
-constexpr int VT_STAGES = 4;
-constexpr int VT_A_STAGE = I8_S * VT_M * VT_KB;                   // 28672
-constexpr int VT_B_STAGE = I8_S * VT_N * VT_KB;                   // 14336
-constexpr int VT_GN = 16;   // rasterisation: a wave of 148 CTAs covers ~9 row tiles x 16 column tiles (see k_var_i8)
+constexpr int VT_STAGES = 5;
+constexpr int VT_A_STAGE = I8_S * VT_M * VT_KB;                   // 24576
+constexpr int VT_B_STAGE = I8_S * VT_N * VT_KB;                   // 12288
+constexpr int VT_GN = 16;   // rasterisation of k_var_i8: a wave of 148 CTAs covers ~9 row tiles x 16 column tiles
 constexpr int VT_SMEM = VT_STAGES * (VT_A_STAGE + VT_B_STAGE) + 256 + 1024;
 static_assert(VT_A_STAGE == I8_A_IMAGE && VT_B_STAGE == I8_B_IMAGE, "image sizes");
+static_assert(I8_S * VT_N <= 512, "weight groups must fit the 512 TMEM columns");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
@@ -97,9 +143,9 @@ __device__ __forceinline__ uint64_t make_desc_sw32(uint32_t saddr) {
     d |= (uint64_t)6 << 61;
     return d;
 }
-// M = 128, N = n, A/B signed 8-bit K-major, D = S32
-__device__ __forceinline__ constexpr uint32_t idesc_i8(int n) {
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(VT_M >> 4) << 24);
+// M = 128, N = n, K-major 8-bit operands (A signed or unsigned, B signed), D = S32
+__device__ __forceinline__ constexpr uint32_t idesc_i8(int n, bool a_signed) {
+    return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(VT_M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_i8(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
@@ -128,7 +174,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Pipeline shared by k_var_i8 and k_cross_i8: 192 threads, warp 0 = producer, warp 1 = MMA issuer, warps 2-5 = epilogue.
+// Pipeline shared by k_var_i8 and k_cross_i8: warp 0 = producer, warp 1 = MMA issuer, warps >= 2 = epilogue.
 struct I8Pipe {
     uint8_t *As, *Bs;
     uint32_t full0, empty0, accum, tmem_base;
@@ -177,9 +223,10 @@ __device__ __forceinline__ void i8_pipe_produce(const I8Pipe& pp, const int8_t* 
 
 // MMA issuer (one thread).  The B planes t0..t0+c-1 of a stage are contiguous (64 rows x 32 B each), i.e. ONE K-major operand with
 // N = 64 c rows, and the accumulators of the weight groups g = s + t are adjacent 64-column blocks of TMEM: digit plane s of A
-// against planes t0.. of B is a single MMA with N = 64 c writing groups s+t0...  10 MMAs (N <= 256) instead of 28 per k-block: the
-// 4 KB A plane is read from shared memory 10 instead of 28 times (SS-mode operand reads were the limiter: 192 B/clk needed for
-// N = 64 against 128 B/clk of shared-memory bandwidth).
+// against planes t0.. of B is a single MMA with N = 64 c writing groups s+t0...  8 MMAs (N <= 256) instead of 21 per k-block: the
+// 4 KB A plane is read from shared memory 8 instead of 21 times (SS-mode operand reads were the limiter of the unmerged version:
+// 192 B/clk needed for N = 64 against 128 B/clk of shared-memory bandwidth).
+template <bool A_SIGNED>
 __device__ __forceinline__ void i8_pipe_mma(const I8Pipe& pp, int kblocks, int* flag) {
     for (int kb = 0; kb < kblocks; kb++) {
         const int s = kb % VT_STAGES, ph = (kb / VT_STAGES) & 1;
@@ -189,127 +236,24 @@ __device__ __forceinline__ void i8_pipe_mma(const I8Pipe& pp, int kblocks, int* 
         const uint32_t acc = kb != 0;
 #define HDBO_I8_MMA(SA, T0, CNT, ACC)                                                                                         \
         umma_i8(pp.tmem_base + ((SA) + (T0)) * VT_N, make_desc_sw32(a0 + (SA) * VT_M * VT_KB),                                 \
-                make_desc_sw32(b0 + (T0) * VT_N * VT_KB), idesc_i8((CNT) * VT_N), (ACC))
-        HDBO_I8_MMA(0, 0, 4, acc); HDBO_I8_MMA(0, 4, 3, acc);      // plane 0 of A initialises all 7 groups at kb = 0
-        HDBO_I8_MMA(1, 0, 4, 1u);  HDBO_I8_MMA(1, 4, 2, 1u);
-        HDBO_I8_MMA(2, 0, 4, 1u);  HDBO_I8_MMA(2, 4, 1, 1u);
-        HDBO_I8_MMA(3, 0, 4, 1u);
-        HDBO_I8_MMA(4, 0, 3, 1u);
-        HDBO_I8_MMA(5, 0, 2, 1u);
-        HDBO_I8_MMA(6, 0, 1, 1u);
+                make_desc_sw32(b0 + (T0) * VT_N * VT_KB), idesc_i8((CNT) * VT_N, A_SIGNED), (ACC))
+        HDBO_I8_MMA(0, 0, 4, acc); HDBO_I8_MMA(0, 4, 2, acc);      // plane 0 of A initialises all 6 groups at kb = 0
+        HDBO_I8_MMA(1, 0, 4, 1u);  HDBO_I8_MMA(1, 4, 1, 1u);
+        HDBO_I8_MMA(2, 0, 4, 1u);
+        HDBO_I8_MMA(3, 0, 3, 1u);
+        HDBO_I8_MMA(4, 0, 2, 1u);
+        HDBO_I8_MMA(5, 0, 1, 1u);
 #undef HDBO_I8_MMA
         umma_commit(pp.empty0 + 8 * s);
     }
     umma_commit(pp.accum);
 }
 
-struct VarI8Params {
-    const int8_t* Aimg;       // K* digit images, tile = 128 candidates
-    const int8_t* Bimg;       // L^-1 digit images, tile = 64 rows of L^-1 (= columns of V)
-    const double* colscale;   // [n_pad] 2^e_i of the L^-1 row = column of V
-    const double* hyp;        // outputscale at [0]
-    double* varpart;          // [ntiles64][rows_pad]
-    int rows_pad, ntiles64, mtiles, nkb;
-    int* flag;                // set when a barrier wait timed out (results are then poisoned with NaN)
-};
-
-__global__ void __launch_bounds__(192, 1) k_var_i8(VarI8Params p) {
-    extern __shared__ uint8_t smem_raw[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // Rasterisation: consecutive CTAs (one wave of 148) cover VT_GN column tiles x ~9 row tiles, so every A (K* digit) tile is
-    // fetched from DRAM once per VT_GN column tiles instead of once per column tile (the A planes of a chunk are 4x the L2).
-    // Column-tile groups with the longest k-range come first (heavy-first).
-    const int per_group = p.mtiles * VT_GN;
-    const int grp = blockIdx.x / per_group, rem = blockIdx.x - grp * per_group;
-    const int bm = rem / VT_GN, bn = p.ntiles64 - 1 - (grp * VT_GN + rem % VT_GN);
-    if (bn < 0) return;                                             // (ntiles64 not a multiple of VT_GN: grid is rounded up)
-    const int kblocks = (bn + 1) * (VT_N / VT_KB);                  // L^-1 is lower triangular: k <= column tile
-    const I8Pipe pp = i8_pipe_setup(smem_raw);
-    const uint32_t tmem_base = pp.tmem_base, accum = pp.accum;
-    if (warp == 0 && lane == 0)
-        i8_pipe_produce(pp, p.Aimg + (size_t)bm * p.nkb * VT_A_STAGE, p.Bimg + (size_t)bn * p.nkb * VT_B_STAGE, kblocks, p.flag);
-    else if (warp == 1 && lane == 0)
-        i8_pipe_mma(pp, kblocks, p.flag);
-    __syncwarp();
-    if (warp >= 2) {                         // ---- epilogue: FP64 recombination of the 7 weight groups, column scale, row sum of squares ----
-        const bool ok = mbar_wait(accum, 0, p.flag);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int q = warp & 3;              // TMEM lane quarter this warp may access
-        const double os = p.hyp[0];
-        double ssq = 0.0;
-#pragma unroll
-        for (int ch = 0; ch < VT_N / 32; ch++) {
-            double v[32];
-#pragma unroll
-            for (int j = 0; j < 32; j++) v[j] = 0.0;
-#pragma unroll
-            for (int g = I8_S - 1; g >= 0; g--) {      // smallest weights first
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + g * VT_N + ch * 32, r);
-                const double w = i8_group_weight(g);
-#pragma unroll
-                for (int j = 0; j < 32; j++) v[j] = fma(w, (double)(int32_t)r[j], v[j]);
-            }
-            const double* cs = p.colscale + bn * VT_N + ch * 32;
-#pragma unroll
-            for (int j = 0; j < 32; j++) { const double x = v[j] * (os * cs[j]); ssq = fma(x, x, ssq); }
-        }
-        if (!ok) ssq = __longlong_as_double(0x7ff8000000000000LL);
-        p.varpart[(size_t)bn * p.rows_pad + bm * VT_M + q * 32 + lane] = ssq;
-    }
-    i8_pipe_teardown(pp);
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
-// Digit images of centred, lengthscale-scaled input rows (candidates: ROWS = 128 per tile, the A side; training points:
-// ROWS = 64, the B side).  One warp per row: zs_j = (x_j - c_j) / l_j, row scale 2^e >= max |zs|, digits of zs 2^-e; the
-// k-range is padded with zeros to a multiple of 32.  norms (optional) = sum_j zs_j^2 in FP64.
-template <int ROWS>
-__global__ void k_slice_rows(const double* __restrict__ X, long long ldx, int rows_valid, int rows_pad, int d,
-                             const double* __restrict__ center, const double* __restrict__ inv_ls, int8_t* __restrict__ img,
-                             double* __restrict__ scale, double* __restrict__ norms) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= rows_pad) return;
-    const int nkb = (d + 31) >> 5, tile = row / ROWS, r = row % ROWS;
-    const bool live = row < rows_valid;
-    const double* src = X + (size_t)row * ldx;
-    double mx = 0.0, ss = 0.0;
-    if (live)
-        for (int j = lane; j < d; j += 32) { const double z = (src[j] - center[j]) * inv_ls[j]; mx = fmax(mx, fabs(z)); ss = fma(z, z, ss); }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
-    int ex = 0;
-    if (mx > 0.0) frexp(mx, &ex);
-    const double down = ldexp(1.0, I8_FRAC_BITS - ex);
-    if (lane == 0) { scale[row] = ldexp(1.0, ex); if (norms) norms[row] = ss; }
-    const int inrow = (((lane >> 4) ^ ((r >> 2) & 1)) << 4) | (lane & 15);   // SWIZZLE_32B position of k = lane inside the 32-byte row
-    for (int kb = 0; kb < nkb; kb++) {
-        const int j = kb * 32 + lane;
-        long long x = 0;
-        if (live && j < d) x = __double2ll_rn((src[j] - center[j]) * inv_ls[j] * down);
-        signed char dg[I8_S];
-        i8_digits(x, dg);
-        int8_t* dst = img + ((size_t)tile * nkb + kb) * (I8_S * ROWS * 32) + r * 32 + inrow;
-#pragma unroll
-        for (int t = 0; t < I8_S; t++) dst[t * ROWS * 32] = dg[t];
-    }
-}
-
-cudaError_t launch_slice_rows(int rows_per_tile, const double* X, long long ldx, int rows_valid, int rows_pad, int d, const double* center,
-                              const double* inv_ls, int8_t* img, double* scale, double* norms, cudaStream_t st) {
-    if (rows_pad == 0) return cudaSuccess;
-    const int grid = (rows_pad + 7) / 8;
-    if (rows_per_tile == 128) k_slice_rows<128><<<grid, 256, 0, st>>>(X, ldx, rows_valid, rows_pad, d, center, inv_ls, img, scale, norms);
-    else k_slice_rows<64><<<grid, 256, 0, st>>>(X, ldx, rows_valid, rows_pad, d, center, inv_ls, img, scale, norms);
-    return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// K*(Z, X) on the int8 tensor cores: the scaled-candidate x scaled-train inner products as 28 exact digit-pair GEMMs (same
-// pipeline as k_var_i8, K = roundup(d, 32)), then per element  r2 = |z|^2 + |x|^2 - 2 z.x  ->  k(r2)  ->  the 7 digits of
-// k (the A operand of k_var_i8, written straight into its tile images: a thread owns one candidate row, i.e. whole 16-byte
-// halves of image rows) and the partial posterior mean over this tile's 64 training points.
+// K*(Z, X) on the int8 tensor cores: the scaled-candidate x scaled-train inner products as 21 exact digit-pair GEMMs
+// (K = roundup(d, 32)), then per element  r2 = |z|^2 + |x|^2 - 2 z.x  ->  k(r2)  ->  the 6 bytes of rint(k 2^48) (the A operand
+// of k_var_i8, written straight into its tile images: a thread owns one candidate row, i.e. whole 16-byte halves of image rows)
+// and the partial posterior mean over this tile's 64 training points.
 struct CrossI8Params {
     const int8_t* Zimg;       // candidate digit images (tile = 128 rows), nkb_d k-blocks
     const int8_t* Ximg;       // training-point digit images (tile = 64 rows)
@@ -320,8 +264,7 @@ struct CrossI8Params {
     int* flag;
 };
 
-// 320 threads: warp 0 producer, warp 1 MMA issuer, warps 2-9 epilogue (two warps per TMEM lane quarter, 32 columns each: the
-// FP64-heavy epilogue needs two warps per scheduler to hide its dependent-issue latency).
+// 320 threads: warp 0 producer, warp 1 MMA issuer, warps 2-9 epilogue (two warps per TMEM lane quarter, 32 columns each).
 template <int KIND>
 __global__ void __launch_bounds__(320, 1) k_cross_i8(CrossI8Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -336,7 +279,7 @@ __global__ void __launch_bounds__(320, 1) k_cross_i8(CrossI8Params p) {
     if (warp == 0 && lane == 0)
         i8_pipe_produce(pp, p.Zimg + (size_t)bm * p.nkb_d * VT_A_STAGE, p.Ximg + (size_t)bn * p.nkb_d * VT_B_STAGE, p.nkb_d, p.flag);
     else if (warp == 1 && lane == 0)
-        i8_pipe_mma(pp, p.nkb_d, p.flag);
+        i8_pipe_mma<true>(pp, p.nkb_d, p.flag);
     __syncwarp();
     if (warp >= 2) {
         const bool ok = mbar_wait(pp.accum, 0, p.flag);
@@ -352,48 +295,39 @@ __global__ void __launch_bounds__(320, 1) k_cross_i8(CrossI8Params p) {
 #pragma unroll
             for (int j = 0; j < 16; j++) v[j] = 0.0;
 #pragma unroll
-            for (int g = I8_S - 1; g >= 0; g--) {          // smallest weights first
+            for (int g = I8_S - 1; g >= 0; g--) {          // smallest weights first; signed x signed: 2^-(8g+14)
                 uint32_t rr[16];
                 tmem_ld16(pp.tmem_base + ((uint32_t)(q * 32) << 16) + g * VT_N + gi * 16, rr);
-                const double w = i8_group_weight(g);
+                const double w = i8_pow2(-(8 * g + 14));
 #pragma unroll
                 for (int j = 0; j < 16; j++) v[j] = fma(w, (double)(int32_t)rr[j], v[j]);
             }
             uint32_t dg[I8_S][4];
 #pragma unroll
-            for (int t = 0; t < I8_S; t++)
+            for (int jq = 0; jq < 4; jq++) {               // 4 columns -> one 32-bit word of every digit plane
+                unsigned lo[4], hi[4];
 #pragma unroll
-                for (int w4 = 0; w4 < 4; w4++) dg[t][w4] = 0u;
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-                const int cl = gi * 16 + j;
-                const double r2 = fmax(fma(v[j] * m2sz, s_xs[cl], znr + s_xn[cl]), 0.0);
-                double k, dk;
-                kernel_eval(KIND, r2, k, dk);
-                const bool valid = rowvalid && (bn * VT_N + cl) < p.n;      // padding rows / columns are exact zeros
-                const double kq = valid ? k : 0.0;
-                msum = fma(os * kq, s_al[cl], msum);
-                const unsigned long long y = (unsigned long long)(__double2ll_rn(kq * 281474976710656.0) + I8_LOW_BIAS);
-                const unsigned lo = (unsigned)y, hi = (unsigned)(y >> 32);
-                const int sh = (j & 3) * 8;
-                dg[6][j >> 2] |= (lo & 127u) << sh;
-                dg[5][j >> 2] |= ((lo >> 7) & 127u) << sh;
-                dg[4][j >> 2] |= ((lo >> 14) & 127u) << sh;
-                dg[3][j >> 2] |= ((lo >> 21) & 127u) << sh;
-                dg[2][j >> 2] |= (__funnelshift_r(lo, hi, 28) & 127u) << sh;
-                dg[1][j >> 2] |= ((hi >> 3) & 127u) << sh;
-                dg[0][j >> 2] |= (hi >> 10) << sh;
+                for (int e = 0; e < 4; e++) {
+                    const int cl = gi * 16 + jq * 4 + e;
+                    const double r2 = fmax(fma(v[jq * 4 + e] * m2sz, s_xs[cl], znr + s_xn[cl]), 0.0);
+                    double k, dk;
+                    kernel_eval(KIND, r2, k, dk);
+                    const bool valid = rowvalid && (bn * VT_N + cl) < p.n;      // padding rows / columns are exact zeros
+                    const double kq = valid ? k : 0.0;
+                    msum = fma(os * kq, s_al[cl], msum);
+                    const unsigned long long X = min(__double2ull_rn(kq * 281474976710656.0), 0xFFFFFFFFFFFFULL);   // rint(k 2^48)
+                    lo[e] = (unsigned)X; hi[e] = (unsigned)(X >> 32);
+                }
+                // byte b of the four values -> one word (3 PRMT each)
+#define HDBO_GATHER(SRC, SEL) __byte_perm(__byte_perm(SRC[0], SRC[1], SEL), __byte_perm(SRC[2], SRC[3], SEL), 0x5410)
+                dg[5][jq] = HDBO_GATHER(lo, 0x0040); dg[4][jq] = HDBO_GATHER(lo, 0x0051);
+                dg[3][jq] = HDBO_GATHER(lo, 0x0062); dg[2][jq] = HDBO_GATHER(lo, 0x0073);
+                dg[1][jq] = HDBO_GATHER(hi, 0x0040); dg[0][jq] = HDBO_GATHER(hi, 0x0051);
+#undef HDBO_GATHER
             }
             int8_t* dst = p.Kimg + ((size_t)bm * p.nkb_n + bn * 2 + (gi >> 1)) * VT_A_STAGE + row * 32 + (((gi & 1) ^ swz) << 4);
 #pragma unroll
-            for (int t = 0; t < I8_S; t++) {
-                uint4 o = make_uint4(dg[t][0], dg[t][1], dg[t][2], dg[t][3]);
-                if (t) {                                   // d_t = f_t - 64: the 7-bit field ^ 0x40, sign-extended (see k_cross)
-                    o.x ^= 0x40404040u; o.x |= (o.x & 0x40404040u) << 1;  o.y ^= 0x40404040u; o.y |= (o.y & 0x40404040u) << 1;
-                    o.z ^= 0x40404040u; o.z |= (o.z & 0x40404040u) << 1;  o.w ^= 0x40404040u; o.w |= (o.w & 0x40404040u) << 1;
-                }
-                *reinterpret_cast<uint4*>(dst + t * VT_M * 32) = o;
-            }
+            for (int t = 0; t < I8_S; t++) *reinterpret_cast<uint4*>(dst + t * VT_M * 32) = make_uint4(dg[t][0], dg[t][1], dg[t][2], dg[t][3]);
         }
         if (!ok) msum = __longlong_as_double(0x7ff8000000000000LL);
         if (half) s_ms[row] = msum;
@@ -421,6 +355,80 @@ cudaError_t launch_cross_i8(int kind, const int8_t* Zimg, const int8_t* Ximg, co
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// V = K* L^-T and its row sums of squares.  192 threads (4 epilogue warps).  Triangular k-range (L^-1 is lower triangular: only
+// k-blocks <= column tile), heavy tiles first.
+struct VarI8Params {
+    const int8_t* Aimg;       // K* digit images (unsigned bytes), tile = 128 candidates
+    const int8_t* Bimg;       // L^-1 digit images (balanced), tile = 64 rows of L^-1 (= columns of V)
+    const double* colscale;   // [n_pad] 2^e_i of the L^-1 row = column of V
+    const double* hyp;        // outputscale at [0]
+    double* varpart;          // [ntiles64][rows_pad]
+    int rows_pad, ntiles64, mtiles, nkb;
+    int* flag;                // set when a barrier wait timed out (results are then poisoned with NaN)
+};
+
+__global__ void __launch_bounds__(192, 1) k_var_i8(VarI8Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // Rasterisation: consecutive CTAs (one wave of 148) cover VT_GN column tiles x ~9 row tiles, so every A (K* digit) tile is
+    // fetched from DRAM once per VT_GN column tiles instead of once per column tile (the A images of a chunk are 4x the L2).
+    // Column-tile groups with the longest k-range come first (heavy-first).
+    const int per_group = p.mtiles * VT_GN;
+    const int grp = blockIdx.x / per_group, rem = blockIdx.x - grp * per_group;
+    const int bm = rem / VT_GN, bn = p.ntiles64 - 1 - (grp * VT_GN + rem % VT_GN);
+    if (bn < 0) return;                                             // (ntiles64 not a multiple of VT_GN: grid is rounded up)
+    const int kblocks = (bn + 1) * (VT_N / VT_KB);
+    const I8Pipe pp = i8_pipe_setup(smem_raw);
+    if (warp == 0 && lane == 0)
+        i8_pipe_produce(pp, p.Aimg + (size_t)bm * p.nkb * VT_A_STAGE, p.Bimg + (size_t)bn * p.nkb * VT_B_STAGE, kblocks, p.flag);
+    else if (warp == 1 && lane == 0)
+        i8_pipe_mma<false>(pp, kblocks, p.flag);
+    __syncwarp();
+    if (warp >= 2) {                         // ---- epilogue: FP64 recombination of the 6 weight groups, column scale, row sum of squares ----
+        const bool ok = mbar_wait(pp.accum, 0, p.flag);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;              // TMEM lane quarter this warp may access
+        const double os = p.hyp[0];
+        double ssq = 0.0;
+#pragma unroll
+        for (int ch = 0; ch < VT_N / 32; ch++) {
+            double v[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = 0.0;
+#pragma unroll
+            for (int g = I8_S - 1; g >= 0; g--) {      // smallest weights first; unsigned x signed: 2^-(8g+15)
+                uint32_t r[32];
+                tmem_ld32(pp.tmem_base + ((uint32_t)(q * 32) << 16) + g * VT_N + ch * 32, r);
+                const double w = i8_pow2(-(8 * g + 15));
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = fma(w, (double)(int32_t)r[j], v[j]);
+            }
+            const double* cs = p.colscale + bn * VT_N + ch * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j++) { const double x = v[j] * (os * cs[j]); ssq = fma(x, x, ssq); }
+        }
+        if (!ok) ssq = __longlong_as_double(0x7ff8000000000000LL);
+        p.varpart[(size_t)bn * p.rows_pad + bm * VT_M + q * 32 + lane] = ssq;
+    }
+    i8_pipe_teardown(pp);
+}
+
+// Aimg: K* digit images for rows_pad / 128 row tiles; Bimg: L^-1 digit images (layout at the top of this file)
+cudaError_t launch_var_i8(const int8_t* Aimg, int rows_pad, const int8_t* Bimg, const double* colscale, const double* hyp,
+                          int n_pad, double* varpart, int* flag, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_var_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const int mt = rows_pad / VT_M, nt = n_pad / VT_N, groups = (nt + VT_GN - 1) / VT_GN;
+    VarI8Params p{Aimg, Bimg, colscale, hyp, varpart, rows_pad, nt, mt, n_pad / VT_KB, flag};
+    k_var_i8<<<mt * VT_GN * groups, 192, VT_SMEM, st>>>(p);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // int8 tensor-pipe ceiling, measured live (bench.py roofline denominator): every CTA issues `iters` x 8 resident-operand MMAs
 // (M = 128, N = 256, K = 32, pseudo-random digits in shared memory, no global traffic) and waits for the last commit.
 __global__ void __launch_bounds__(128, 1) k_i8_peak(int iters, int* flag) {
@@ -444,7 +452,7 @@ __global__ void __launch_bounds__(128, 1) k_i8_peak(int iters, int* flag) {
         const uint64_t ad = make_desc_sw32(smem_u32(base)), bd = make_desc_sw32(smem_u32(base + 4096));
         for (int it = 0; it < iters; it++) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) umma_i8(tmem_base + (j & 1) * 256, ad, bd, idesc_i8(256), (uint32_t)(it != 0));
+            for (int j = 0; j < 8; j++) umma_i8(tmem_base + (j & 1) * 256, ad, bd, idesc_i8(256, true), (uint32_t)(it != 0));
         }
         umma_commit(smem_u32(bar));
         mbar_wait(smem_u32(bar), 0, flag);
@@ -458,21 +466,6 @@ cudaError_t launch_i8_peak(int iters, int sms, int* flag, double* ops_out, cudaS
     constexpr int SM = 16384 + 64 + 1024;
     k_i8_peak<<<sms, 128, SM, st>>>(iters, flag);
     if (ops_out) *ops_out = 2.0 * 128 * 256 * 32 * 8.0 * iters * sms;
-    return cudaGetLastError();
-}
-
-// Aimg: K* digit images for rows_pad / 128 row tiles; Bimg: L^-1 digit images (layout at the top of this file)
-cudaError_t launch_var_i8(const int8_t* Aimg, int rows_pad, const int8_t* Bimg, const double* colscale, const double* hyp,
-                          int n_pad, double* varpart, int* flag, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_var_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
-    const int mt = rows_pad / VT_M, nt = n_pad / VT_N, groups = (nt + VT_GN - 1) / VT_GN;
-    VarI8Params p{Aimg, Bimg, colscale, hyp, varpart, rows_pad, nt, mt, n_pad / VT_KB, flag};
-    k_var_i8<<<mt * VT_GN * groups, 192, VT_SMEM, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -140,7 +140,7 @@ def test_i8_c_abi_argument_checks(cuda_device):
     assert lib.hdbo_i8_state_bytes(C.byref(gpb.desc)) == 0
     gp = _gp(X, y, O.MATERN52, (ls, os_, nz, mu), cuda_device, "i8")
     need = lib.hdbo_i8_state_bytes(C.byref(gp.desc))
-    assert need == 7 * 128 * 128 + 8 * 128 + 7 * 128 * 32 + 8 * 128 + 16   # L^-1 images + scales, X images + scales, flag
+    assert need == 6 * 128 * 128 + 8 * 128 + 6 * 128 * 32 + 8 * 128 + 16   # L^-1 images + scales, X images + scales, flag
     state = torch.empty(need + 256, dtype=torch.uint8, device=cuda_device)
     assert lib.hdbo_gp_slice_linv(C.byref(gp.desc), state.data_ptr() + 8, 0) == -2      # misaligned state
     assert lib.hdbo_gp_slice_linv(C.byref(gp.desc), 0, 0) == -2
