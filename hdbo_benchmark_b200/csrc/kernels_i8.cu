@@ -119,7 +119,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 // bounded wait: a protocol bug becomes a NaN result (flag) instead of a hung GPU
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* flag) {
-    for (long i = 0; i < 200000000L; i++) {
+    for (long i = 0; i < 20000000L; i++) {
         uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
@@ -174,23 +174,29 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Pipeline shared by k_var_i8 and k_cross_i8: warp 0 = producer, warp 1 = MMA issuer, warps >= 2 = epilogue.
+// Pipeline shared by k_var_i8 and k_cross_i8.  PERSISTENT kernels: one CTA per SM walks a static list of tiles
+// (t = blockIdx.x, + gridDim.x, ...); warp 0 = producer, warp 1 = MMA issuer, warps >= 2 = epilogue.  The operand ring keeps
+// running across tile boundaries (the producer prefetches the next tile's k-blocks while the epilogue of the current one runs), the
+// MMA issuer starts the next tile as soon as the epilogue warps have drained TMEM (`tmem_empty`), so TMEM allocation, barrier
+// set-up, pipeline fill and most of the epilogue are off the critical path.
 struct I8Pipe {
     uint8_t *As, *Bs;
-    uint32_t full0, empty0, accum, tmem_base;
+    uint32_t full0, empty0, accum, tmem_empty, tmem_base;
 };
 
-__device__ __forceinline__ I8Pipe i8_pipe_setup(uint8_t* smem_raw) {
+__device__ __forceinline__ I8Pipe i8_pipe_setup(uint8_t* smem_raw, int epilogue_warps) {
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     I8Pipe pp;
     pp.As = base;
     pp.Bs = base + VT_STAGES * VT_A_STAGE;
     uint64_t* bars = (uint64_t*)(base + VT_STAGES * (VT_A_STAGE + VT_B_STAGE));
     pp.full0 = smem_u32(bars); pp.empty0 = smem_u32(bars + VT_STAGES); pp.accum = smem_u32(bars + 2 * VT_STAGES);
-    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * VT_STAGES + 1);
+    pp.tmem_empty = smem_u32(bars + 2 * VT_STAGES + 1);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * VT_STAGES + 2);
     if (threadIdx.x == 0) {
         for (int s = 0; s < VT_STAGES; s++) { mbar_init(pp.full0 + 8 * s, 1); mbar_init(pp.empty0 + 8 * s, 1); }
         mbar_init(pp.accum, 1);
+        mbar_init(pp.tmem_empty, epilogue_warps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if ((threadIdx.x >> 5) == 1) {
@@ -210,27 +216,31 @@ __device__ __forceinline__ void i8_pipe_teardown(const I8Pipe& pp) {
     if ((threadIdx.x >> 5) == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(pp.tmem_base), "r"(512) : "memory");
 }
 
-// producer (one thread): two bulk copies per k-block, images asrc[kb], bsrc[kb]
-__device__ __forceinline__ void i8_pipe_produce(const I8Pipe& pp, const int8_t* asrc, const int8_t* bsrc, int kblocks, int* flag) {
-    for (int kb = 0; kb < kblocks; kb++) {
-        const int s = kb % VT_STAGES, ph = (kb / VT_STAGES) & 1;
-        if (!mbar_wait(pp.empty0 + 8 * s, ph ^ 1, flag)) break;
+// producer (one thread): two bulk copies per k-block, images asrc[kb], bsrc[kb]; kbg = running k-block count of this CTA
+__device__ __forceinline__ bool i8_pipe_produce(const I8Pipe& pp, const int8_t* asrc, const int8_t* bsrc, int kblocks, uint32_t& kbg, int* flag) {
+    for (int kb = 0; kb < kblocks; kb++, kbg++) {
+        const uint32_t s = kbg % VT_STAGES, ph = (kbg / VT_STAGES) & 1;
+        if (!mbar_wait(pp.empty0 + 8 * s, ph ^ 1, flag)) return false;
         mbar_expect_tx(pp.full0 + 8 * s, VT_A_STAGE + VT_B_STAGE);
         bulk_load(smem_u32(pp.As + s * VT_A_STAGE), asrc + (size_t)kb * VT_A_STAGE, VT_A_STAGE, pp.full0 + 8 * s);
         bulk_load(smem_u32(pp.Bs + s * VT_B_STAGE), bsrc + (size_t)kb * VT_B_STAGE, VT_B_STAGE, pp.full0 + 8 * s);
     }
+    return true;
 }
 
-// MMA issuer (one thread).  The B planes t0..t0+c-1 of a stage are contiguous (64 rows x 32 B each), i.e. ONE K-major operand with
-// N = 64 c rows, and the accumulators of the weight groups g = s + t are adjacent 64-column blocks of TMEM: digit plane s of A
-// against planes t0.. of B is a single MMA with N = 64 c writing groups s+t0...  8 MMAs (N <= 256) instead of 21 per k-block: the
-// 4 KB A plane is read from shared memory 8 instead of 21 times (SS-mode operand reads were the limiter of the unmerged version:
-// 192 B/clk needed for N = 64 against 128 B/clk of shared-memory bandwidth).
+// MMA issuer (one thread), one tile.  The B planes t0..t0+c-1 of a stage are contiguous (64 rows x 32 B each), i.e. ONE K-major
+// operand with N = 64 c rows, and the accumulators of the weight groups g = s + t are adjacent 64-column blocks of TMEM: digit
+// plane s of A against planes t0.. of B is a single MMA with N = 64 c writing groups s+t0...  8 MMAs (N <= 256) instead of 21 per
+// k-block: the 4 KB A plane is read from shared memory 8 instead of 21 times (SS-mode operand reads were the limiter of the
+// unmerged version: 192 B/clk needed for N = 64 against 128 B/clk of shared-memory bandwidth).
+// `tile_it` = how many tiles this CTA has finished: the accumulators may be overwritten once the epilogue has drained them.
 template <bool A_SIGNED>
-__device__ __forceinline__ void i8_pipe_mma(const I8Pipe& pp, int kblocks, int* flag) {
-    for (int kb = 0; kb < kblocks; kb++) {
-        const int s = kb % VT_STAGES, ph = (kb / VT_STAGES) & 1;
-        if (!mbar_wait(pp.full0 + 8 * s, ph, flag)) break;
+__device__ __forceinline__ bool i8_pipe_mma(const I8Pipe& pp, int kblocks, uint32_t& kbg, uint32_t tile_it, int* flag) {
+    if (tile_it > 0 && !mbar_wait(pp.tmem_empty, (tile_it - 1) & 1, flag)) return false;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int kb = 0; kb < kblocks; kb++, kbg++) {
+        const uint32_t s = kbg % VT_STAGES, ph = (kbg / VT_STAGES) & 1;
+        if (!mbar_wait(pp.full0 + 8 * s, ph, flag)) return false;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a0 = smem_u32(pp.As + s * VT_A_STAGE), b0 = smem_u32(pp.Bs + s * VT_B_STAGE);
         const uint32_t acc = kb != 0;
@@ -247,6 +257,29 @@ __device__ __forceinline__ void i8_pipe_mma(const I8Pipe& pp, int kblocks, int* 
         umma_commit(pp.empty0 + 8 * s);
     }
     umma_commit(pp.accum);
+    return true;
+}
+
+// epilogue warps: the accumulators of this CTA's tile number `tile_it` are complete
+__device__ __forceinline__ bool i8_pipe_wait_accum(const I8Pipe& pp, uint32_t tile_it, int* flag) {
+    const bool ok = mbar_wait(pp.accum, tile_it & 1, flag);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    return ok;
+}
+// epilogue warps (all lanes): this warp has read everything it needs from TMEM
+__device__ __forceinline__ void i8_pipe_release_tmem(const I8Pipe& pp) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pp.tmem_empty) : "memory");
+}
+
+static int i8_sm_count() {
+    static int sms = [] {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        return n;
+    }();
+    return sms;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -260,79 +293,94 @@ struct CrossI8Params {
     const double *zscale, *xscale, *zn, *xn, *alpha, *hyp;
     int8_t* Kimg;             // out: K*/outputscale digit images (tile = 128 rows, n_pad / 32 k-blocks)
     double* meanpart;         // out: [ntiles64][rows_pad]
-    int m, n, rows_pad, ntiles64, nkb_d, nkb_n;
+    int m, n, rows_pad, ntiles64, ntiles, nkb_d, nkb_n;
     int* flag;
 };
 
 // 320 threads: warp 0 producer, warp 1 MMA issuer, warps 2-9 epilogue (two warps per TMEM lane quarter, 32 columns each).
+// The epilogue first turns its 32 columns of the 6 accumulator groups into 32 FP64 inner products (registers) and releases
+// TMEM; the FP64-heavy part (distance -> kernel -> digits) then overlaps the MMAs of the CTA's next tile.
 template <int KIND>
 __global__ void __launch_bounds__(320, 1) k_cross_i8(CrossI8Params p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ double s_xn[VT_N], s_xs[VT_N], s_al[VT_N], s_ms[VT_M];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int bn = blockIdx.x % p.ntiles64, bm = blockIdx.x / p.ntiles64;
-    if (tid >= 64 && tid < 64 + VT_N) {
-        const int c = bn * VT_N + tid - 64;
-        s_xn[tid - 64] = p.xn[c]; s_xs[tid - 64] = p.xscale[c]; s_al[tid - 64] = p.alpha[c];
+    const I8Pipe pp = i8_pipe_setup(smem_raw, 8);
+    if (warp == 0 && lane == 0) {
+        uint32_t kbg = 0;
+        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+            const int bn = t % p.ntiles64, bm = t / p.ntiles64;
+            if (!i8_pipe_produce(pp, p.Zimg + (size_t)bm * p.nkb_d * VT_A_STAGE, p.Ximg + (size_t)bn * p.nkb_d * VT_B_STAGE, p.nkb_d, kbg, p.flag)) break;
+        }
+    } else if (warp == 1 && lane == 0) {
+        uint32_t kbg = 0, it = 0;
+        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, it++)
+            if (!i8_pipe_mma<true>(pp, p.nkb_d, kbg, it, p.flag)) break;
     }
-    const I8Pipe pp = i8_pipe_setup(smem_raw);   // (contains the __syncthreads that publishes s_xn / s_xs / s_al)
-    if (warp == 0 && lane == 0)
-        i8_pipe_produce(pp, p.Zimg + (size_t)bm * p.nkb_d * VT_A_STAGE, p.Ximg + (size_t)bn * p.nkb_d * VT_B_STAGE, p.nkb_d, p.flag);
-    else if (warp == 1 && lane == 0)
-        i8_pipe_mma<true>(pp, p.nkb_d, p.flag);
     __syncwarp();
     if (warp >= 2) {
-        const bool ok = mbar_wait(pp.accum, 0, p.flag);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int q = warp & 3, half = (warp - 2) >> 2, row = q * 32 + lane, grow = bm * VT_M + row;
-        const double os = p.hyp[0], znr = p.zn[grow], m2sz = -2.0 * p.zscale[grow];
-        const bool rowvalid = grow < p.m;
+        const int q = warp & 3, half = (warp - 2) >> 2, row = q * 32 + lane;
         const int swz = (row >> 2) & 1;
-        double msum = 0.0;
-#pragma unroll 1
-        for (int gi = 2 * half; gi < 2 * half + 2; gi++) {   // 16 columns at a time = one 16-byte half of an image row per plane
-            double v[16];
+        const double os = p.hyp[0];
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, it++) {
+            const int bn = t % p.ntiles64, bm = t / p.ntiles64, grow = bm * VT_M + row;
+            if (tid >= 64 && tid < 64 + VT_N) {            // (the previous tile's readers passed the s_ms barrier below)
+                const int c = bn * VT_N + tid - 64;
+                s_xn[tid - 64] = p.xn[c]; s_xs[tid - 64] = p.xscale[c]; s_al[tid - 64] = p.alpha[c];
+            }
+            const double znr = p.zn[grow], m2sz = -2.0 * p.zscale[grow];
+            const bool rowvalid = grow < p.m;
+            const bool ok = i8_pipe_wait_accum(pp, it, p.flag);
+            double v[32];
 #pragma unroll
-            for (int j = 0; j < 16; j++) v[j] = 0.0;
+            for (int j = 0; j < 32; j++) v[j] = 0.0;
 #pragma unroll
             for (int g = I8_S - 1; g >= 0; g--) {          // smallest weights first; signed x signed: 2^-(8g+14)
-                uint32_t rr[16];
-                tmem_ld16(pp.tmem_base + ((uint32_t)(q * 32) << 16) + g * VT_N + gi * 16, rr);
+                uint32_t rr[32];
+                tmem_ld32(pp.tmem_base + ((uint32_t)(q * 32) << 16) + g * VT_N + half * 32, rr);
                 const double w = i8_pow2(-(8 * g + 14));
 #pragma unroll
-                for (int j = 0; j < 16; j++) v[j] = fma(w, (double)(int32_t)rr[j], v[j]);
+                for (int j = 0; j < 32; j++) v[j] = fma(w, (double)(int32_t)rr[j], v[j]);
             }
-            uint32_t dg[I8_S][4];
+            i8_pipe_release_tmem(pp);                      // the MMA issuer may start this CTA's next tile
+            asm volatile("bar.sync 1, 256;" ::: "memory"); // s_xn / s_xs / s_al of this tile are in place
+            double msum = 0.0;
 #pragma unroll
-            for (int jq = 0; jq < 4; jq++) {               // 4 columns -> one 32-bit word of every digit plane
-                unsigned lo[4], hi[4];
+            for (int gq = 0; gq < 2; gq++) {               // 16 columns = one 16-byte half of an image row per plane
+                uint32_t dg[I8_S][4];
 #pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const int cl = gi * 16 + jq * 4 + e;
-                    const double r2 = fmax(fma(v[jq * 4 + e] * m2sz, s_xs[cl], znr + s_xn[cl]), 0.0);
-                    double k, dk;
-                    kernel_eval(KIND, r2, k, dk);
-                    const bool valid = rowvalid && (bn * VT_N + cl) < p.n;      // padding rows / columns are exact zeros
-                    const double kq = valid ? k : 0.0;
-                    msum = fma(os * kq, s_al[cl], msum);
-                    const unsigned long long X = min(__double2ull_rn(kq * 281474976710656.0), 0xFFFFFFFFFFFFULL);   // rint(k 2^48)
-                    lo[e] = (unsigned)X; hi[e] = (unsigned)(X >> 32);
-                }
-                // byte b of the four values -> one word (3 PRMT each)
+                for (int jq = 0; jq < 4; jq++) {           // 4 columns -> one 32-bit word of every digit plane
+                    unsigned lo[4], hi[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int cl = half * 32 + gq * 16 + jq * 4 + e;
+                        const double r2 = fmax(fma(v[gq * 16 + jq * 4 + e] * m2sz, s_xs[cl], znr + s_xn[cl]), 0.0);
+                        double k, dk;
+                        kernel_eval(KIND, r2, k, dk);
+                        const bool valid = rowvalid && (bn * VT_N + cl) < p.n;      // padding rows / columns are exact zeros
+                        const double kq = valid ? k : 0.0;
+                        msum = fma(os * kq, s_al[cl], msum);
+                        const unsigned long long X = min(__double2ull_rn(kq * 281474976710656.0), 0xFFFFFFFFFFFFULL);   // rint(k 2^48)
+                        lo[e] = (unsigned)X; hi[e] = (unsigned)(X >> 32);
+                    }
+                    // byte b of the four values -> one word (3 PRMT each)
 #define HDBO_GATHER(SRC, SEL) __byte_perm(__byte_perm(SRC[0], SRC[1], SEL), __byte_perm(SRC[2], SRC[3], SEL), 0x5410)
-                dg[5][jq] = HDBO_GATHER(lo, 0x0040); dg[4][jq] = HDBO_GATHER(lo, 0x0051);
-                dg[3][jq] = HDBO_GATHER(lo, 0x0062); dg[2][jq] = HDBO_GATHER(lo, 0x0073);
-                dg[1][jq] = HDBO_GATHER(hi, 0x0040); dg[0][jq] = HDBO_GATHER(hi, 0x0051);
+                    dg[5][jq] = HDBO_GATHER(lo, 0x0040); dg[4][jq] = HDBO_GATHER(lo, 0x0051);
+                    dg[3][jq] = HDBO_GATHER(lo, 0x0062); dg[2][jq] = HDBO_GATHER(lo, 0x0073);
+                    dg[1][jq] = HDBO_GATHER(hi, 0x0040); dg[0][jq] = HDBO_GATHER(hi, 0x0051);
 #undef HDBO_GATHER
-            }
-            int8_t* dst = p.Kimg + ((size_t)bm * p.nkb_n + bn * 2 + (gi >> 1)) * VT_A_STAGE + row * 32 + (((gi & 1) ^ swz) << 4);
+                }
+                int8_t* dst = p.Kimg + ((size_t)bm * p.nkb_n + bn * 2 + half) * VT_A_STAGE + row * 32 + ((gq ^ swz) << 4);
 #pragma unroll
-            for (int t = 0; t < I8_S; t++) *reinterpret_cast<uint4*>(dst + t * VT_M * 32) = make_uint4(dg[t][0], dg[t][1], dg[t][2], dg[t][3]);
+                for (int tt = 0; tt < I8_S; tt++)
+                    *reinterpret_cast<uint4*>(dst + tt * VT_M * 32) = make_uint4(dg[tt][0], dg[tt][1], dg[tt][2], dg[tt][3]);
+            }
+            if (!ok) msum = __longlong_as_double(0x7ff8000000000000LL);
+            if (half) s_ms[row] = msum;
+            asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 epilogue warps
+            if (!half) p.meanpart[(size_t)bn * p.rows_pad + grow] = msum + s_ms[row];
         }
-        if (!ok) msum = __longlong_as_double(0x7ff8000000000000LL);
-        if (half) s_ms[row] = msum;
-        asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 epilogue warps
-        if (!half) p.meanpart[(size_t)bn * p.rows_pad + grow] = msum + s_ms[row];
     }
     i8_pipe_teardown(pp);
 }
@@ -347,8 +395,10 @@ cudaError_t launch_cross_i8(int kind, const int8_t* Zimg, const int8_t* Ximg, co
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    CrossI8Params p{Zimg, Ximg, zscale, xscale, zn, xn, alpha, hyp, Kimg, meanpart, m, n, rows_pad, n_pad / VT_N, (d + 31) / 32, n_pad / VT_KB, flag};
-    const int grid = (rows_pad / VT_M) * (n_pad / VT_N);
+    const int ntiles = (rows_pad / VT_M) * (n_pad / VT_N);
+    CrossI8Params p{Zimg, Ximg, zscale, xscale, zn, xn, alpha, hyp, Kimg, meanpart, m, n, rows_pad, n_pad / VT_N, ntiles, (d + 31) / 32,
+                    n_pad / VT_KB, flag};
+    const int grid = ntiles < i8_sm_count() ? ntiles : i8_sm_count();
     if (kind == 0) k_cross_i8<0><<<grid, 320, VT_SMEM, st>>>(p);
     else k_cross_i8<1><<<grid, 320, VT_SMEM, st>>>(p);
     return cudaGetLastError();
@@ -356,59 +406,77 @@ cudaError_t launch_cross_i8(int kind, const int8_t* Zimg, const int8_t* Ximg, co
 
 // ---------------------------------------------------------------------------------------------------------------------
 // V = K* L^-T and its row sums of squares.  192 threads (4 epilogue warps).  Triangular k-range (L^-1 is lower triangular: only
-// k-blocks <= column tile), heavy tiles first.
+// k-blocks <= column tile).
 struct VarI8Params {
     const int8_t* Aimg;       // K* digit images (unsigned bytes), tile = 128 candidates
     const int8_t* Bimg;       // L^-1 digit images (balanced), tile = 64 rows of L^-1 (= columns of V)
     const double* colscale;   // [n_pad] 2^e_i of the L^-1 row = column of V
     const double* hyp;        // outputscale at [0]
     double* varpart;          // [ntiles64][rows_pad]
-    int rows_pad, ntiles64, mtiles, nkb;
+    int rows_pad, ntiles64, mtiles, nkb, nslots;
     int* flag;                // set when a barrier wait timed out (results are then poisoned with NaN)
 };
+
+// Tile list of k_var_i8.  Slots t are rasterised so that tiles processed at the same time by the 148 CTAs (t .. t+147) cover
+// VT_GN column tiles x ~9 row tiles: every A (K* digit) tile is fetched from DRAM once per VT_GN column tiles instead of once per
+// column tile (the A images of a chunk are 4x the L2).  Column-tile groups with the longest k-range come first, and a CTA's
+// slots t, t + 148, ... rotate through the positions of a group (148 mod 16 = 4), which balances the triangular work.
+__device__ __forceinline__ bool var_tile(const VarI8Params& p, int t, int& bm, int& bn) {
+    const int per_group = p.mtiles * VT_GN;
+    const int grp = t / per_group, rem = t - grp * per_group;
+    bm = rem / VT_GN; bn = p.ntiles64 - 1 - (grp * VT_GN + rem % VT_GN);
+    return bn >= 0;                                                 // (ntiles64 not a multiple of VT_GN: empty slots)
+}
 
 __global__ void __launch_bounds__(192, 1) k_var_i8(VarI8Params p) {
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // Rasterisation: consecutive CTAs (one wave of 148) cover VT_GN column tiles x ~9 row tiles, so every A (K* digit) tile is
-    // fetched from DRAM once per VT_GN column tiles instead of once per column tile (the A images of a chunk are 4x the L2).
-    // Column-tile groups with the longest k-range come first (heavy-first).
-    const int per_group = p.mtiles * VT_GN;
-    const int grp = blockIdx.x / per_group, rem = blockIdx.x - grp * per_group;
-    const int bm = rem / VT_GN, bn = p.ntiles64 - 1 - (grp * VT_GN + rem % VT_GN);
-    if (bn < 0) return;                                             // (ntiles64 not a multiple of VT_GN: grid is rounded up)
-    const int kblocks = (bn + 1) * (VT_N / VT_KB);
-    const I8Pipe pp = i8_pipe_setup(smem_raw);
-    if (warp == 0 && lane == 0)
-        i8_pipe_produce(pp, p.Aimg + (size_t)bm * p.nkb * VT_A_STAGE, p.Bimg + (size_t)bn * p.nkb * VT_B_STAGE, kblocks, p.flag);
-    else if (warp == 1 && lane == 0)
-        i8_pipe_mma<false>(pp, kblocks, p.flag);
+    const I8Pipe pp = i8_pipe_setup(smem_raw, 4);
+    int bm, bn;
+    if (warp == 0 && lane == 0) {
+        uint32_t kbg = 0;
+        for (int t = blockIdx.x; t < p.nslots; t += gridDim.x) {
+            if (!var_tile(p, t, bm, bn)) continue;
+            if (!i8_pipe_produce(pp, p.Aimg + (size_t)bm * p.nkb * VT_A_STAGE, p.Bimg + (size_t)bn * p.nkb * VT_B_STAGE,
+                                 (bn + 1) * (VT_N / VT_KB), kbg, p.flag)) break;
+        }
+    } else if (warp == 1 && lane == 0) {
+        uint32_t kbg = 0, it = 0;
+        for (int t = blockIdx.x; t < p.nslots; t += gridDim.x) {
+            if (!var_tile(p, t, bm, bn)) continue;
+            if (!i8_pipe_mma<false>(pp, (bn + 1) * (VT_N / VT_KB), kbg, it++, p.flag)) break;
+        }
+    }
     __syncwarp();
     if (warp >= 2) {                         // ---- epilogue: FP64 recombination of the 6 weight groups, column scale, row sum of squares ----
-        const bool ok = mbar_wait(pp.accum, 0, p.flag);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;              // TMEM lane quarter this warp may access
         const double os = p.hyp[0];
-        double ssq = 0.0;
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < p.nslots; t += gridDim.x) {
+            if (!var_tile(p, t, bm, bn)) continue;
+            const bool ok = i8_pipe_wait_accum(pp, it++, p.flag);
+            double ssq = 0.0;
 #pragma unroll
-        for (int ch = 0; ch < VT_N / 32; ch++) {
-            double v[32];
+            for (int ch = 0; ch < VT_N / 32; ch++) {
+                double v[32];
 #pragma unroll
-            for (int j = 0; j < 32; j++) v[j] = 0.0;
+                for (int j = 0; j < 32; j++) v[j] = 0.0;
 #pragma unroll
-            for (int g = I8_S - 1; g >= 0; g--) {      // smallest weights first; unsigned x signed: 2^-(8g+15)
-                uint32_t r[32];
-                tmem_ld32(pp.tmem_base + ((uint32_t)(q * 32) << 16) + g * VT_N + ch * 32, r);
-                const double w = i8_pow2(-(8 * g + 15));
+                for (int g = I8_S - 1; g >= 0; g--) {      // smallest weights first; unsigned x signed: 2^-(8g+15)
+                    uint32_t r[32];
+                    tmem_ld32(pp.tmem_base + ((uint32_t)(q * 32) << 16) + g * VT_N + ch * 32, r);
+                    const double w = i8_pow2(-(8 * g + 15));
 #pragma unroll
-                for (int j = 0; j < 32; j++) v[j] = fma(w, (double)(int32_t)r[j], v[j]);
+                    for (int j = 0; j < 32; j++) v[j] = fma(w, (double)(int32_t)r[j], v[j]);
+                }
+                if (ch == VT_N / 32 - 1) i8_pipe_release_tmem(pp);
+                const double* cs = p.colscale + bn * VT_N + ch * 32;
+#pragma unroll
+                for (int j = 0; j < 32; j++) { const double x = v[j] * (os * cs[j]); ssq = fma(x, x, ssq); }
             }
-            const double* cs = p.colscale + bn * VT_N + ch * 32;
-#pragma unroll
-            for (int j = 0; j < 32; j++) { const double x = v[j] * (os * cs[j]); ssq = fma(x, x, ssq); }
+            if (!ok) ssq = __longlong_as_double(0x7ff8000000000000LL);
+            p.varpart[(size_t)bn * p.rows_pad + bm * VT_M + q * 32 + lane] = ssq;
         }
-        if (!ok) ssq = __longlong_as_double(0x7ff8000000000000LL);
-        p.varpart[(size_t)bn * p.rows_pad + bm * VT_M + q * 32 + lane] = ssq;
     }
     i8_pipe_teardown(pp);
 }
@@ -423,8 +491,10 @@ cudaError_t launch_var_i8(const int8_t* Aimg, int rows_pad, const int8_t* Bimg, 
         attr_done = true;
     }
     const int mt = rows_pad / VT_M, nt = n_pad / VT_N, groups = (nt + VT_GN - 1) / VT_GN;
-    VarI8Params p{Aimg, Bimg, colscale, hyp, varpart, rows_pad, nt, mt, n_pad / VT_KB, flag};
-    k_var_i8<<<mt * VT_GN * groups, 192, VT_SMEM, st>>>(p);
+    const int nslots = mt * VT_GN * groups;
+    VarI8Params p{Aimg, Bimg, colscale, hyp, varpart, rows_pad, nt, mt, n_pad / VT_KB, nslots, flag};
+    const int grid = mt * nt < i8_sm_count() ? mt * nt : i8_sm_count();
+    k_var_i8<<<grid, 192, VT_SMEM, st>>>(p);
     return cudaGetLastError();
 }
 
