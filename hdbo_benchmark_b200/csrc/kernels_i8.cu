@@ -110,7 +110,10 @@ constexpr int VT_B_STAGE = I8_S * VT_N * VT_KB;                   // 12288
 constexpr int VT_GN = 16;   // rasterisation of k_var_i8: a wave of 148 CTAs covers ~9 row tiles x 16 column tiles
 constexpr int VT_SMEM = VT_STAGES * (VT_A_STAGE + VT_B_STAGE) + 256 + 1024;
 static_assert(VT_A_STAGE == I8_A_IMAGE && VT_B_STAGE == I8_B_IMAGE, "image sizes");
-static_assert(I8_S * VT_N <= 512, "weight groups must fit the 512 TMEM columns");
+static_assert(I8_S * VT_N + 2 * I8_S * 8 <= 512, "weight groups + double-buffered A planes must fit the 512 TMEM columns");
+#ifndef HDBO_VAR_A_TMEM
+#define HDBO_VAR_A_TMEM false   // measured: A planes via tcgen05.cp + TS-mode MMAs are exact but 20 % SLOWER (31.6 -> 38.1 ms per 2^18 pool)
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
@@ -150,6 +153,15 @@ __device__ __forceinline__ constexpr uint32_t idesc_i8(int n, bool a_signed) {
 __device__ __forceinline__ void umma_i8(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// A operand from TMEM (TS mode): no shared-memory read for A at MMA time
+__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_c), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// shared memory -> TMEM: 128 rows x 256 bits (one digit plane of one k-block = 8 TMEM columns)
+__device__ __forceinline__ void utccp_128x256b(uint32_t tmem_dst, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_dst), "l"(sdesc) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -234,7 +246,7 @@ __device__ __forceinline__ bool i8_pipe_produce(const I8Pipe& pp, const int8_t* 
 // k-block: the 4 KB A plane is read from shared memory 8 instead of 21 times (SS-mode operand reads were the limiter of the
 // unmerged version: 192 B/clk needed for N = 64 against 128 B/clk of shared-memory bandwidth).
 // `tile_it` = how many tiles this CTA has finished: the accumulators may be overwritten once the epilogue has drained them.
-template <bool A_SIGNED>
+template <bool A_SIGNED, bool A_TMEM = false>
 __device__ __forceinline__ bool i8_pipe_mma(const I8Pipe& pp, int kblocks, uint32_t& kbg, uint32_t tile_it, int* flag) {
     if (tile_it > 0 && !mbar_wait(pp.tmem_empty, (tile_it - 1) & 1, flag)) return false;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -244,9 +256,18 @@ __device__ __forceinline__ bool i8_pipe_mma(const I8Pipe& pp, int kblocks, uint3
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a0 = smem_u32(pp.As + s * VT_A_STAGE), b0 = smem_u32(pp.Bs + s * VT_B_STAGE);
         const uint32_t acc = kb != 0;
+        // A_TMEM: the 6 A planes of this k-block are first copied to TMEM (columns 384.., double-buffered by k-block parity; the
+        // copy and the MMAs execute in issue order), so the MMAs read only B from shared memory.
+        const uint32_t at0 = pp.tmem_base + I8_S * VT_N + (kbg & 1) * (I8_S * 8);
+        if (A_TMEM) {
+#pragma unroll
+            for (int sa = 0; sa < I8_S; sa++) utccp_128x256b(at0 + sa * 8, make_desc_sw32(a0 + sa * VT_M * VT_KB));
+        }
 #define HDBO_I8_MMA(SA, T0, CNT, ACC)                                                                                         \
-        umma_i8(pp.tmem_base + ((SA) + (T0)) * VT_N, make_desc_sw32(a0 + (SA) * VT_M * VT_KB),                                 \
-                make_desc_sw32(b0 + (T0) * VT_N * VT_KB), idesc_i8((CNT) * VT_N, A_SIGNED), (ACC))
+        if (A_TMEM) umma_i8_ts(pp.tmem_base + ((SA) + (T0)) * VT_N, at0 + (SA) * 8, make_desc_sw32(b0 + (T0) * VT_N * VT_KB), \
+                               idesc_i8((CNT) * VT_N, A_SIGNED), (ACC));                                                      \
+        else umma_i8(pp.tmem_base + ((SA) + (T0)) * VT_N, make_desc_sw32(a0 + (SA) * VT_M * VT_KB),                            \
+                     make_desc_sw32(b0 + (T0) * VT_N * VT_KB), idesc_i8((CNT) * VT_N, A_SIGNED), (ACC))
         HDBO_I8_MMA(0, 0, 4, acc); HDBO_I8_MMA(0, 4, 2, acc);      // plane 0 of A initialises all 6 groups at kb = 0
         HDBO_I8_MMA(1, 0, 4, 1u);  HDBO_I8_MMA(1, 4, 1, 1u);
         HDBO_I8_MMA(2, 0, 4, 1u);
@@ -297,15 +318,18 @@ struct CrossI8Params {
     int* flag;
 };
 
-// 320 threads: warp 0 producer, warp 1 MMA issuer, warps 2-9 epilogue (two warps per TMEM lane quarter, 32 columns each).
-// The epilogue first turns its 32 columns of the 6 accumulator groups into 32 FP64 inner products (registers) and releases
+// 576 threads: warp 0 producer, warp 1 MMA issuer, warps 2-17 epilogue (four warps per TMEM lane quarter, 16 columns each: the
+// FP64 kernel evaluation is a long dependent chain per element, so the epilogue needs 4 warps per scheduler to keep the FP64 and
+// ALU pipes busy -- with 8 warps the issue slots were 38 % used, profiles/r01_ncu_i8_v3.txt).
+// The epilogue first turns its 16 columns of the 6 accumulator groups into 16 FP64 inner products (registers) and releases
 // TMEM; the FP64-heavy part (distance -> kernel -> digits) then overlaps the MMAs of the CTA's next tile.
+constexpr int CE_WARPS = 16, CE_THREADS = 64 + CE_WARPS * 32;
 template <int KIND>
-__global__ void __launch_bounds__(320, 1) k_cross_i8(CrossI8Params p) {
+__global__ void __launch_bounds__(CE_THREADS, 1) k_cross_i8(CrossI8Params p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ double s_xn[VT_N], s_xs[VT_N], s_al[VT_N], s_ms[VT_M];
+    __shared__ double s_xn[VT_N], s_xs[VT_N], s_al[VT_N], s_ms[3][VT_M];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const I8Pipe pp = i8_pipe_setup(smem_raw, 8);
+    const I8Pipe pp = i8_pipe_setup(smem_raw, CE_WARPS);
     if (warp == 0 && lane == 0) {
         uint32_t kbg = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
@@ -319,7 +343,7 @@ __global__ void __launch_bounds__(320, 1) k_cross_i8(CrossI8Params p) {
     }
     __syncwarp();
     if (warp >= 2) {
-        const int q = warp & 3, half = (warp - 2) >> 2, row = q * 32 + lane;
+        const int q = warp & 3, sl = (warp - 2) >> 2, row = q * 32 + lane;   // sl: 16-column slice of the tile
         const int swz = (row >> 2) & 1;
         const double os = p.hyp[0];
         uint32_t it = 0;
@@ -332,54 +356,51 @@ __global__ void __launch_bounds__(320, 1) k_cross_i8(CrossI8Params p) {
             const double znr = p.zn[grow], m2sz = -2.0 * p.zscale[grow];
             const bool rowvalid = grow < p.m;
             const bool ok = i8_pipe_wait_accum(pp, it, p.flag);
-            double v[32];
+            double v[16];
 #pragma unroll
-            for (int j = 0; j < 32; j++) v[j] = 0.0;
+            for (int j = 0; j < 16; j++) v[j] = 0.0;
 #pragma unroll
             for (int g = I8_S - 1; g >= 0; g--) {          // smallest weights first; signed x signed: 2^-(8g+14)
-                uint32_t rr[32];
-                tmem_ld32(pp.tmem_base + ((uint32_t)(q * 32) << 16) + g * VT_N + half * 32, rr);
+                uint32_t rr[16];
+                tmem_ld16(pp.tmem_base + ((uint32_t)(q * 32) << 16) + g * VT_N + sl * 16, rr);
                 const double w = i8_pow2(-(8 * g + 14));
 #pragma unroll
-                for (int j = 0; j < 32; j++) v[j] = fma(w, (double)(int32_t)rr[j], v[j]);
+                for (int j = 0; j < 16; j++) v[j] = fma(w, (double)(int32_t)rr[j], v[j]);
             }
             i8_pipe_release_tmem(pp);                      // the MMA issuer may start this CTA's next tile
-            asm volatile("bar.sync 1, 256;" ::: "memory"); // s_xn / s_xs / s_al of this tile are in place
+            asm volatile("bar.sync 1, %0;" ::"n"(CE_WARPS * 32) : "memory");   // s_xn / s_xs / s_al of this tile are in place
             double msum = 0.0;
+            uint32_t dg[I8_S][4];                          // 16 columns = one 16-byte half of an image row per digit plane
 #pragma unroll
-            for (int gq = 0; gq < 2; gq++) {               // 16 columns = one 16-byte half of an image row per plane
-                uint32_t dg[I8_S][4];
+            for (int jq = 0; jq < 4; jq++) {               // 4 columns -> one 32-bit word of every digit plane
+                unsigned lo[4], hi[4];
 #pragma unroll
-                for (int jq = 0; jq < 4; jq++) {           // 4 columns -> one 32-bit word of every digit plane
-                    unsigned lo[4], hi[4];
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const int cl = half * 32 + gq * 16 + jq * 4 + e;
-                        const double r2 = fmax(fma(v[gq * 16 + jq * 4 + e] * m2sz, s_xs[cl], znr + s_xn[cl]), 0.0);
-                        double k, dk;
-                        kernel_eval(KIND, r2, k, dk);
-                        const bool valid = rowvalid && (bn * VT_N + cl) < p.n;      // padding rows / columns are exact zeros
-                        const double kq = valid ? k : 0.0;
-                        msum = fma(os * kq, s_al[cl], msum);
-                        const unsigned long long X = min(__double2ull_rn(kq * 281474976710656.0), 0xFFFFFFFFFFFFULL);   // rint(k 2^48)
-                        lo[e] = (unsigned)X; hi[e] = (unsigned)(X >> 32);
-                    }
-                    // byte b of the four values -> one word (3 PRMT each)
-#define HDBO_GATHER(SRC, SEL) __byte_perm(__byte_perm(SRC[0], SRC[1], SEL), __byte_perm(SRC[2], SRC[3], SEL), 0x5410)
-                    dg[5][jq] = HDBO_GATHER(lo, 0x0040); dg[4][jq] = HDBO_GATHER(lo, 0x0051);
-                    dg[3][jq] = HDBO_GATHER(lo, 0x0062); dg[2][jq] = HDBO_GATHER(lo, 0x0073);
-                    dg[1][jq] = HDBO_GATHER(hi, 0x0040); dg[0][jq] = HDBO_GATHER(hi, 0x0051);
-#undef HDBO_GATHER
+                for (int e = 0; e < 4; e++) {
+                    const int cl = sl * 16 + jq * 4 + e;
+                    const double r2 = fmax(fma(v[jq * 4 + e] * m2sz, s_xs[cl], znr + s_xn[cl]), 0.0);
+                    double k, dk;
+                    kernel_eval(KIND, r2, k, dk);
+                    const bool valid = rowvalid && (bn * VT_N + cl) < p.n;      // padding rows / columns are exact zeros
+                    const double kq = valid ? k : 0.0;
+                    msum = fma(os * kq, s_al[cl], msum);
+                    const unsigned long long X = min(__double2ull_rn(kq * 281474976710656.0), 0xFFFFFFFFFFFFULL);   // rint(k 2^48)
+                    lo[e] = (unsigned)X; hi[e] = (unsigned)(X >> 32);
                 }
-                int8_t* dst = p.Kimg + ((size_t)bm * p.nkb_n + bn * 2 + half) * VT_A_STAGE + row * 32 + ((gq ^ swz) << 4);
-#pragma unroll
-                for (int tt = 0; tt < I8_S; tt++)
-                    *reinterpret_cast<uint4*>(dst + tt * VT_M * 32) = make_uint4(dg[tt][0], dg[tt][1], dg[tt][2], dg[tt][3]);
+                // byte b of the four values -> one word (3 PRMT each)
+#define HDBO_GATHER(SRC, SEL) __byte_perm(__byte_perm(SRC[0], SRC[1], SEL), __byte_perm(SRC[2], SRC[3], SEL), 0x5410)
+                dg[5][jq] = HDBO_GATHER(lo, 0x0040); dg[4][jq] = HDBO_GATHER(lo, 0x0051);
+                dg[3][jq] = HDBO_GATHER(lo, 0x0062); dg[2][jq] = HDBO_GATHER(lo, 0x0073);
+                dg[1][jq] = HDBO_GATHER(hi, 0x0040); dg[0][jq] = HDBO_GATHER(hi, 0x0051);
+#undef HDBO_GATHER
             }
+            int8_t* dst = p.Kimg + ((size_t)bm * p.nkb_n + bn * 2 + (sl >> 1)) * VT_A_STAGE + row * 32 + (((sl & 1) ^ swz) << 4);
+#pragma unroll
+            for (int tt = 0; tt < I8_S; tt++)
+                *reinterpret_cast<uint4*>(dst + tt * VT_M * 32) = make_uint4(dg[tt][0], dg[tt][1], dg[tt][2], dg[tt][3]);
             if (!ok) msum = __longlong_as_double(0x7ff8000000000000LL);
-            if (half) s_ms[row] = msum;
-            asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 epilogue warps
-            if (!half) p.meanpart[(size_t)bn * p.rows_pad + grow] = msum + s_ms[row];
+            if (sl) s_ms[sl - 1][row] = msum;
+            asm volatile("bar.sync 1, %0;" ::"n"(CE_WARPS * 32) : "memory");
+            if (!sl) p.meanpart[(size_t)bn * p.rows_pad + grow] = ((msum + s_ms[0][row]) + s_ms[1][row]) + s_ms[2][row];
         }
     }
     i8_pipe_teardown(pp);
@@ -399,8 +420,8 @@ cudaError_t launch_cross_i8(int kind, const int8_t* Zimg, const int8_t* Ximg, co
     CrossI8Params p{Zimg, Ximg, zscale, xscale, zn, xn, alpha, hyp, Kimg, meanpart, m, n, rows_pad, n_pad / VT_N, ntiles, (d + 31) / 32,
                     n_pad / VT_KB, flag};
     const int grid = ntiles < i8_sm_count() ? ntiles : i8_sm_count();
-    if (kind == 0) k_cross_i8<0><<<grid, 320, VT_SMEM, st>>>(p);
-    else k_cross_i8<1><<<grid, 320, VT_SMEM, st>>>(p);
+    if (kind == 0) k_cross_i8<0><<<grid, CE_THREADS, VT_SMEM, st>>>(p);
+    else k_cross_i8<1><<<grid, CE_THREADS, VT_SMEM, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -444,7 +465,7 @@ __global__ void __launch_bounds__(192, 1) k_var_i8(VarI8Params p) {
         uint32_t kbg = 0, it = 0;
         for (int t = blockIdx.x; t < p.nslots; t += gridDim.x) {
             if (!var_tile(p, t, bm, bn)) continue;
-            if (!i8_pipe_mma<false>(pp, (bn + 1) * (VT_N / VT_KB), kbg, it++, p.flag)) break;
+            if (!i8_pipe_mma<false, HDBO_VAR_A_TMEM>(pp, (bn + 1) * (VT_N / VT_KB), kbg, it++, p.flag)) break;
         }
     }
     __syncwarp();
