@@ -23,6 +23,7 @@ from ._lib import HdboGp, check, ptr
 
 DEFAULT_CHUNK_ROWS = 148 * 128  # one 128-row tile per SM per column tile
 WORKSPACE_CAP_BYTES = 8 << 30
+I8_MAX_N_PAD = 8192   # int8 mode: int32 group sums stay exact up to this size (csrc/i8.cuh); larger GPs use the FP64 path
 
 
 def _rup(x: int, m: int) -> int:
@@ -83,6 +84,7 @@ class DeviceGP:
         if self.batch != 1:
             self.var_mode = "f64"
         self._i8_state: Optional[torch.Tensor] = None
+        self._i8_dirty = True
         self.desc = HdboGp(
             n=self.n, d=self.d, n_pad=npad, d_pad=dpad, kind=self.kind, batch=B,
             X=ptr(self.X), ldx=self.X.stride(0), y=ptr(self.y), center=ptr(self.center), inv_ls=ptr(self.inv_ls),
@@ -111,6 +113,7 @@ class DeviceGP:
     def fit_once(self, need_r2: Optional[bool] = None) -> None:
         need = self.keep_r2 if need_r2 is None else need_r2
         check(self.lib.hdbo_gp_fit(C.byref(self.desc), int(bool(need)), _stream()), "hdbo_gp_fit")
+        self._i8_dirty = True
 
     def fit(self, need_r2: Optional[bool] = None, max_tries: int = 3) -> float:
         """Factorise with the psd_safe_cholesky jitter schedule (1e-8 * 10**i, i < max_tries).  One host sync."""
@@ -129,8 +132,7 @@ class DeviceGP:
             self.hyp[:, 3] = 0.0
         self.fitted = True
         self.jitter_used = jitter
-        if self.var_mode == "i8":
-            self.slice_linv()
+        self._i8_dirty = True      # int8 mode: the digit images are re-sliced lazily by the next pool evaluation
         return jitter
 
     # ---- exact int8 variance mode: digit planes of L^-1, once per fit ----
@@ -141,6 +143,7 @@ class DeviceGP:
                 raise _lib.HdboError("hdbo_i8_state_bytes rejected its arguments")
             self._i8_state = torch.empty(need, dtype=torch.uint8, device=self.device)
         check(self.lib.hdbo_gp_slice_linv(C.byref(self.desc), ptr(self._i8_state), _stream()), "hdbo_gp_slice_linv")
+        self._i8_dirty = False
 
     def i8_flag(self) -> int:
         """Non-zero if a pipeline wait of the int8 variance kernel ever timed out (its outputs are then NaN).  Host sync."""
@@ -149,7 +152,9 @@ class DeviceGP:
         return int(self._i8_state[-16:-12].view(torch.int32).item())
 
     def _pool_call(self, Zptr, ldz, m, observation_noise, acq_kind, acq_param, mean, var, acq, bso, ws, stream) -> None:
-        if self.var_mode == "i8" and self._i8_state is not None:
+        if self.var_mode == "i8" and self.n_pad <= I8_MAX_N_PAD:
+            if self._i8_dirty or self._i8_state is None:
+                self.slice_linv()
             check(self.lib.hdbo_posterior_acq_i8(C.byref(self.desc), ptr(self._i8_state), Zptr, ldz, m, int(observation_noise),
                                                  acq_kind, float(acq_param), mean, var, acq, bso, ptr(ws), ws.numel(), stream),
                   "hdbo_posterior_acq_i8")

@@ -176,3 +176,36 @@ def test_i8_full_size_against_f64_mode(cuda_device):
     assert float(((res["i8"][1] - res["f64"][1]).abs() / res["f64"][1].abs()).max()) < REL
     assert int(res["i8"][2].argmax()) == int(res["f64"][2].argmax())
     assert (res["i8"][1] > 0).all()
+
+
+def test_i8_mode_through_the_botorch_surface(cuda_device, monkeypatch):
+    """HDBO_VAR_MODE=i8: SingleTaskGP + LogExpectedImprovement under no_grad (the raw-sample screening of optimize_acqf) runs on the
+    int8 path, the autograd path stays FP64; both agree with the oracle, and a hyper-parameter change re-slices lazily."""
+    monkeypatch.setenv("HDBO_VAR_MODE", "i8")
+    from hdbo_benchmark_b200 import acquisition as A
+    from hdbo_benchmark_b200 import gp_modules as G
+    from hdbo_benchmark_b200.models import SingleTaskGP
+
+    n, d = 260, 12
+    X, y, ls, os_, nz, mu = O.synthetic_problem(n, d, "prior", 1e-3, seed=2)
+    model = SingleTaskGP(X, y.unsqueeze(-1), covar_module=G.ScaleKernel(G.MaternKernel(ard_num_dims=d)),
+                         likelihood=G.GaussianLikelihood(), outcome_transform=None)
+    model.likelihood.noise = nz
+    model.mean_module.constant = mu
+    Z = O.sobol_candidates(700, d, seed=4)
+    best = float(y.max()) - 0.2
+    for scale in (1.0, 0.7):
+        model.covar_module.base_kernel.lengthscale = ls * scale
+        model.covar_module.outputscale = float(os_) * scale
+        model.eval()
+        st = O.fit_state(X, y, ls * scale, float(os_) * scale, nz, mu, O.MATERN52)
+        a_o, g_o = O.acquisition_value_and_grad_autograd(st, Z[:30], O.ACQ_LOGEI, best)
+        a_all = O.acquisition(*O.posterior(st, Z), O.ACQ_LOGEI, best)
+        f = A.LogExpectedImprovement(model, best_f=best)
+        with torch.no_grad():
+            a = f(Z.unsqueeze(1))
+        assert model._gp.var_mode == "i8" and model._gp._i8_state is not None and model._gp.i8_flag() == 0
+        assert float((a.cpu() - a_all).abs().max()) < REL * max(1.0, float(a_all.abs().max()))
+        Zg = Z[:30].clone().unsqueeze(1).requires_grad_(True)
+        (g,) = torch.autograd.grad(f(Zg).sum(), Zg)
+        assert float((g.squeeze(1).cpu() - g_o).abs().max()) < REL * float(g_o.abs().max())
