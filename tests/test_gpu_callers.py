@@ -181,3 +181,37 @@ def test_import_shims_resolve_reference_style_code(cuda_device):
         if installed:
             for k in [k for k, v in sys.modules.items() if getattr(v, "__hdbo_b200_shim__", False)]:
                 del sys.modules[k]
+
+
+def test_joint_posterior_samples_match_oracle_and_thompson_picks(cuda_device):
+    """joint posterior samples over a candidate set (m x m covariance, its Cholesky factor, mean + L z) against the
+    oracle with the same base samples and jitter; MaxPosteriorSampling returns the arg-max candidates of each sample."""
+    from hdbo_benchmark_b200 import gp_modules as G
+    from hdbo_benchmark_b200.models import SingleTaskGP
+    from hdbo_benchmark_b200.thompson import MaxPosteriorSampling, joint_posterior_samples
+
+    n, d, m, S = 150, 6, 333, 5
+    X, y, ls, os_, nz, mu = O.synthetic_problem(n, d, "short", 1e-2, seed=3)
+    st = O.fit_state(X, y, ls, os_, nz, mu, O.MATERN52)
+    Z = O.sobol_candidates(m, d, seed=8)
+    z = torch.randn(S, m, dtype=torch.float64, generator=torch.Generator().manual_seed(5))
+    model = SingleTaskGP(X, y.unsqueeze(-1), covar_module=G.ScaleKernel(G.MaternKernel(ard_num_dims=d)),
+                         likelihood=G.GaussianLikelihood(), outcome_transform=None)
+    model.covar_module.base_kernel.lengthscale = ls
+    model.covar_module.outputscale = float(os_)
+    model.likelihood.noise = nz
+    model.mean_module.constant = mu
+    model.eval()
+    gp = model._device_gp()
+    samples, mean, jitter = joint_posterior_samples(gp, Z.to(cuda_device), z)
+    mean_o, Sigma_o = O.posterior_joint(st, Z.unsqueeze(0))
+    Lo = torch.linalg.cholesky(Sigma_o[0] + jitter * torch.eye(m, dtype=torch.float64))
+    samples_o = mean_o[0] + z @ Lo.T
+    assert float((mean.cpu() - mean_o[0]).abs().max()) < 1e-9
+    # the factor of a (nearly low-rank) covariance amplifies rounding: compare at 1e-6 of the sample scale
+    assert float((samples.cpu() - samples_o).abs().max()) < 1e-6 * float(samples_o.abs().max())
+    picker = MaxPosteriorSampling(model, replacement=False, seed=1)
+    Xn = picker(Z, num_samples=4)
+    assert Xn.shape == (4, d)
+    rows = {tuple(r.tolist()) for r in Xn}
+    assert len(rows) == 4 and all(any(torch.equal(r, zc) for zc in Z) for r in Xn)
