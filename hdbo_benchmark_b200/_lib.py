@@ -36,6 +36,14 @@ class HdboError(RuntimeError):
     pass
 
 
+class HdboLbfgs(C.Structure):
+    """Mirror of `struct hdbo_lbfgs` (include/hdbo_b200.h)."""
+    _fields_ = [("R", C.c_int32), ("D", C.c_int32), ("M", C.c_int32), ("T", C.c_int32),
+                ("lo", C.c_void_p), ("hi", C.c_void_p), ("x", C.c_void_p), ("f", C.c_void_p), ("g", C.c_void_p),
+                ("S", C.c_void_p), ("Y", C.c_void_p), ("rho", C.c_void_p), ("step", C.c_void_p), ("meta", C.c_void_p), ("Xt", C.c_void_p),
+                ("ft", C.c_void_p), ("gt", C.c_void_p), ("ftol", C.c_double), ("gtol", C.c_double), ("maxiter", C.c_int32)]
+
+
 _SIGNATURES = {
     "hdbo_version": (C.c_int, []),
     "hdbo_gp_fit": (C.c_int, [C.POINTER(HdboGp), C.c_int, _dp]),
@@ -50,6 +58,8 @@ _SIGNATURES = {
     "hdbo_gp_slice_linv": (C.c_int, [C.POINTER(HdboGp), _dp, _dp]),
     "hdbo_posterior_acq_i8": (C.c_int, [C.POINTER(HdboGp), _dp, _dp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_double,
                                         _dp, _dp, _dp, C.c_int64, _dp, C.c_size_t, _dp]),
+    "hdbo_lbfgs_propose": (C.c_int, [C.POINTER(HdboLbfgs), _dp]),
+    "hdbo_lbfgs_accept": (C.c_int, [C.POINTER(HdboLbfgs), _dp]),
     "hdbo_i8_peak_probe": (C.c_int, [_dp, C.c_int, C.c_int, C.POINTER(C.c_double), _dp]),
     "hdbo_i8_state_flag": (C.c_void_p, [C.POINTER(HdboGp), _dp]),
     "hdbo_posterior_fwd": (C.c_int, [C.POINTER(HdboGp), _dp, C.c_int64, C.c_int64, C.c_int, _dp, _dp, C.c_int64,

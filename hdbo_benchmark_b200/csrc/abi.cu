@@ -5,6 +5,7 @@
 #include "elem.cuh"
 #include "grad.cuh"
 #include "i8.cuh"
+#include "lbfgs.cuh"
 
 #include <cstdlib>
 #include <vector>
@@ -281,6 +282,32 @@ extern "C" int hdbo_posterior_acq_i8(const hdbo_gp* gp, void* i8_state, const do
     I8State s = carve_i8(gp, i8_state);
     return posterior_acq_impl(gp, &s, Z, ldz, m, observation_noise, acq_kind, acq_param, mean, var, acq, bso, workspace,
                               workspace_bytes, stream_);
+}
+
+// ---- batched device L-BFGS ----
+static int lbfgs_fill(LbfgsParams& p, const hdbo_lbfgs* s) {
+    if (!s || s->R < 0 || s->D <= 0 || s->M <= 0 || s->M > 32 || s->T <= 0 || s->T > 16) return -1;
+    if (!s->lo || !s->hi || !s->x || !s->f || !s->g || !s->S || !s->Y || !s->rho || !s->meta || !s->Xt || !s->step) return -1;
+    if ((size_t)(s->D + 16 + s->M) * sizeof(double) > 200 * 1024) return -1;
+    p.R = s->R; p.D = s->D; p.M = s->M; p.T = s->T; p.lo = s->lo; p.hi = s->hi; p.x = s->x; p.f = s->f; p.g = s->g;
+    p.S = s->S; p.Y = s->Y; p.rho = s->rho; p.step = s->step; p.meta = s->meta; p.Xt = s->Xt; p.ft = s->ft; p.gt = s->gt;
+    p.ftol = s->ftol; p.gtol = s->gtol; p.maxiter = s->maxiter;
+    return 0;
+}
+
+extern "C" int hdbo_lbfgs_propose(const hdbo_lbfgs* s, void* stream_) {
+    LbfgsParams p{};
+    if (int e = lbfgs_fill(p, s)) return e;
+    TRY_CUDA(launch_lbfgs_propose(p, (cudaStream_t)stream_));
+    return 0;
+}
+
+extern "C" int hdbo_lbfgs_accept(const hdbo_lbfgs* s, void* stream_) {
+    LbfgsParams p{};
+    if (int e = lbfgs_fill(p, s)) return e;
+    if (!s->ft || !s->gt) return -1;
+    TRY_CUDA(launch_lbfgs_accept(p, (cudaStream_t)stream_));
+    return 0;
 }
 
 extern "C" int hdbo_i8_peak_probe(int32_t* flag, int iters, int sms, double* ops_out, void* stream_) {

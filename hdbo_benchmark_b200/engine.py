@@ -234,6 +234,33 @@ class DeviceGP:
             out_host.copy_(acq, non_blocking=True)
         return acq, val, idx
 
+    # ---- A4 + A5 + A6 without the autograd tape: acquisition value and d/dZ for m points (device L-BFGS inner loop) ----
+    def acq_value_grad(self, Z: torch.Tensor, acq_kind: int, acq_param: float, sign: float = 1.0, bufs: Optional[dict] = None):
+        """Z [m, d] float64 contiguous on the device -> (acq [m], dacq/dZ [m, d]); `sign` = -1 evaluates the acquisition of
+        the negated mean (minimisation problems).  `bufs` (a dict the caller keeps) caches workspace and outputs across calls."""
+        assert self.fitted and self.batch == 1
+        m, d = Z.shape
+        bufs = bufs if bufs is not None else {}
+        if bufs.get("m") != m:
+            f64 = dict(dtype=torch.float64, device=self.device)
+            rows = _rup(m, 128)
+            need = self.lib.hdbo_posterior_workspace_bytes(C.byref(self.desc), rows, 1)
+            bufs.update(m=m, ws=torch.empty(need, dtype=torch.uint8, device=self.device), mean=torch.empty(m, **f64),
+                        var=torch.empty(m, **f64), acq=torch.empty(m, **f64), dmean=torch.empty(m, **f64),
+                        dvar=torch.empty(m, **f64), dZ=torch.empty(m, d, **f64))
+        b, st, lib = bufs, _stream(), self.lib
+        check(lib.hdbo_posterior_fwd(C.byref(self.desc), ptr(Z), Z.stride(0), m, 0, ptr(b["mean"]), ptr(b["var"]), m, ptr(b["ws"]),
+                                     b["ws"].numel(), st), "hdbo_posterior_fwd")
+        if sign < 0:
+            b["mean"].neg_()
+        check(lib.hdbo_acq_elementwise(ptr(b["mean"]), ptr(b["var"]), m, acq_kind, float(acq_param), ptr(b["acq"]), ptr(b["dmean"]),
+                                       ptr(b["dvar"]), st), "hdbo_acq_elementwise")
+        if sign < 0:
+            b["dmean"].neg_()
+        check(lib.hdbo_posterior_bwd(C.byref(self.desc), m, 1, ptr(b["dmean"]), ptr(b["dvar"]), 0, m, 0, ptr(b["dZ"]), d, m * d,
+                                     ptr(b["ws"]), b["ws"].numel(), st), "hdbo_posterior_bwd")
+        return b["acq"], b["dZ"]
+
     def argmax(self, v: torch.Tensor):
         v = v.reshape(-1)
         out_val = torch.empty(1, dtype=torch.float64, device=self.device)

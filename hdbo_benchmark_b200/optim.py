@@ -129,6 +129,112 @@ def gen_candidates_scipy(initial_conditions: torch.Tensor, acquisition_function:
     return cand, vals
 
 
+def _device_lbfgs_supported(acq_function, q: int) -> bool:
+    """The device optimiser drives the C ABI directly: analytic (q = 1) acquisition on a single GP, affine input transform."""
+    from .acquisition import AnalyticAcquisitionFunction
+    from .models import Normalize
+
+    model = getattr(acq_function, "model", None)
+    if q != 1 or not isinstance(acq_function, AnalyticAcquisitionFunction) or model is None:
+        return False
+    if getattr(model, "_is_fully_bayesian", False):
+        return False
+    it = getattr(model, "input_transform", None)
+    return it is None or isinstance(it, Normalize)
+
+
+def gen_candidates_device(initial_conditions: torch.Tensor, acquisition_function, lower_bounds=None, upper_bounds=None,
+                          options: Optional[Dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Batched box-constrained L-BFGS on the device: every restart is an independent problem, the whole
+    backtracking line search of an iteration is one batched value+gradient evaluation, and the host only enqueues
+    `hdbo_lbfgs_propose -> hdbo_posterior_fwd -> hdbo_acq_elementwise -> hdbo_posterior_bwd -> hdbo_lbfgs_accept` per iteration,
+    polling the convergence flags every `check_every` iterations.  Same contract as `gen_candidates_scipy`."""
+    import ctypes as C
+
+    from . import _lib
+    from ._lib import HdboLbfgs, check, ptr
+    from .engine import _stream
+
+    options = dict(options or {})
+    model = acquisition_function.model
+    gp = model._device_gp()
+    dev = gp.device
+    f64 = dict(dtype=torch.float64, device=dev)
+    shape = initial_conditions.shape                      # [R, 1, d]
+    d = shape[-1]
+    R = int(np.prod(shape[:-1]))
+    M, T = int(options.get("maxcor", 10)), int(options.get("line_search_trials", 8))
+    maxiter = int(options.get("maxiter", 200))
+    # optimise in the model's input space (affine image of the caller's box)
+    it = getattr(model, "input_transform", None)
+    off = torch.zeros(d, **f64) if it is None else it.offset.to(dev, torch.float64)
+    coef = torch.ones(d, **f64) if it is None else it.coefficient.to(dev, torch.float64)
+    inf = float("inf")
+    lo = torch.full((d,), -inf, **f64) if lower_bounds is None else torch.as_tensor(lower_bounds, dtype=torch.float64).to(dev).reshape(-1).expand(d)
+    hi = torch.full((d,), inf, **f64) if upper_bounds is None else torch.as_tensor(upper_bounds, dtype=torch.float64).to(dev).reshape(-1).expand(d)
+    lo_t, hi_t = ((lo - off) / coef).contiguous(), ((hi - off) / coef).contiguous()
+    x = ((initial_conditions.detach().to(dev, torch.float64).reshape(R, d) - off) / coef)
+    x = torch.minimum(torch.maximum(x, lo_t), hi_t).contiguous()
+    scale, shift = acquisition_function._scale_shift()
+    sign = 1.0 if acquisition_function.maximize else -1.0
+    kind, param = acquisition_function._kind, acquisition_function._std_param(scale, shift, sign)
+    bufs0, bufs = {}, {}
+    a0, g0 = gp.acq_value_grad(x, kind, param, sign, bufs0)
+    f = (-a0).clone()
+    g = (-g0).clone()
+    S = torch.zeros(R, M, d, **f64)
+    Y = torch.zeros(R, M, d, **f64)
+    rho = torch.zeros(R, M, **f64)
+    meta = torch.zeros(R, 4, dtype=torch.int32, device=dev)
+    step = torch.ones(R, **f64)
+    Xt = torch.empty(R * T, d, **f64)
+    ft = torch.empty(R * T, **f64)
+    gt = torch.empty(R * T, d, **f64)
+    st = HdboLbfgs(R=R, D=d, M=M, T=T, lo=ptr(lo_t), hi=ptr(hi_t), x=ptr(x), f=ptr(f), g=ptr(g), S=ptr(S), Y=ptr(Y), rho=ptr(rho),
+                   step=ptr(step), meta=ptr(meta), Xt=ptr(Xt), ft=ptr(ft), gt=ptr(gt), ftol=float(options.get("ftol", 2.220446049250313e-09)),
+                   gtol=float(options.get("gtol", 1e-5)), maxiter=maxiter)
+    lib = gp.lib
+    check_every = int(options.get("check_every", 10))
+
+    def iteration():
+        check(lib.hdbo_lbfgs_propose(C.byref(st), _stream()), "hdbo_lbfgs_propose")
+        a, dZ = gp.acq_value_grad(Xt, kind, param, sign, bufs)
+        torch.neg(a, out=ft)
+        torch.neg(dZ, out=gt)
+        check(lib.hdbo_lbfgs_accept(C.byref(st), _stream()), "hdbo_lbfgs_accept")
+
+    # Two eager iterations (they also do the one-time kernel-attribute set-up and size the buffers), then the iteration -- ~15
+    # small dependent launches -- is captured once into a CUDA graph and replayed; the host only polls the flags between blocks.
+    done_iters = 0
+    for _ in range(min(2, maxiter)):
+        iteration()
+        done_iters += 1
+    graph = None
+    if options.get("cuda_graph", True) and maxiter > done_iters:
+        try:
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                iteration()
+            done_iters += 1
+        except Exception:   # capture not possible (e.g. an outer capture is active): run eagerly
+            graph = None
+    while done_iters < maxiter:
+        for _ in range(min(check_every, maxiter - done_iters)):
+            graph.replay() if graph is not None else iteration()
+            done_iters += 1
+        if bool((meta[:, 2] != 0).all()):
+            break
+    if not bool(torch.isfinite(f).all()):
+        raise RuntimeError("acquisition value is not finite")
+    gen_candidates_device.last_info = {"iterations": done_iters, "per_restart_iterations": meta[:, 3].tolist(),
+                                       "flags": meta[:, 2].tolist(), "cuda_graph": graph is not None}
+    cand = (x * coef + off).reshape(shape)
+    with torch.no_grad():
+        vals = acquisition_function(cand)
+    return cand, vals
+
+
 def optimize_acqf(acq_function, bounds, q: int, num_restarts: int, raw_samples: Optional[int] = None,
                   options: Optional[Dict] = None, batch_initial_conditions: Optional[torch.Tensor] = None,
                   return_best_only: bool = True, sequential: bool = False, **kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -155,9 +261,19 @@ def optimize_acqf(acq_function, bounds, q: int, num_restarts: int, raw_samples: 
         ics = torch.as_tensor(batch_initial_conditions).to(_compute_device(acq_function), torch.float64)
     batch_limit = options.get("batch_limit", num_restarts)
     cands, vals = [], []
+    # options["method"] = "device-lbfgs": batched L-BFGS on the device (analytic q = 1 acquisitions); default = scipy L-BFGS-B
+    on_device = options.get("method") == "device-lbfgs" and _device_lbfgs_supported(acq_function, q)
     for i in range(0, ics.shape[0], batch_limit):
+        if on_device:
+            c, v = gen_candidates_device(ics[i:i + batch_limit], acq_function, bounds_t[0], bounds_t[1],
+                                         options={k: v for k, v in options.items()
+                                                  if k in ("maxiter", "ftol", "gtol", "maxcor", "line_search_trials", "check_every", "cuda_graph")})
+            cands.append(c)
+            vals.append(v.to(c.device, torch.float64))
+            continue
         c, v = gen_candidates_scipy(ics[i:i + batch_limit], acq_function, bounds_t[0], bounds_t[1],
-                                    options={k: v for k, v in options.items() if k in ("maxiter", "ftol", "gtol", "maxfun", "method")})
+                                    options={k: v for k, v in options.items() if k in ("maxiter", "ftol", "gtol", "maxfun", "method")
+                                             and v != "device-lbfgs"})
         cands.append(c)
         vals.append(v.to(c.device, torch.float64))
     cand = torch.cat(cands)

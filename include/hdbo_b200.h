@@ -171,6 +171,29 @@ int hdbo_profile_collect(double* ms_by_class, int64_t* launches_by_class);
  * writes the flops it performs to *flops_out (HOST pointer).  Timed by the caller: measured FP64 tensor peak. */
 int hdbo_fp64_peak_probe(double* scratch, int iters, int sms, double* flops_out, void* stream);
 
+/* Batched box-constrained L-BFGS on the device: R independent problems (the restarts of optimize_acqf), minimisation.
+ * Replaces: scipy.optimize.minimize(method="L-BFGS-B") inside botorch.generation.gen_candidates_scipy, whose per-iteration
+ * float64-ndarray round trip dominates `next_candidate()` once the acquisition itself takes microseconds.
+ * One iteration = hdbo_lbfgs_propose (direction from the (s, y) ring, T trial points clip(x + 2^-j dir) of a backtracking line
+ * search) -> the caller evaluates value + gradient at the R x T trial points (hdbo_posterior_fwd / hdbo_acq_elementwise /
+ * hdbo_posterior_bwd) into ft / gt -> hdbo_lbfgs_accept (Armijo pick, ring update, convergence flags in meta).  No host
+ * synchronisation is needed until the caller polls meta[r][2].  Initial state: x, f, g at the starting points, meta zeroed,
+ * step = 1. */
+typedef struct hdbo_lbfgs {
+    int32_t R, D, M, T;          /* problems, variables each, history pairs (<= 32), trial steps (<= 16)                 */
+    const double *lo, *hi;       /* [D] box shared by the problems (+-inf = unbounded)                                  */
+    double *x, *f, *g;           /* [R][D], [R], [R][D]                                                                 */
+    double *S, *Y, *rho;         /* [R][M][D], [R][M][D], [R][M]                                                        */
+    double* step;                /* [R] first trial step length of the next line search (initialise to 1)              */
+    int32_t* meta;               /* [R][4]: pairs stored, newest index, done (1 converged, 2 stalled), iterations       */
+    double* Xt;                  /* [R][T][D] trial points                                                              */
+    const double *ft, *gt;       /* [R][T], [R][T][D] value / gradient at the trial points                              */
+    double ftol, gtol;           /* relative decrease / projected-gradient sup-norm tolerances (scipy: 2.2e-9, 1e-5)    */
+    int32_t maxiter;
+} hdbo_lbfgs;
+int hdbo_lbfgs_propose(const hdbo_lbfgs* s, void* stream);
+int hdbo_lbfgs_accept(const hdbo_lbfgs* s, void* stream);
+
 /* Same for the int8 tensor pipe: `sms` CTAs issue resident-operand tcgen05.mma kind::i8 (M128 N256 K32) only; *ops_out (HOST) =
  * integer operations performed (2 per multiply-accumulate).  flag: device int32, set if the completion wait timed out. */
 int hdbo_i8_peak_probe(int32_t* flag, int iters, int sms, double* ops_out, void* stream);
