@@ -434,15 +434,19 @@ struct VarI8Params {
     const double* colscale;   // [n_pad] 2^e_i of the L^-1 row = column of V
     const double* hyp;        // outputscale at [0]
     double* varpart;          // [ntiles64][rows_pad]
-    int rows_pad, ntiles64, mtiles, nkb, nslots;
+    int rows_pad, ntiles64, mtiles, nkb, nslots, nwaves;
     int* flag;                // set when a barrier wait timed out (results are then poisoned with NaN)
 };
 
 // Tile list of k_var_i8.  Slots t are rasterised so that tiles processed at the same time by the 148 CTAs (t .. t+147) cover
 // VT_GN column tiles x ~9 row tiles: every A (K* digit) tile is fetched from DRAM once per VT_GN column tiles instead of once per
-// column tile (the A images of a chunk are 4x the L2).  Column-tile groups with the longest k-range come first, and a CTA's
-// slots t, t + 148, ... rotate through the positions of a group (148 mod 16 = 4), which balances the triangular work.
-__device__ __forceinline__ bool var_tile(const VarI8Params& p, int t, int& bm, int& bn) {
+// column tile (the A images of a chunk are 4x the L2).  Column-tile groups with the longest k-range come first.  CTA c takes the
+// slots w G + c of the even "waves" w and w G + (G-1-c) of the odd ones (serpentine): with round-robin, CTA 0 always got the
+// heaviest tile of a wave (4.2 % static imbalance in the k-block count, 7 % measured); serpentine balances it to < 0.1 %.
+__device__ __forceinline__ bool var_tile(const VarI8Params& p, int wave, int& bm, int& bn) {
+    const int G = gridDim.x, c = (wave & 1) ? G - 1 - (int)blockIdx.x : (int)blockIdx.x;
+    const int t = wave * G + c;
+    if (t >= p.nslots) return false;
     const int per_group = p.mtiles * VT_GN;
     const int grp = t / per_group, rem = t - grp * per_group;
     bm = rem / VT_GN; bn = p.ntiles64 - 1 - (grp * VT_GN + rem % VT_GN);
@@ -456,15 +460,15 @@ __global__ void __launch_bounds__(192, 1) k_var_i8(VarI8Params p) {
     int bm, bn;
     if (warp == 0 && lane == 0) {
         uint32_t kbg = 0;
-        for (int t = blockIdx.x; t < p.nslots; t += gridDim.x) {
-            if (!var_tile(p, t, bm, bn)) continue;
+        for (int wv = 0; wv < p.nwaves; wv++) {
+            if (!var_tile(p, wv, bm, bn)) continue;
             if (!i8_pipe_produce(pp, p.Aimg + (size_t)bm * p.nkb * VT_A_STAGE, p.Bimg + (size_t)bn * p.nkb * VT_B_STAGE,
                                  (bn + 1) * (VT_N / VT_KB), kbg, p.flag)) break;
         }
     } else if (warp == 1 && lane == 0) {
         uint32_t kbg = 0, it = 0;
-        for (int t = blockIdx.x; t < p.nslots; t += gridDim.x) {
-            if (!var_tile(p, t, bm, bn)) continue;
+        for (int wv = 0; wv < p.nwaves; wv++) {
+            if (!var_tile(p, wv, bm, bn)) continue;
             if (!i8_pipe_mma<false, HDBO_VAR_A_TMEM>(pp, (bn + 1) * (VT_N / VT_KB), kbg, it++, p.flag)) break;
         }
     }
@@ -473,8 +477,8 @@ __global__ void __launch_bounds__(192, 1) k_var_i8(VarI8Params p) {
         const int q = warp & 3;              // TMEM lane quarter this warp may access
         const double os = p.hyp[0];
         uint32_t it = 0;
-        for (int t = blockIdx.x; t < p.nslots; t += gridDim.x) {
-            if (!var_tile(p, t, bm, bn)) continue;
+        for (int wv = 0; wv < p.nwaves; wv++) {
+            if (!var_tile(p, wv, bm, bn)) continue;
             const bool ok = i8_pipe_wait_accum(pp, it++, p.flag);
             double ssq = 0.0;
 #pragma unroll
@@ -513,8 +517,8 @@ cudaError_t launch_var_i8(const int8_t* Aimg, int rows_pad, const int8_t* Bimg, 
     }
     const int mt = rows_pad / VT_M, nt = n_pad / VT_N, groups = (nt + VT_GN - 1) / VT_GN;
     const int nslots = mt * VT_GN * groups;
-    VarI8Params p{Aimg, Bimg, colscale, hyp, varpart, rows_pad, nt, mt, n_pad / VT_KB, nslots, flag};
     const int grid = mt * nt < i8_sm_count() ? mt * nt : i8_sm_count();
+    VarI8Params p{Aimg, Bimg, colscale, hyp, varpart, rows_pad, nt, mt, n_pad / VT_KB, nslots, (nslots + grid - 1) / grid, flag};
     k_var_i8<<<grid, 192, VT_SMEM, st>>>(p);
     return cudaGetLastError();
 }
