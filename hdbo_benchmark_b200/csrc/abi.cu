@@ -157,7 +157,7 @@ I8State carve_i8(const hdbo_gp* gp, void* base) {
 // scale -> cross -> var for `mc` candidates starting at Z (rows_alloc = row capacity of the workspace arrays).
 // i8 != nullptr: both GEMMs run as exact int8 digit-pair products on tcgen05 (kernels_i8.cu); K* only exists as digit images.
 cudaError_t posterior_chunk(const hdbo_gp* gp, const PostWs& w, int64_t rows_alloc, const double* Z, int64_t ldz,
-                            int64_t mc, int keep, cudaStream_t st, const I8State* i8 = nullptr) {
+                            int64_t mc, int keep, cudaStream_t st, const I8State* i8 = nullptr, int* var_tiles = nullptr) {
     const int np = gp->n_pad, dp = gp->d_pad, B = gp->batch;
     const int rp = (int)rup(mc, 128), mt = rp / 128, nt = np / 128;
     cudaError_t e;
@@ -190,6 +190,21 @@ cudaError_t posterior_chunk(const hdbo_gp* gp, const PostWs& w, int64_t rows_all
     e = launch_cross(c, B, st);
     prof_mark(0, st);
     if (e != cudaSuccess) return e;
+    if (var_tiles) *var_tiles = nt;
+    if (keep && var_tiles && (long long)mt * nt * B < 148) {
+        // Few candidates (the inner loop of optimize_acqf): a grid of 128x128 tiles would occupy a handful of SMs for the whole
+        // k-range.  V comes from the generic GEMM (which cuts such launches into 64x64 / 32x32 tiles) + one row-reduction pass.
+        GemmParams g{};
+        g.A = w.Kstar; g.B = gp->Linv; g.C = w.V; g.Ct = nullptr;
+        g.lda = g.ldb = g.ldc = np; g.bsA = (long long)rows_alloc * np; g.bsB = (long long)np * np; g.bsC = (long long)rows_alloc * np;
+        g.mtiles = mt; g.ntiles = nt; g.kblocks = np / BK; g.krange = KR_LE_N; g.lower_only = 0; g.alpha = 1.0; g.beta = 0.0;
+        prof_mark(1, st);
+        e = launch_gemm_nt(g, B, st);
+        if (e == cudaSuccess) e = launch_row_sumsq(w.V, np, (long long)rows_alloc * np, rp, np, w.varpart, 2LL * nt * rows_alloc, B, st);
+        prof_mark(1, st);
+        *var_tiles = 1;
+        return e;
+    }
     VarParams v{};
     v.Kstar = w.Kstar; v.Linv = gp->Linv; v.V = keep ? w.V : nullptr; v.varpart = w.varpart;
     v.ldk = np; v.ldl = np; v.ldv = np;
@@ -384,8 +399,9 @@ extern "C" int hdbo_posterior_fwd(const hdbo_gp* gp, const double* Z, int64_t ld
     cudaStream_t st = (cudaStream_t)stream_;
     PostWs w = carve(gp, rows, 1, workspace);
     const int nt = gp->n_pad / 128;
-    TRY_CUDA(posterior_chunk(gp, w, rows, Z, ldz, m, 1, st));
-    TRY_CUDA(launch_finalize_acq(w.meanpart, w.varpart, (long long)nt * rows, nt, nt, (int)rows, (int)m, gp->hyp,
+    int vt = nt;
+    TRY_CUDA(posterior_chunk(gp, w, rows, Z, ldz, m, 1, st, nullptr, &vt));
+    TRY_CUDA(launch_finalize_acq(w.meanpart, w.varpart, (long long)nt * rows, nt, vt, (int)rows, (int)m, gp->hyp,
                                  observation_noise, HDBO_ACQ_NONE, 0.0, mean, var, nullptr, bso, gp->batch, st));
     return 0;
 }

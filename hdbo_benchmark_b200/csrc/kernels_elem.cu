@@ -154,6 +154,27 @@ cudaError_t launch_finalize_acq(const double* meanpart, const double* varpart, l
     return cudaGetLastError();
 }
 
+// row sums of squares of V [rows][cols] (one warp per row) -> out[b*bso + row]   (small-m variance path)
+__global__ void k_row_sumsq(const double* __restrict__ V, int ldv, long long bsV, int rows, int cols, double* __restrict__ out,
+                            long long bso) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31, b = blockIdx.y;
+    if (row >= rows) return;
+    const double2* src = reinterpret_cast<const double2*>(V + b * bsV + (size_t)row * ldv);
+    double s = 0.0;
+    for (int j = lane; j < cols / 2; j += 32) { const double2 v = src[j]; s = fma(v.x, v.x, s); s = fma(v.y, v.y, s); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[b * bso + row] = s;
+}
+
+cudaError_t launch_row_sumsq(const double* V, int ldv, long long bsV, int rows, int cols, double* out, long long bso, int batch,
+                             cudaStream_t stream) {
+    if (rows == 0) return cudaSuccess;
+    dim3 grid((rows + 7) / 8, batch);
+    k_row_sumsq<<<grid, 256, 0, stream>>>(V, ldv, bsV, rows, cols, out, bso);
+    return cudaGetLastError();
+}
+
 // acquisition from given mean / var arrays: value + partials (used by the autograd path and tested on its own)
 __global__ void k_acq_elem(const double* __restrict__ mean, const double* __restrict__ var, long long m, int acq_kind,
                            double acq_param, double* __restrict__ acq, double* __restrict__ dmean, double* __restrict__ dvar) {

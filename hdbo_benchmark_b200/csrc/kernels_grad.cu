@@ -298,6 +298,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dz(DzParams p) {
     }
 }
 
+// the same epilogue on a product P = C Xs that the generic GEMM already formed (few-candidate path of posterior_bwd)
+__global__ void k_dz_finish(const double* __restrict__ P, int ldp, long long bsP, const double* __restrict__ Zs, int ldz, long long bsZ,
+                            const double* __restrict__ csum, long long bscs, const double* __restrict__ inv_ls, int m, int d,
+                            double* __restrict__ dZ, int lddz, long long bsdz) {
+    const int b = blockIdx.y;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)m * d) return;
+    const int c = (int)(idx / d), k = (int)(idx - (long long)c * d);
+    dZ[b * bsdz + (size_t)c * lddz + k] =
+        2.0 * inv_ls[(size_t)b * d + k] * (Zs[b * bsZ + (size_t)c * ldz + k] * csum[b * bscs + c] - P[b * bsP + (size_t)c * ldp + k]);
+}
+
 // joint covariance of each q-group: Sigma[a][b] = os k(r2(z_a,z_b)) - V_a.V_b (+ noise on the diagonal).  One block per group.
 __global__ void k_joint_cov(const double* __restrict__ Zs, int ldz, long long bsZ, const double* __restrict__ V, int ldv,
                             long long bsV, const double* __restrict__ hyp, int q, int kind, int observation_noise,
@@ -399,6 +411,25 @@ cudaError_t posterior_bwd(const hdbo_gp* gp, const BwdBuffers& w, int64_t rows_a
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     // (4) dZ = 2/l o (z csum - C Xs)
     if ((e = launch_transpose(gp->Xs, dp, (long long)np * dp, np, dp, w.XsT, np, (long long)dpt * np, dpt, B, st)) != cudaSuccess) return e;
+    if ((long long)mt * (dpt / 128) * B < 148 && dpt <= np) {
+        // few candidates (optimize_acqf inner loop): 128x128 tiles would leave most SMs idle for the whole k = n range; the
+        // generic GEMM cuts the product into 32x32 / 64x64 tiles, P lands in the (now free) dV scratch
+        GemmParams g{};
+        g.A = w.Kstar; g.B = w.XsT; g.C = w.T; g.Ct = nullptr;
+        g.lda = np; g.ldb = np; g.ldc = dpt; g.bsA = bsM; g.bsB = (long long)dpt * np; g.bsC = bsM;
+        g.mtiles = mt; g.ntiles = dpt / 128; g.kblocks = np / BK; g.krange = KR_FULL; g.lower_only = 0; g.alpha = 1.0; g.beta = 0.0;
+        if ((e = launch_gemm_nt(g, B, st)) != cudaSuccess) return e;
+        const long long tot = (long long)m * gp->d;
+        k_dz_finish<<<dim3((unsigned)((tot + 255) / 256), B), 256, 0, st>>>(w.T, dpt, bsM, w.Zs, dp, (long long)rows_alloc * dp, w.csum,
+                                                                             rows_alloc, gp->inv_ls, (int)m, gp->d, dZ, lddz, bsdz);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (gSigma && q > 1) {
+            k_dz_pairs<<<dim3((unsigned)(m / q), B), 256, 0, st>>>(w.Zs, dp, (long long)rows_alloc * dp, gSigma, bsS, gp->hyp, gp->inv_ls, q,
+                                                                   gp->d, gp->kind, dZ, lddz, bsdz);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
     static bool attr_done = false;
     if (!attr_done) {
         if ((e = cudaFuncSetAttribute(k_dz, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES)) != cudaSuccess) return e;
