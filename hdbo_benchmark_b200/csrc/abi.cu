@@ -120,8 +120,8 @@ PostWs carve(const hdbo_gp* gp, int64_t rows, int keep, void* base) {
     w.Kstar = take(B * rows * np);
     w.meanpart = take(B * 2 * nt * rows);  // the int8 kernels work on 64-column tiles: twice the partials
     w.varpart = take(B * 2 * nt * rows);
-    w.zscale = take(rows);
-    w.Zdig = reinterpret_cast<int8_t*>(take((size_t)I8_S * rows * rup(gp->d, 32) / 8));
+    w.zscale = take(B * rows);
+    w.Zdig = reinterpret_cast<int8_t*>(take(B * (size_t)I8_S * rows * rup(gp->d, 32) / 8));
     if (keep) {
         w.DK = take(B * rows * np);
         w.V = take(B * rows * np);
@@ -142,13 +142,13 @@ struct I8State {
     size_t bytes;
 };
 I8State carve_i8(const hdbo_gp* gp, void* base) {
-    const size_t np = gp->n_pad, d32 = rup(gp->d, 32);
+    const size_t np = gp->n_pad, d32 = rup(gp->d, 32), B = gp->batch;   // per-GP blocks are contiguous inside each array
     I8State s{};
     char* p = (char*)base;
-    s.digits = (int8_t*)p;  p += (size_t)I8_S * np * np;
-    s.scale = (double*)p;   p += np * sizeof(double);
-    s.Xdig = (int8_t*)p;    p += (size_t)I8_S * np * d32;
-    s.xscale = (double*)p;  p += np * sizeof(double);
+    s.digits = (int8_t*)p;  p += B * (size_t)I8_S * np * np;
+    s.scale = (double*)p;   p += B * np * sizeof(double);
+    s.Xdig = (int8_t*)p;    p += B * (size_t)I8_S * np * d32;
+    s.xscale = (double*)p;  p += B * np * sizeof(double);
     s.flag = (int32_t*)p;   p += 16;
     s.bytes = (size_t)(p - (char*)base);
     return s;
@@ -164,15 +164,15 @@ cudaError_t posterior_chunk(const hdbo_gp* gp, const PostWs& w, int64_t rows_all
     if (i8) {
         // whole chunk on the int8 tensor cores: candidate digit images -> K* digit images + mean partials -> variance partials
         int8_t* Kimg = reinterpret_cast<int8_t*>(w.Kstar);   // tile images: 6 bytes per element of the 8-byte K* slab
-        e = launch_slice_rows(128, Z, ldz, (int)mc, rp, gp->d, gp->center, gp->inv_ls, w.Zdig, w.zscale, w.zn, st);
+        e = launch_slice_rows(128, Z, ldz, (int)mc, rp, gp->d, gp->center, gp->inv_ls, w.Zdig, w.zscale, w.zn, rows_alloc, B, st);
         if (e != cudaSuccess) return e;
         prof_mark(0, st);
         e = launch_cross_i8(gp->kind, w.Zdig, i8->Xdig, w.zscale, i8->xscale, w.zn, gp->xn, gp->alpha, gp->hyp, Kimg, w.meanpart,
-                            (int)mc, gp->n, rp, np, gp->d, i8->flag, st);
+                            (int)mc, gp->n, rp, (int)rows_alloc, np, gp->d, B, i8->flag, st);
         prof_mark(0, st);
         if (e != cudaSuccess) return e;
         prof_mark(1, st);
-        e = launch_var_i8(Kimg, rp, i8->digits, i8->scale, gp->hyp, np, w.varpart, i8->flag, st);
+        e = launch_var_i8(Kimg, rp, (int)rows_alloc, i8->digits, i8->scale, gp->hyp, np, w.varpart, B, i8->flag, st);
         prof_mark(1, st);
         return e;
     }
@@ -181,7 +181,7 @@ cudaError_t posterior_chunk(const hdbo_gp* gp, const PostWs& w, int64_t rows_all
     c.Kstar = w.Kstar; c.DK = keep ? w.DK : nullptr; c.meanpart = w.meanpart;
     c.ldz = dp; c.ldx = dp; c.ldk = np;
     c.bsZ = (long long)rows_alloc * dp; c.bsX = (long long)np * dp; c.bszn = rows_alloc; c.bsxn = np; c.bsalpha = np;
-    c.bsK = (long long)rows_alloc * np; c.bsmp = (long long)nt * rows_alloc;
+    c.bsK = (long long)rows_alloc * np; c.bsmp = 2LL * nt * rows_alloc;
     c.m = (int)mc; c.n = gp->n; c.mtiles = mt; c.ntiles = nt; c.kblocks = dp / BK; c.kind = gp->kind;
     e = launch_scale_inputs(Z, (int)ldz, 0, (int)mc, gp->d, gp->center, gp->inv_ls, gp->d, w.Zs, dp, rp,
                             (long long)rows_alloc * dp, w.zn, rows_alloc, B, st);
@@ -266,24 +266,25 @@ extern "C" int hdbo_posterior_acq(const hdbo_gp* gp, const double* Z, int64_t ld
 
 // ---- exact int8 (tcgen05) variance path: digit planes of L^-1 once per fit, then the pool evaluation ----
 extern "C" size_t hdbo_i8_state_bytes(const hdbo_gp* gp) {
-    if (check_gp(gp) || gp->batch != 1 || gp->n_pad > I8_MAX_N_PAD) return 0;   // int32 group sums: see i8.cuh
+    if (check_gp(gp) || gp->n_pad > I8_MAX_N_PAD) return 0;   // int32 group sums: see i8.cuh
     return carve_i8(gp, nullptr).bytes;
 }
 
 extern "C" int32_t* hdbo_i8_state_flag(const hdbo_gp* gp, void* i8_state) {
-    if (check_gp(gp) || gp->batch != 1 || !i8_state) return nullptr;
+    if (check_gp(gp) || !i8_state) return nullptr;
     return carve_i8(gp, i8_state).flag;
 }
 
 extern "C" int hdbo_gp_slice_linv(const hdbo_gp* gp, void* i8_state, void* stream_) {
     if (int e = check_gp(gp)) return e;
-    if (gp->batch != 1 || gp->n_pad > I8_MAX_N_PAD) return -1;
+    if (gp->n_pad > I8_MAX_N_PAD) return -1;
     if (!i8_state || ((uintptr_t)i8_state & 127)) return -2;
     cudaStream_t st = (cudaStream_t)stream_;
     I8State s = carve_i8(gp, i8_state);
     TRY_CUDA(cudaMemsetAsync(s.flag, 0, 16, st));
-    TRY_CUDA(launch_slice_linv(gp->Linv, gp->n_pad, gp->n_pad, s.digits, s.scale, st));
-    TRY_CUDA(launch_slice_rows(64, gp->X, gp->ldx, gp->n, gp->n_pad, gp->d, gp->center, gp->inv_ls, s.Xdig, s.xscale, nullptr, st));
+    TRY_CUDA(launch_slice_linv(gp->Linv, gp->n_pad, gp->n_pad, s.digits, s.scale, gp->batch, st));
+    TRY_CUDA(launch_slice_rows(64, gp->X, gp->ldx, gp->n, gp->n_pad, gp->d, gp->center, gp->inv_ls, s.Xdig, s.xscale, nullptr,
+                               gp->n_pad, gp->batch, st));
     return 0;
 }
 
@@ -291,7 +292,7 @@ extern "C" int hdbo_posterior_acq_i8(const hdbo_gp* gp, void* i8_state, const do
                                      int observation_noise, int acq_kind, double acq_param, double* mean, double* var, double* acq,
                                      int64_t bso, void* workspace, size_t workspace_bytes, void* stream_) {
     if (int e = check_gp(gp)) return e;
-    if (gp->batch != 1 || gp->n_pad > I8_MAX_N_PAD) return -1;
+    if (gp->n_pad > I8_MAX_N_PAD) return -1;
     if (!i8_state || ((uintptr_t)i8_state & 127)) return -2;
     if (workspace && ((uintptr_t)workspace & 127)) return -13;
     I8State s = carve_i8(gp, i8_state);

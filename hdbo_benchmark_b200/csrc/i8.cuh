@@ -39,14 +39,16 @@ __device__ __forceinline__ void i8_signed_digits(long long X, unsigned (&d)[I8_S
 
 __device__ __forceinline__ double i8_pow2(int e) { return __longlong_as_double((long long)(1023 + e) << 52); }
 
-cudaError_t launch_slice_linv(const double* Linv, int ld, int n_pad, int8_t* img, double* scale, cudaStream_t st);
+// batch = number of GPs that share inputs but differ in hyper-parameters (SAAS samples); per-GP data is contiguous per GP
+cudaError_t launch_slice_linv(const double* Linv, int ld, int n_pad, int8_t* img, double* scale, int batch, cudaStream_t st);
 cudaError_t launch_slice_rows(int rows_per_tile, const double* X, long long ldx, int rows_valid, int rows_pad, int d, const double* center,
-                              const double* inv_ls, int8_t* img, double* scale, double* norms, cudaStream_t st);
+                              const double* inv_ls, int8_t* img, double* scale, double* norms, long long bs_rows, int batch,
+                              cudaStream_t st);
 cudaError_t launch_cross_i8(int kind, const int8_t* Zimg, const int8_t* Ximg, const double* zscale, const double* xscale, const double* zn,
                             const double* xn, const double* alpha, const double* hyp, int8_t* Kimg, double* meanpart, int m, int n,
-                            int rows_pad, int n_pad, int d, int* flag, cudaStream_t st);
-cudaError_t launch_var_i8(const int8_t* Aimg, int rows_pad, const int8_t* Bimg, const double* colscale, const double* hyp,
-                          int n_pad, double* varpart, int* flag, cudaStream_t st);
+                            int rows_pad, int rows_alloc, int n_pad, int d, int batch, int* flag, cudaStream_t st);
+cudaError_t launch_var_i8(const int8_t* Aimg, int rows_pad, int rows_alloc, const int8_t* Bimg, const double* colscale, const double* hyp,
+                          int n_pad, double* varpart, int batch, int* flag, cudaStream_t st);
 cudaError_t launch_i8_peak(int iters, int sms, int* flag, double* ops_out, cudaStream_t st);
 
 }  // namespace hdbo

@@ -129,7 +129,7 @@ __global__ void k_finalize_acq(const double* __restrict__ meanpart, const double
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     double sm = 0.0, sv = 0.0;
-    for (int t = 0; t < ntiles; t++) sm += meanpart[b * bsp + (size_t)t * rows_pad + i];
+    for (int t = 0; t < ntiles; t++) sm += meanpart[b * 2 * bsp + (size_t)t * rows_pad + i];
     for (int t = 0; t < ntiles_var; t++) sv += varpart[b * 2 * bsp + (size_t)t * rows_pad + i];
     const double os = hyp[b * 4 + 0], noise = hyp[b * 4 + 1], m0 = hyp[b * 4 + 2];
     const double mean = m0 + sm;

@@ -32,6 +32,8 @@ __global__ void k_slice_linv(const double* __restrict__ Linv, int ld, int n_pad,
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= n_pad) return;
+    const size_t b = blockIdx.y;                         // batch: matrices / image sets / scale vectors are contiguous per GP
+    Linv += b * (size_t)n_pad * ld; img += b * (size_t)I8_S * n_pad * n_pad; scale += b * n_pad;
     const double* src = Linv + (size_t)row * ld;
     double mx = 0.0;
     for (int j = lane; j <= row; j += 32) mx = fmax(mx, fabs(src[j]));
@@ -53,8 +55,8 @@ __global__ void k_slice_linv(const double* __restrict__ Linv, int ld, int n_pad,
     }
 }
 
-cudaError_t launch_slice_linv(const double* Linv, int ld, int n_pad, int8_t* img, double* scale, cudaStream_t st) {
-    k_slice_linv<<<(n_pad + 7) / 8, 256, 0, st>>>(Linv, ld, n_pad, img, scale);
+cudaError_t launch_slice_linv(const double* Linv, int ld, int n_pad, int8_t* img, double* scale, int batch, cudaStream_t st) {
+    k_slice_linv<<<dim3((n_pad + 7) / 8, batch), 256, 0, st>>>(Linv, ld, n_pad, img, scale);
     return cudaGetLastError();
 }
 
@@ -64,11 +66,14 @@ cudaError_t launch_slice_linv(const double* Linv, int ld, int n_pad, int8_t* img
 template <int ROWS>
 __global__ void k_slice_rows(const double* __restrict__ X, long long ldx, int rows_valid, int rows_pad, int d,
                              const double* __restrict__ center, const double* __restrict__ inv_ls, int8_t* __restrict__ img,
-                             double* __restrict__ scale, double* __restrict__ norms) {
+                             double* __restrict__ scale, double* __restrict__ norms, long long bs_rows) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows_pad) return;
     const int nkb = (d + 31) >> 5, tile = row / ROWS, r = row % ROWS;
+    const size_t b = blockIdx.y;                         // batch: per-GP lengthscales; outputs strided by bs_rows rows
+    inv_ls += b * d; img += b * (size_t)bs_rows * nkb * 32 * I8_S; scale += b * bs_rows;
+    if (norms) norms += b * bs_rows;
     const bool live = row < rows_valid;
     const double* src = X + (size_t)row * ldx;
     double mx = 0.0, ss = 0.0;
@@ -93,11 +98,12 @@ __global__ void k_slice_rows(const double* __restrict__ X, long long ldx, int ro
 }
 
 cudaError_t launch_slice_rows(int rows_per_tile, const double* X, long long ldx, int rows_valid, int rows_pad, int d, const double* center,
-                              const double* inv_ls, int8_t* img, double* scale, double* norms, cudaStream_t st) {
+                              const double* inv_ls, int8_t* img, double* scale, double* norms, long long bs_rows, int batch,
+                              cudaStream_t st) {
     if (rows_pad == 0) return cudaSuccess;
-    const int grid = (rows_pad + 7) / 8;
-    if (rows_per_tile == 128) k_slice_rows<128><<<grid, 256, 0, st>>>(X, ldx, rows_valid, rows_pad, d, center, inv_ls, img, scale, norms);
-    else k_slice_rows<64><<<grid, 256, 0, st>>>(X, ldx, rows_valid, rows_pad, d, center, inv_ls, img, scale, norms);
+    const dim3 grid((rows_pad + 7) / 8, batch);
+    if (rows_per_tile == 128) k_slice_rows<128><<<grid, 256, 0, st>>>(X, ldx, rows_valid, rows_pad, d, center, inv_ls, img, scale, norms, bs_rows);
+    else k_slice_rows<64><<<grid, 256, 0, st>>>(X, ldx, rows_valid, rows_pad, d, center, inv_ls, img, scale, norms, bs_rows);
     return cudaGetLastError();
 }
 
@@ -316,6 +322,9 @@ struct CrossI8Params {
     double* meanpart;         // out: [ntiles64][rows_pad]
     int m, n, rows_pad, ntiles64, ntiles, nkb_d, nkb_n;
     int* flag;
+    // batch (SAAS hyper-samples): tiles [b][bm][bn]; per-GP strides
+    int tiles_per_gp, n_pad, rows_alloc;
+    long long bsK;            // bytes between the K* image sets of consecutive GPs
 };
 
 // 576 threads: warp 0 producer, warp 1 MMA issuer, warps 2-17 epilogue (four warps per TMEM lane quarter, 16 columns each: the
@@ -333,8 +342,10 @@ __global__ void __launch_bounds__(CE_THREADS, 1) k_cross_i8(CrossI8Params p) {
     if (warp == 0 && lane == 0) {
         uint32_t kbg = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-            const int bn = t % p.ntiles64, bm = t / p.ntiles64;
-            if (!i8_pipe_produce(pp, p.Zimg + (size_t)bm * p.nkb_d * VT_A_STAGE, p.Ximg + (size_t)bn * p.nkb_d * VT_B_STAGE, p.nkb_d, kbg, p.flag)) break;
+            const int b = t / p.tiles_per_gp, tt = t - b * p.tiles_per_gp, bn = tt % p.ntiles64, bm = tt / p.ntiles64;
+            const int8_t* zi = p.Zimg + (size_t)b * p.rows_alloc * p.nkb_d * 32 * I8_S;
+            const int8_t* xi = p.Ximg + (size_t)b * p.n_pad * p.nkb_d * 32 * I8_S;
+            if (!i8_pipe_produce(pp, zi + (size_t)bm * p.nkb_d * VT_A_STAGE, xi + (size_t)bn * p.nkb_d * VT_B_STAGE, p.nkb_d, kbg, p.flag)) break;
         }
     } else if (warp == 1 && lane == 0) {
         uint32_t kbg = 0, it = 0;
@@ -345,15 +356,16 @@ __global__ void __launch_bounds__(CE_THREADS, 1) k_cross_i8(CrossI8Params p) {
     if (warp >= 2) {
         const int q = warp & 3, sl = (warp - 2) >> 2, row = q * 32 + lane;   // sl: 16-column slice of the tile
         const int swz = (row >> 2) & 1;
-        const double os = p.hyp[0];
         uint32_t it = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, it++) {
-            const int bn = t % p.ntiles64, bm = t / p.ntiles64, grow = bm * VT_M + row;
+            const int b = t / p.tiles_per_gp, tt = t - b * p.tiles_per_gp, bn = tt % p.ntiles64, bm = tt / p.ntiles64, grow = bm * VT_M + row;
+            const double os = p.hyp[b * 4];
             if (tid >= 64 && tid < 64 + VT_N) {            // (the previous tile's readers passed the s_ms barrier below)
-                const int c = bn * VT_N + tid - 64;
+                const size_t c = (size_t)b * p.n_pad + bn * VT_N + tid - 64;
                 s_xn[tid - 64] = p.xn[c]; s_xs[tid - 64] = p.xscale[c]; s_al[tid - 64] = p.alpha[c];
             }
-            const double znr = p.zn[grow], m2sz = -2.0 * p.zscale[grow];
+            const size_t zr = (size_t)b * p.rows_alloc + grow;
+            const double znr = p.zn[zr], m2sz = -2.0 * p.zscale[zr];
             const bool rowvalid = grow < p.m;
             const bool ok = i8_pipe_wait_accum(pp, it, p.flag);
             double v[16];
@@ -393,14 +405,14 @@ __global__ void __launch_bounds__(CE_THREADS, 1) k_cross_i8(CrossI8Params p) {
                 dg[1][jq] = HDBO_GATHER(hi, 0x0040); dg[0][jq] = HDBO_GATHER(hi, 0x0051);
 #undef HDBO_GATHER
             }
-            int8_t* dst = p.Kimg + ((size_t)bm * p.nkb_n + bn * 2 + (sl >> 1)) * VT_A_STAGE + row * 32 + (((sl & 1) ^ swz) << 4);
+            int8_t* dst = p.Kimg + (size_t)b * p.bsK + ((size_t)bm * p.nkb_n + bn * 2 + (sl >> 1)) * VT_A_STAGE + row * 32 + (((sl & 1) ^ swz) << 4);
 #pragma unroll
             for (int tt = 0; tt < I8_S; tt++)
                 *reinterpret_cast<uint4*>(dst + tt * VT_M * 32) = make_uint4(dg[tt][0], dg[tt][1], dg[tt][2], dg[tt][3]);
             if (!ok) msum = __longlong_as_double(0x7ff8000000000000LL);
             if (sl) s_ms[sl - 1][row] = msum;
             asm volatile("bar.sync 1, %0;" ::"n"(CE_WARPS * 32) : "memory");
-            if (!sl) p.meanpart[(size_t)bn * p.rows_pad + grow] = ((msum + s_ms[0][row]) + s_ms[1][row]) + s_ms[2][row];
+            if (!sl) p.meanpart[(size_t)b * p.ntiles64 * p.rows_alloc + (size_t)bn * p.rows_pad + grow] = ((msum + s_ms[0][row]) + s_ms[1][row]) + s_ms[2][row];
         }
     }
     i8_pipe_teardown(pp);
@@ -408,7 +420,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1) k_cross_i8(CrossI8Params p) {
 
 cudaError_t launch_cross_i8(int kind, const int8_t* Zimg, const int8_t* Ximg, const double* zscale, const double* xscale, const double* zn,
                             const double* xn, const double* alpha, const double* hyp, int8_t* Kimg, double* meanpart, int m, int n,
-                            int rows_pad, int n_pad, int d, int* flag, cudaStream_t st) {
+                            int rows_pad, int rows_alloc, int n_pad, int d, int batch, int* flag, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(k_cross_i8<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM);
@@ -416,9 +428,9 @@ cudaError_t launch_cross_i8(int kind, const int8_t* Zimg, const int8_t* Ximg, co
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    const int ntiles = (rows_pad / VT_M) * (n_pad / VT_N);
+    const int per_gp = (rows_pad / VT_M) * (n_pad / VT_N), ntiles = per_gp * batch;
     CrossI8Params p{Zimg, Ximg, zscale, xscale, zn, xn, alpha, hyp, Kimg, meanpart, m, n, rows_pad, n_pad / VT_N, ntiles, (d + 31) / 32,
-                    n_pad / VT_KB, flag};
+                    n_pad / VT_KB, flag, per_gp, n_pad, rows_alloc, (long long)rows_alloc * n_pad * 8};
     const int grid = ntiles < i8_sm_count() ? ntiles : i8_sm_count();
     if (kind == 0) k_cross_i8<0><<<grid, CE_THREADS, VT_SMEM, st>>>(p);
     else k_cross_i8<1><<<grid, CE_THREADS, VT_SMEM, st>>>(p);
@@ -436,6 +448,8 @@ struct VarI8Params {
     double* varpart;          // [ntiles64][rows_pad]
     int rows_pad, ntiles64, mtiles, nkb, nslots, nwaves;
     int* flag;                // set when a barrier wait timed out (results are then poisoned with NaN)
+    int slots_per_gp, n_pad, rows_alloc;   // batch: slots [b][...]; per-GP strides derive from these
+    long long bsK;                         // bytes between the K* image sets of consecutive GPs
 };
 
 // Tile list of k_var_i8.  Slots t are rasterised so that tiles processed at the same time by the 148 CTAs (t .. t+147) cover
@@ -443,10 +457,11 @@ struct VarI8Params {
 // column tile (the A images of a chunk are 4x the L2).  Column-tile groups with the longest k-range come first.  CTA c takes the
 // slots w G + c of the even "waves" w and w G + (G-1-c) of the odd ones (serpentine): with round-robin, CTA 0 always got the
 // heaviest tile of a wave (4.2 % static imbalance in the k-block count, 7 % measured); serpentine balances it to < 0.1 %.
-__device__ __forceinline__ bool var_tile(const VarI8Params& p, int wave, int& bm, int& bn) {
+__device__ __forceinline__ bool var_tile(const VarI8Params& p, int wave, int& b, int& bm, int& bn) {
     const int G = gridDim.x, c = (wave & 1) ? G - 1 - (int)blockIdx.x : (int)blockIdx.x;
-    const int t = wave * G + c;
+    int t = wave * G + c;
     if (t >= p.nslots) return false;
+    b = t / p.slots_per_gp; t -= b * p.slots_per_gp;
     const int per_group = p.mtiles * VT_GN;
     const int grp = t / per_group, rem = t - grp * per_group;
     bm = rem / VT_GN; bn = p.ntiles64 - 1 - (grp * VT_GN + rem % VT_GN);
@@ -457,28 +472,29 @@ __global__ void __launch_bounds__(192, 1) k_var_i8(VarI8Params p) {
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const I8Pipe pp = i8_pipe_setup(smem_raw, 4);
-    int bm, bn;
+    int b, bm, bn;
     if (warp == 0 && lane == 0) {
         uint32_t kbg = 0;
         for (int wv = 0; wv < p.nwaves; wv++) {
-            if (!var_tile(p, wv, bm, bn)) continue;
-            if (!i8_pipe_produce(pp, p.Aimg + (size_t)bm * p.nkb * VT_A_STAGE, p.Bimg + (size_t)bn * p.nkb * VT_B_STAGE,
+            if (!var_tile(p, wv, b, bm, bn)) continue;
+            if (!i8_pipe_produce(pp, p.Aimg + (size_t)b * p.bsK + (size_t)bm * p.nkb * VT_A_STAGE,
+                                 p.Bimg + (size_t)b * I8_S * p.n_pad * p.n_pad + (size_t)bn * p.nkb * VT_B_STAGE,
                                  (bn + 1) * (VT_N / VT_KB), kbg, p.flag)) break;
         }
     } else if (warp == 1 && lane == 0) {
         uint32_t kbg = 0, it = 0;
         for (int wv = 0; wv < p.nwaves; wv++) {
-            if (!var_tile(p, wv, bm, bn)) continue;
+            if (!var_tile(p, wv, b, bm, bn)) continue;
             if (!i8_pipe_mma<false, HDBO_VAR_A_TMEM>(pp, (bn + 1) * (VT_N / VT_KB), kbg, it++, p.flag)) break;
         }
     }
     __syncwarp();
     if (warp >= 2) {                         // ---- epilogue: FP64 recombination of the 6 weight groups, column scale, row sum of squares ----
         const int q = warp & 3;              // TMEM lane quarter this warp may access
-        const double os = p.hyp[0];
         uint32_t it = 0;
         for (int wv = 0; wv < p.nwaves; wv++) {
-            if (!var_tile(p, wv, bm, bn)) continue;
+            if (!var_tile(p, wv, b, bm, bn)) continue;
+            const double os = p.hyp[b * 4];
             const bool ok = i8_pipe_wait_accum(pp, it++, p.flag);
             double ssq = 0.0;
 #pragma unroll
@@ -495,20 +511,20 @@ __global__ void __launch_bounds__(192, 1) k_var_i8(VarI8Params p) {
                     for (int j = 0; j < 32; j++) v[j] = fma(w, (double)(int32_t)r[j], v[j]);
                 }
                 if (ch == VT_N / 32 - 1) i8_pipe_release_tmem(pp);
-                const double* cs = p.colscale + bn * VT_N + ch * 32;
+                const double* cs = p.colscale + (size_t)b * p.n_pad + bn * VT_N + ch * 32;
 #pragma unroll
                 for (int j = 0; j < 32; j++) { const double x = v[j] * (os * cs[j]); ssq = fma(x, x, ssq); }
             }
             if (!ok) ssq = __longlong_as_double(0x7ff8000000000000LL);
-            p.varpart[(size_t)bn * p.rows_pad + bm * VT_M + q * 32 + lane] = ssq;
+            p.varpart[(size_t)b * p.ntiles64 * p.rows_alloc + (size_t)bn * p.rows_pad + bm * VT_M + q * 32 + lane] = ssq;
         }
     }
     i8_pipe_teardown(pp);
 }
 
 // Aimg: K* digit images for rows_pad / 128 row tiles; Bimg: L^-1 digit images (layout at the top of this file)
-cudaError_t launch_var_i8(const int8_t* Aimg, int rows_pad, const int8_t* Bimg, const double* colscale, const double* hyp,
-                          int n_pad, double* varpart, int* flag, cudaStream_t st) {
+cudaError_t launch_var_i8(const int8_t* Aimg, int rows_pad, int rows_alloc, const int8_t* Bimg, const double* colscale, const double* hyp,
+                          int n_pad, double* varpart, int batch, int* flag, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(k_var_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM);
@@ -516,9 +532,11 @@ cudaError_t launch_var_i8(const int8_t* Aimg, int rows_pad, const int8_t* Bimg, 
         attr_done = true;
     }
     const int mt = rows_pad / VT_M, nt = n_pad / VT_N, groups = (nt + VT_GN - 1) / VT_GN;
-    const int nslots = mt * VT_GN * groups;
-    const int grid = mt * nt < i8_sm_count() ? mt * nt : i8_sm_count();
-    VarI8Params p{Aimg, Bimg, colscale, hyp, varpart, rows_pad, nt, mt, n_pad / VT_KB, nslots, (nslots + grid - 1) / grid, flag};
+    const int per_gp = mt * VT_GN * groups, nslots = per_gp * batch;
+    const long long live = (long long)mt * nt * batch;
+    const int grid = live < i8_sm_count() ? (int)live : i8_sm_count();
+    VarI8Params p{Aimg, Bimg, colscale, hyp, varpart, rows_pad, nt, mt, n_pad / VT_KB, nslots, (nslots + grid - 1) / grid, flag,
+                  per_gp, n_pad, rows_alloc, (long long)rows_alloc * n_pad * 8};
     k_var_i8<<<grid, 192, VT_SMEM, st>>>(p);
     return cudaGetLastError();
 }

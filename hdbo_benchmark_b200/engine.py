@@ -43,7 +43,7 @@ class DeviceGP:
     def __init__(self, X: torch.Tensor, y: torch.Tensor, kind: int, batch: int = 1, keep_r2: bool = False,
                  var_mode: Optional[str] = None):
         """var_mode: "f64" (FP64 DMMA variance contraction, the default) or "i8" (exact digit-sliced int8 contraction on the
-        tcgen05 tensor cores for the no-grad pool evaluation; batch == 1).  Default from $HDBO_VAR_MODE."""
+        tcgen05 tensor cores for the no-grad pool evaluation, n_pad <= 8192).  Default from $HDBO_VAR_MODE."""
         if not X.is_cuda:
             raise _lib.HdboError("DeviceGP needs CUDA tensors: the hot path has no CPU implementation")
         self.lib = _lib.load()
@@ -81,8 +81,6 @@ class DeviceGP:
         self.var_mode = (var_mode or os.environ.get("HDBO_VAR_MODE", "f64")).lower()
         if self.var_mode not in ("f64", "i8"):
             raise ValueError(f"var_mode must be 'f64' or 'i8', got {self.var_mode!r}")
-        if self.batch != 1:
-            self.var_mode = "f64"
         self._i8_state: Optional[torch.Tensor] = None
         self._i8_dirty = True
         self.desc = HdboGp(

@@ -136,15 +136,13 @@ def test_i8_c_abi_argument_checks(cuda_device):
     lib = _lib.load()
     X, y, ls, os_, nz, mu = O.synthetic_problem(100, 5)
     gpb = DeviceGP(X.to(cuda_device), y.to(cuda_device), O.MATERN52, batch=2, var_mode="i8")
-    assert gpb.var_mode == "f64"                                   # batched (SAAS) GPs stay on the FP64 path
-    assert lib.hdbo_i8_state_bytes(C.byref(gpb.desc)) == 0
     gp = _gp(X, y, O.MATERN52, (ls, os_, nz, mu), cuda_device, "i8")
     need = lib.hdbo_i8_state_bytes(C.byref(gp.desc))
     assert need == 6 * 128 * 128 + 8 * 128 + 6 * 128 * 32 + 8 * 128 + 16   # L^-1 images + scales, X images + scales, flag
+    assert lib.hdbo_i8_state_bytes(C.byref(gpb.desc)) == 2 * (need - 16) + 16   # batched (SAAS) GPs: per-GP blocks
     state = torch.empty(need + 256, dtype=torch.uint8, device=cuda_device)
     assert lib.hdbo_gp_slice_linv(C.byref(gp.desc), state.data_ptr() + 8, 0) == -2      # misaligned state
     assert lib.hdbo_gp_slice_linv(C.byref(gp.desc), 0, 0) == -2
-    assert lib.hdbo_gp_slice_linv(C.byref(gpb.desc), state.data_ptr(), 0) == -1
     Z = torch.rand(10, 5, dtype=torch.float64, device=cuda_device)
     out = torch.empty(10, dtype=torch.float64, device=cuda_device)
     ws = gp.workspace(128)
@@ -209,3 +207,34 @@ def test_i8_mode_through_the_botorch_surface(cuda_device, monkeypatch):
         Zg = Z[:30].clone().unsqueeze(1).requires_grad_(True)
         (g,) = torch.autograd.grad(f(Zg).sum(), Zg)
         assert float((g.squeeze(1).cpu() - g_o).abs().max()) < REL * float(g_o.abs().max())
+
+
+def test_i8_saas_batch_matches_per_sample_oracle(cuda_device):
+    """A10 on the int8 path: S GPs with their own lengthscales / outputscales / noises, one batched launch sequence."""
+    from hdbo_benchmark_b200 import _lib
+    from hdbo_benchmark_b200.engine import DeviceGP
+    from hdbo_benchmark_b200.models import sample_saas_prior
+
+    n, d, S, m = 150, 70, 5, 333
+    X, y, *_ = O.synthetic_problem(n, d)
+    smp = sample_saas_prior(S, d, seed=4)
+    states = O.saas_fit_states(X, y, smp["lengthscale"], smp["outputscale"], smp["noise"], smp["mean"])
+    Z = O.sobol_candidates(m, d, seed=9)
+    Z[:50] = X[:50]
+    mu_o, var_o, _, _ = O.saas_posterior(states, Z)
+    best = float(y.max())
+    out = {}
+    for mode in ("f64", "i8"):
+        gp = DeviceGP(X.to(cuda_device), y.to(cuda_device), O.MATERN52, batch=S, var_mode=mode)
+        gp.set_hyper(smp["lengthscale"].to(cuda_device), smp["outputscale"], smp["noise"], smp["mean"])
+        gp.fit()
+        for chunk in (128, 148 * 128):
+            mean, var, acq = gp.posterior_acq(Z.to(cuda_device), _lib.ACQ_LOGEI, best, chunk_rows=chunk)
+            assert mean.shape == (S, m)
+            assert float((mean.cpu() - mu_o).abs().max()) < REL * float(mu_o.abs().max())
+            assert float(((var.cpu() - var_o).abs() / var_o.abs()).max()) < REL
+        out[mode] = acq.cpu()
+        assert gp.i8_flag() == 0
+    a_o = O.log_expected_improvement(mu_o, var_o, best)
+    assert float((out["i8"] - a_o).abs().max()) < REL * max(1.0, float(a_o.abs().max()))
+    assert torch.equal(out["i8"].argmax(dim=1), out["f64"].argmax(dim=1))
