@@ -238,3 +238,31 @@ def test_i8_saas_batch_matches_per_sample_oracle(cuda_device):
     a_o = O.log_expected_improvement(mu_o, var_o, best)
     assert float((out["i8"] - a_o).abs().max()) < REL * max(1.0, float(a_o.abs().max()))
     assert torch.equal(out["i8"].argmax(dim=1), out["f64"].argmax(dim=1))
+
+
+def test_i8_largest_supported_size_and_fallback_beyond_it(cuda_device):
+    """n_pad = 8192 is the largest size whose int32 digit-group sums are guaranteed exact (csrc/i8.cuh); beyond it the engine
+    silently keeps the FP64 DMMA path."""
+    from hdbo_benchmark_b200 import _lib
+    from hdbo_benchmark_b200.engine import DeviceGP
+
+    d, m = 16, 300
+    g = torch.Generator().manual_seed(0)
+    for n, expect_i8 in ((8192, True), (8200, False)):
+        X = torch.rand(n, d, generator=g, dtype=torch.float64)
+        y = torch.sin(3.0 * X[:, :3].sum(-1)) + 0.05 * torch.randn(n, generator=g, dtype=torch.float64)
+        ls = torch.full((d,), 0.9, dtype=torch.float64)
+        Z = torch.rand(m, d, generator=g, dtype=torch.float64).to(cuda_device)
+        res = {}
+        for mode in ("f64", "i8"):
+            gp = DeviceGP(X.to(cuda_device), y.to(cuda_device), O.MATERN52, var_mode=mode)
+            gp.set_hyper(ls.to(cuda_device), 1.0, 1e-2, 0.0)
+            gp.fit()
+            mean, var, _ = gp.posterior_acq(Z, _lib.ACQ_NONE)
+            res[mode] = (mean[0].clone(), var[0].clone())
+            if mode == "i8":
+                assert (gp._i8_state is not None) == expect_i8 and gp.i8_flag() == 0
+            del gp
+        assert float((res["i8"][0] - res["f64"][0]).abs().max()) < 1e-9 * float(res["f64"][0].abs().max())
+        assert float(((res["i8"][1] - res["f64"][1]).abs() / res["f64"][1].abs()).max()) < REL
+        torch.cuda.empty_cache()
