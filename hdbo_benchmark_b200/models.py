@@ -333,7 +333,6 @@ class SingleTaskGP(ExactGPBase):
                 prior = LogNormalPrior(SQRT2 + 0.5 * math.log(d), SQRT3)
                 covar_module = RBFKernel(ard_num_dims=d, lengthscale_prior=prior, lengthscale_constraint=GreaterThan(
                     2.5e-2, transform=None, initial_value=float(prior.mode)))
-        self._user_covar = covar_module
         self.likelihood = likelihood
         self.covar_module = covar_module
         self.mean_module = mean_module if mean_module is not None else ConstantMean()

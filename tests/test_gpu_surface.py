@@ -222,3 +222,71 @@ def test_fit_gpytorch_mll_and_optimize_acqf_end_to_end(cuda_device):
     raw = draw_sobol_samples(bounds, 256, 1, seed=1).squeeze(1)
     assert oracle_logei(cand)[0] >= oracle_logei(raw).max() - 1e-9
     assert abs(float(val) - float(oracle_logei(cand)[0])) < 1e-6 * max(1.0, abs(float(val)))
+
+
+@pytest.mark.parametrize("flavour", ["botorch_default", "legacy", "in_repo_rbf_scale", "isotropic"])
+def test_fast_mll_closure_matches_generic_closure(cuda_device, flavour):
+    """fit.py's fast closure (numpy transforms/priors + CUDA-graph replay of fit + gradient) against the generic autograd closure:
+    same -mll and raw-parameter gradient at several points, and fit_gpytorch_mll reaches the same optimum either way."""
+    import copy
+
+    import numpy as np
+
+    from hdbo_benchmark_b200 import gp_modules as G
+    from hdbo_benchmark_b200.fit import _FastClosure, _bounds_for, _named_raw_parameters, fit_gpytorch_mll
+    from hdbo_benchmark_b200.models import ExactMarginalLogLikelihood, SingleTaskGP
+
+    n, d = 90, 7
+    X, y, *_ = O.synthetic_problem(n, d, "prior", 1e-3, seed=6)
+    Y = 2.0 * y.unsqueeze(-1) - 1.0
+
+    def make():
+        if flavour == "botorch_default":
+            return SingleTaskGP(X, Y)
+        if flavour == "legacy":
+            return SingleTaskGP(X, Y, legacy_defaults=True)
+        if flavour == "in_repo_rbf_scale":     # /root/reference/src/hdbo_benchmark/utils/experiments/load_solvers.py:131-138
+            k = G.ScaleKernel(G.RBFKernel(ard_num_dims=d, lengthscale_prior=G.LogNormalPrior(0.5 * math.log(d), 1.0)))
+            return SingleTaskGP(X, Y, covar_module=k)
+        return SingleTaskGP(X, Y, covar_module=G.ScaleKernel(G.MaternKernel(lengthscale_prior=G.GammaPrior(3.0, 6.0)),
+                                                             outputscale_prior=G.GammaPrior(2.0, 0.15)))
+
+    model = make()
+    mll = ExactMarginalLogLikelihood(model.likelihood, model)
+    model.train()
+    params = _named_raw_parameters(mll)
+    fast = _FastClosure.build(mll, params)
+    assert fast is not None
+    x0 = np.concatenate([p.detach().cpu().numpy().reshape(-1) for _, p in params])
+    rng = np.random.default_rng(0)
+    lo = np.array([(-np.inf if b[0] is None else b[0] + 1e-3) for b in _bounds_for(mll, params)])
+    hi = np.array([(np.inf if b[1] is None else b[1] - 1e-3) for b in _bounds_for(mll, params)])
+    for k in range(4):
+        x = np.clip(x0 + 0.3 * k * rng.standard_normal(x0.shape), lo, hi)   # (untransformed parameters are box-bounded)
+        f_fast, g_fast = fast(x)
+        off = 0
+        with torch.no_grad():
+            for _, p in params:
+                p.copy_(torch.from_numpy(x[off:off + p.numel()]).view_as(p).to(p.device)); off += p.numel()
+        for _, p in params:
+            p.grad = None
+        loss = -mll(model(model.train_inputs[0]), model.train_targets).sum()
+        loss.backward()
+        g_ref = np.concatenate([p.grad.detach().cpu().numpy().reshape(-1) for _, p in params])
+        assert abs(f_fast - float(loss)) < 1e-9 * max(1.0, abs(float(loss)))
+        assert np.abs(g_fast - g_ref).max() < 1e-8 * max(1.0, np.abs(g_ref).max())
+    torch.manual_seed(0)
+    m_fast, m_slow = make(), make()
+    fit_gpytorch_mll(ExactMarginalLogLikelihood(m_fast.likelihood, m_fast))
+    fit_gpytorch_mll(ExactMarginalLogLikelihood(m_slow.likelihood, m_slow), optimizer_kwargs={"options": {"fast_closure": False}})
+    # both runs stop inside the same ftol-flat neighbourhood (tiny rounding differences change the L-BFGS path): equal optimum
+    # value to 1e-5, parameters to a few 1e-3
+    vals = []
+    for mdl in (m_fast, m_slow):
+        mdl.train()
+        mm = ExactMarginalLogLikelihood(mdl.likelihood, mdl)
+        with torch.no_grad():
+            vals.append(float(mm(mdl(mdl.train_inputs[0]), mdl.train_targets).sum()))
+    assert abs(vals[0] - vals[1]) < 1e-5 * max(1.0, abs(vals[1])), vals
+    for (na, pa), (nb, pb) in zip(m_fast.named_parameters(), m_slow.named_parameters()):
+        assert na == nb and float((pa - pb).abs().max()) < 2e-2 * max(1.0, float(pb.abs().max())), na
