@@ -438,7 +438,7 @@ cudaError_t launch_cross_i8(int kind, const int8_t* Zimg, const int8_t* Ximg, co
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// V = K* L^-T and its row sums of squares.  192 threads (4 epilogue warps).  Triangular k-range (L^-1 is lower triangular: only
+// V = K* L^-T and its row sums of squares.  Triangular k-range (L^-1 is lower triangular: only
 // k-blocks <= column tile).
 struct VarI8Params {
     const int8_t* Aimg;       // K* digit images (unsigned bytes), tile = 128 candidates
@@ -468,10 +468,13 @@ __device__ __forceinline__ bool var_tile(const VarI8Params& p, int wave, int& b,
     return bn >= 0;                                                 // (ntiles64 not a multiple of VT_GN: empty slots)
 }
 
-__global__ void __launch_bounds__(192, 1) k_var_i8(VarI8Params p) {
+// 320 threads: producer warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter, 32 columns each): the accumulators are
+// drained -- and TMEM handed back to the MMA issuer for the CTA's next tile -- in half the time of a 4-warp epilogue.
+__global__ void __launch_bounds__(320, 1) k_var_i8(VarI8Params p) {
     extern __shared__ uint8_t smem_raw[];
+    __shared__ double s_part[VT_M];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const I8Pipe pp = i8_pipe_setup(smem_raw, 4);
+    const I8Pipe pp = i8_pipe_setup(smem_raw, 8);
     int b, bm, bn;
     if (warp == 0 && lane == 0) {
         uint32_t kbg = 0;
@@ -490,33 +493,33 @@ __global__ void __launch_bounds__(192, 1) k_var_i8(VarI8Params p) {
     }
     __syncwarp();
     if (warp >= 2) {                         // ---- epilogue: FP64 recombination of the 6 weight groups, column scale, row sum of squares ----
-        const int q = warp & 3;              // TMEM lane quarter this warp may access
+        const int q = warp & 3, ch = (warp - 2) >> 2, row = q * 32 + lane;   // TMEM lane quarter, 32-column half of the tile
         uint32_t it = 0;
         for (int wv = 0; wv < p.nwaves; wv++) {
             if (!var_tile(p, wv, b, bm, bn)) continue;
             const double os = p.hyp[b * 4];
             const bool ok = i8_pipe_wait_accum(pp, it++, p.flag);
+            double v[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = 0.0;
+#pragma unroll
+            for (int g = I8_S - 1; g >= 0; g--) {      // smallest weights first; unsigned x signed: 2^-(8g+15)
+                uint32_t r[32];
+                tmem_ld32(pp.tmem_base + ((uint32_t)(q * 32) << 16) + g * VT_N + ch * 32, r);
+                const double w = i8_pow2(-(8 * g + 15));
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = fma(w, (double)(int32_t)r[j], v[j]);
+            }
+            i8_pipe_release_tmem(pp);
+            const double* cs = p.colscale + (size_t)b * p.n_pad + bn * VT_N + ch * 32;
             double ssq = 0.0;
 #pragma unroll
-            for (int ch = 0; ch < VT_N / 32; ch++) {
-                double v[32];
-#pragma unroll
-                for (int j = 0; j < 32; j++) v[j] = 0.0;
-#pragma unroll
-                for (int g = I8_S - 1; g >= 0; g--) {      // smallest weights first; unsigned x signed: 2^-(8g+15)
-                    uint32_t r[32];
-                    tmem_ld32(pp.tmem_base + ((uint32_t)(q * 32) << 16) + g * VT_N + ch * 32, r);
-                    const double w = i8_pow2(-(8 * g + 15));
-#pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = fma(w, (double)(int32_t)r[j], v[j]);
-                }
-                if (ch == VT_N / 32 - 1) i8_pipe_release_tmem(pp);
-                const double* cs = p.colscale + (size_t)b * p.n_pad + bn * VT_N + ch * 32;
-#pragma unroll
-                for (int j = 0; j < 32; j++) { const double x = v[j] * (os * cs[j]); ssq = fma(x, x, ssq); }
-            }
+            for (int j = 0; j < 32; j++) { const double x = v[j] * (os * cs[j]); ssq = fma(x, x, ssq); }
             if (!ok) ssq = __longlong_as_double(0x7ff8000000000000LL);
-            p.varpart[(size_t)b * p.ntiles64 * p.rows_alloc + (size_t)bn * p.rows_pad + bm * VT_M + q * 32 + lane] = ssq;
+            if (ch) s_part[row] = ssq;
+            asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 epilogue warps
+            if (!ch) p.varpart[(size_t)b * p.ntiles64 * p.rows_alloc + (size_t)bn * p.rows_pad + bm * VT_M + row] = ssq + s_part[row];
+            asm volatile("bar.sync 1, 256;" ::: "memory");     // s_part may be rewritten for the next tile
         }
     }
     i8_pipe_teardown(pp);
@@ -537,7 +540,7 @@ cudaError_t launch_var_i8(const int8_t* Aimg, int rows_pad, int rows_alloc, cons
     const int grid = live < i8_sm_count() ? (int)live : i8_sm_count();
     VarI8Params p{Aimg, Bimg, colscale, hyp, varpart, rows_pad, nt, mt, n_pad / VT_KB, nslots, (nslots + grid - 1) / grid, flag,
                   per_gp, n_pad, rows_alloc, (long long)rows_alloc * n_pad * 8};
-    k_var_i8<<<grid, 192, VT_SMEM, st>>>(p);
+    k_var_i8<<<grid, 320, VT_SMEM, st>>>(p);
     return cudaGetLastError();
 }
 
