@@ -407,3 +407,27 @@ def sobol_candidates(m, d, seed=3, skip=0):
     if skip:
         eng.fast_forward(skip)
     return eng.draw(m, dtype=torch.float64)
+
+
+# ----------------------------------------------------------------------------------------
+# SAAS NUTS potential: what Pyro's NUTS differentiates ~1e4-1e5 times per `saas_bo` fit
+# (solver selected at /root/reference/src/hdbo_benchmark/utils/experiments/load_solvers.py:183-194).
+# Model of botorch.models.fully_bayesian.SaasPyroModel [UPSTREAM]: mean ~ N(0,1); outputscale ~ Gamma(2, 0.15);
+# noise ~ Gamma(0.9, 10); tausq ~ HalfCauchy(0.1); inv_length_sq_k ~ HalfCauchy(1); lengthscale_k = (tausq inv_length_sq_k)^-1/2;
+# Matern-5/2.  Positive sites are sampled in log space (ExpTransform): potential U(z) = -[log p(y | theta(z)) +
+# sum log prior(theta(z)) + sum log |d theta / d z|].  z = [log inv_length_sq (d), log tausq, log outputscale, log noise, mean].
+# ----------------------------------------------------------------------------------------
+def saas_potential(X, y, z, min_noise=0.0):
+    """z [d + 4] (differentiable) -> scalar potential energy."""
+    d = X.shape[1]
+    n = X.shape[0]
+    z_l, z_t, z_o, z_n, mean = z[:d], z[d], z[d + 1], z[d + 2], z[d + 3]
+    ils, tausq, os_, noise = torch.exp(z_l), torch.exp(z_t), torch.exp(z_o), torch.exp(z_n)
+    ls = torch.rsqrt(tausq * ils)
+    ll = exact_mll(X, y, ls, os_, noise + min_noise, mean, MATERN52) * n
+    def half_cauchy(v, s):
+        return math.log(2.0 / math.pi) - math.log(s) - torch.log1p((v / s) ** 2)
+    lp = gamma_log_prob(os_, 2.0, 0.15) + gamma_log_prob(noise, 0.9, 10.0) + half_cauchy(tausq, 0.1) + half_cauchy(ils, 1.0).sum()
+    lp = lp - 0.5 * mean * mean - 0.5 * LOG_2PI
+    jac = z_l.sum() + z_t + z_o + z_n
+    return -(ll + lp + jac)

@@ -215,3 +215,22 @@ def test_joint_posterior_samples_match_oracle_and_thompson_picks(cuda_device):
     assert Xn.shape == (4, d)
     rows = {tuple(r.tolist()) for r in Xn}
     assert len(rows) == 4 and all(any(torch.equal(r, zc) for zc in Z) for r in Xn)
+
+
+def test_saas_nuts_potential_and_gradient_match_oracle_autograd(cuda_device):
+    """the potential energy Pyro's NUTS differentiates for `saas_bo`, batched over chain states."""
+    from hdbo_benchmark_b200.saas import SaasPotential
+
+    n, d, Cn = 70, 9, 5
+    X, y, *_ = O.synthetic_problem(n, d)
+    g = torch.Generator().manual_seed(3)
+    Z = torch.randn(Cn, d + 4, generator=g, dtype=torch.float64) * 0.7
+    Z[:, d] -= 2.0          # tausq around exp(-2)
+    Z[:, d + 2] -= 3.0      # noise around exp(-3)
+    U, dU = SaasPotential(X, y)(Z)
+    for c in range(Cn):
+        z = Z[c].clone().requires_grad_(True)
+        u = O.saas_potential(X, y, z)
+        (gz,) = torch.autograd.grad(u, z)
+        assert abs(float(U[c]) - float(u.detach())) < REL * max(1.0, abs(float(u.detach())))
+        assert float((dU[c].cpu() - gz).abs().max()) < REL * max(1.0, float(gz.abs().max()))
