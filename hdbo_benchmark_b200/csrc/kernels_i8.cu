@@ -585,4 +585,5 @@ cudaError_t launch_i8_peak(int iters, int sms, int* flag, double* ops_out, cudaS
     return cudaGetLastError();
 }
 
+
 }  // namespace hdbo
