@@ -266,3 +266,25 @@ def test_i8_largest_supported_size_and_fallback_beyond_it(cuda_device):
         assert float((res["i8"][0] - res["f64"][0]).abs().max()) < 1e-9 * float(res["f64"][0].abs().max())
         assert float(((res["i8"][1] - res["f64"][1]).abs() / res["f64"][1].abs()).max()) < REL
         torch.cuda.empty_cache()
+
+
+def test_i8_results_are_bitwise_deterministic_and_chunk_invariant(cuda_device):
+    """Integer accumulation + a fixed recombination order: the int8 path returns identical bits whatever the chunking of the pool,
+    and on repeated calls (size-independent property, also checked at the headline shape)."""
+    from hdbo_benchmark_b200 import _lib
+
+    for n, d, m, chunks in ((600, 40, 3000, (128, 512, 1024, 148 * 128)), (4096, 256, 40000, (4096, 148 * 128, 2 * 148 * 128))):
+        X, y, ls, os_, nz, mu = O.synthetic_problem(n, d)
+        gp = _gp(X, y, O.MATERN52, (ls, os_, nz, mu), cuda_device, "i8")
+        Z = torch.rand(m, d, dtype=torch.float64, generator=torch.Generator().manual_seed(n)).to(cuda_device)
+        ref = None
+        for chunk in chunks + (chunks[0],):
+            mean, var, acq = gp.posterior_acq(Z, _lib.ACQ_LOGEI, float(y.max()), chunk_rows=chunk)
+            cur = (mean.clone(), var.clone(), acq.clone())
+            if ref is None:
+                ref = cur
+            else:
+                assert all(torch.equal(a, b) for a, b in zip(cur, ref)), chunk
+        assert gp.i8_flag() == 0
+        del gp
+        torch.cuda.empty_cache()
