@@ -14,11 +14,9 @@ namespace hdbo {
 
 __device__ __forceinline__ double sqrt_pos(double x) {
     double y = (double)rsqrtf((float)x);          // MUFU.RSQ seed, relative error ~2^-22
-    double e = fma(-x * y, y, 1.0);               // Newton for 1/sqrt(x): y <- y + y e / 2
+    const double e = fma(-x * y, y, 1.0);         // one Newton step for 1/sqrt(x): y <- y + y e / 2   (error ~2^-43)
     y = fma(0.5 * y, e, y);
-    e = fma(-x * y, y, 1.0);
-    y = fma(0.5 * y, e, y);
-    double r = x * y;                             // sqrt(x) estimate, then one Heron-style correction
+    const double r = x * y;                       // sqrt(x) estimate, then one Heron-style correction: error ~2^-86 before rounding
     return fma(fma(-r, r, x), 0.5 * y, r);
 }
 
