@@ -122,23 +122,14 @@ k_leaf_blocked(double* __restrict__ Awork, double* __restrict__ L, double* __res
     __syncthreads();
     LF_STAMP(1);
 
-    for (int kb = 0; kb < 4; kb++) {
-        const int o = kb * 32;
-        // ---- diagonal block: warp 0, in registers ----
-        if (warp == 0) {
-            double a[32];
-#pragma unroll
-            for (int k = 0; k < 32; k++) a[k] = S[(o + lane) * LF_LD + o + k];
-            const int bad = lf_warp_chol32(a, invd + o);
-            if (bad && lane == 0) atomicCAS(info + b, 0, tile * 128 + o + bad);
-#pragma unroll
-            for (int k = 0; k < 32; k++)
-                if (k <= lane) S[(o + lane) * LF_LD + o + k] = a[k];
-        }
-        __syncthreads();
-        LF_STAMP(2 + kb * 3);
-        // ---- warp 7: inverse of the diagonal block (registers) | threads < 32*(3-kb): panel rows below ----
-        if (warp == 7) {
+    // Warp 7 computes the inverses of the four diagonal blocks OFF the critical path: block kb's inverse is only needed by the
+    // final assembly of the tile inverse, and it depends only on the finished diagonal factor (never touched again) and invd, so it
+    // overlaps the panel solves, the trailing updates and the next diagonal factorisations of warps 0-6.  Warps 0-6 synchronise
+    // among themselves on named barrier 1 (224 threads); warp 0 hands each finished diagonal block to warp 7 through barrier 2+kb.
+    if (warp == 7) {
+        for (int kb = 0; kb < 4; kb++) {
+            const int o = kb * 32;
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + kb) : "memory");        // diagonal block kb is in shared memory
             double a[32], x[32];
 #pragma unroll
             for (int k = 0; k < 32; k++) a[k] = S[(o + lane) * LF_LD + o + k];
@@ -146,48 +137,76 @@ k_leaf_blocked(double* __restrict__ Awork, double* __restrict__ L, double* __res
 #pragma unroll
             for (int i = 0; i < 32; i++) Dv[(kb * 32 + i) * 36 + lane] = (i >= lane) ? x[i] : 0.0;
         }
-        if (tid < 32 * (3 - kb)) {
-            const int r = o + 32 + tid;
-            double acc[32];
+    } else {
+        for (int kb = 0; kb < 4; kb++) {
+            const int o = kb * 32;
+            // ---- diagonal block: warp 0, in registers ----
+            if (warp == 0) {
+                double a[32];
 #pragma unroll
-            for (int c = 0; c < 32; c++) acc[c] = S[r * LF_LD + o + c];
+                for (int k = 0; k < 32; k++) a[k] = S[(o + lane) * LF_LD + o + k];
+                const int bad = lf_warp_chol32(a, invd + o);
+                if (bad && lane == 0) atomicCAS(info + b, 0, tile * 128 + o + bad);
 #pragma unroll
-            for (int k = 0; k < 32; k++) {
-                const double xk = acc[k] * invd[o + k];
-                acc[k] = xk;
-#pragma unroll
-                for (int c = k + 1; c < 32; c++) acc[c] = fma(-xk, S[(o + c) * LF_LD + o + k], acc[c]);
+                for (int k = 0; k < 32; k++)
+                    if (k <= lane) S[(o + lane) * LF_LD + o + k] = a[k];
+                __threadfence_block();
+                asm volatile("bar.arrive %0, 64;" ::"r"(2 + kb) : "memory");  // -> warp 7
             }
+            asm volatile("bar.sync 1, 224;" ::: "memory");
+            LF_STAMP(2 + kb * 3);
+            // ---- panel rows below the diagonal block: TWO threads per row (adjacent lanes; even / odd columns), right-looking
+            //      substitution in registers; the pivot-column value hops to the partner lane with one shuffle per step.
+            //      (One thread per row -- 528 dependent-ish FMAs + 528 shared-memory reads -- took as long as a 32x32 diagonal
+            //      factorisation, 12 k clk per step of the 4-step leaf.)
+            if (tid < 64 * (3 - kb)) {           // whole warps: 64 threads per 32 rows
+                const int r = o + 32 + (tid >> 1), h = tid & 1;
+                double acc[16];                  // columns h, h+2, ..., h+30
 #pragma unroll
-            for (int c = 0; c < 32; c++) S[r * LF_LD + o + c] = acc[c];
-        }
-        __syncthreads();
-        LF_STAMP(3 + kb * 3);
-        // ---- trailing updates C_ib,jb -= L_ib,kb L_jb,kb^T, one 16x32 half-block per warp item ----
-        {
-            int item = 0;
-            for (int ib = kb + 1; ib < 4; ib++)
-                for (int jb = kb + 1; jb <= ib; jb++)
-                    for (int h = 0; h < 2; h++, item++) {
-                        if ((item & 7) != warp) continue;
-                        const int r0 = ib * 32 + h * 16, c0 = jb * 32;
-                        double acc[2][4][2];
-                        lf_block_mma(acc, 32,
-                                     [&](int r, int k) { return S + (r0 + r) * LF_LD + o + k; },
-                                     [&](int k, int c) { return S + (c0 + c) * LF_LD + o + k; });
+                for (int c = 0; c < 16; c++) acc[c] = S[r * LF_LD + o + 2 * c + h];
 #pragma unroll
-                        for (int mt = 0; mt < 2; mt++)
+                for (int k = 0; k < 32; k++) {
+                    double xk = acc[k >> 1] * invd[o + k];                      // meaningful on the owner lane (h == k & 1)
+                    xk = __shfl_sync(LF_FULL, xk, (lane & ~1) | (k & 1));       // owner of column k -> both lanes of the pair
+                    if (h == (k & 1)) acc[k >> 1] = xk;
 #pragma unroll
-                            for (int nt = 0; nt < 4; nt++) {
-                                double* p = S + (r0 + mt * 8 + (lane >> 2)) * LF_LD + c0 + nt * 8 + (lane & 3) * 2;
-                                p[0] -= acc[mt][nt][0];
-                                p[1] -= acc[mt][nt][1];
-                            }
+                    for (int c = (k >> 1); c < 16; c++) {
+                        const int col = 2 * c + h;
+                        if (col > k) acc[c] = fma(-xk, S[(o + col) * LF_LD + o + k], acc[c]);
                     }
+                }
+#pragma unroll
+                for (int c = 0; c < 16; c++) S[r * LF_LD + o + 2 * c + h] = acc[c];
+            }
+            asm volatile("bar.sync 1, 224;" ::: "memory");
+            LF_STAMP(3 + kb * 3);
+            // ---- trailing updates C_ib,jb -= L_ib,kb L_jb,kb^T, one 16x32 half-block per warp item (warps 0-6) ----
+            {
+                int item = 0;
+                for (int ib = kb + 1; ib < 4; ib++)
+                    for (int jb = kb + 1; jb <= ib; jb++)
+                        for (int h = 0; h < 2; h++, item++) {
+                            if ((item % 7) != warp) continue;
+                            const int r0 = ib * 32 + h * 16, c0 = jb * 32;
+                            double acc[2][4][2];
+                            lf_block_mma(acc, 32,
+                                         [&](int r, int k) { return S + (r0 + r) * LF_LD + o + k; },
+                                         [&](int k, int c) { return S + (c0 + c) * LF_LD + o + k; });
+#pragma unroll
+                            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                                for (int nt = 0; nt < 4; nt++) {
+                                    double* p = S + (r0 + mt * 8 + (lane >> 2)) * LF_LD + c0 + nt * 8 + (lane & 3) * 2;
+                                    p[0] -= acc[mt][nt][0];
+                                    p[1] -= acc[mt][nt][1];
+                                }
+                        }
+            }
+            asm volatile("bar.sync 1, 224;" ::: "memory");
+            LF_STAMP(4 + kb * 3);
         }
-        __syncthreads();
-        LF_STAMP(4 + kb * 3);
     }
+    __syncthreads();
     // ---- L tile out; then the diagonal blocks of S become their inverses ----
     double* Lg = L + base;
     for (int e = tid; e < 128 * 128; e += LF_THREADS) {
