@@ -26,31 +26,46 @@ constexpr int LF_SMEM_DOUBLES = 128 * LF_LD + 4 * 32 * 36 + 128;
 constexpr int LF_SMEM_BYTES = LF_SMEM_DOUBLES * 8;
 constexpr unsigned LF_FULL = 0xffffffffu;
 
-// 1/sqrt(a) and sqrt(a) for a pivot on the 128-long critical path.  The two library sequences are independent and
-// overlap; a hand-rolled MUFU.RSQ seed + two FP64 Newton steps was measured SLOWER (23.1k vs 12.5k clk per 32x32
-// block, tools/leaf_bench.cu): a dependent FP64 op costs ~40 clk on B200, so the 12-op chain loses.
+// 1/sqrt(a) and sqrt(a) for a pivot on the 128-long critical path: MUFU.RSQ seed (2^-22) + two FP64 Newton steps (-> 2^-88
+// before rounding) + one Heron correction for the square root; straight-line, ~12 dependent FP64 ops.  (With the pivot chain
+// software-pipelined this beats the library rsqrt()/sqrt() pair; an earlier attempt inside the un-pipelined loop did not.)
 __device__ __forceinline__ void lf_rsqrt_sqrt(double a, double& inv, double& d) {
-    inv = rsqrt(a);
-    d = sqrt(a);
+    double y = (double)rsqrtf((float)a);
+    double e = fma(-a * y, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    e = fma(-a * y, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    const double r = a * y;
+    inv = y;
+    d = fma(fma(-r, r, a), 0.5 * y, r);
 }
 
 // lane i holds row i (lower part) of a 32x32 SPD block; on exit row i of its Cholesky factor.  invd[j] = 1/L_jj.
+// Software-pipelined: the dependent chain of a pivot is  shuffle(pivot) -> rsqrt/sqrt -> mul -> shuffle(L_{j+1,j}) -> fma, and the
+// NEXT pivot only needs column j+1 of the update.  So column j+1 is updated first, the next pivot is broadcast and its rsqrt/sqrt
+// are issued immediately, and the remaining 30-j shuffle+fma pairs of the rank-1 update fill that latency (in program order the
+// whole update loop sat in front of the next pivot's chain: 440 clk per pivot instead of ~250).
 __device__ __forceinline__ int lf_warp_chol32(double (&a)[32], double* invd) {
     const int lane = threadIdx.x & 31;
     int bad = 0;
-    // Per-pivot dependency chain: shuffle(pivot) -> rsqrt/sqrt -> mul -> shuffle(column) -> fma, ~390 clk measured.
-    // An LDL^T variant (reciprocal in the loop, sqrt/rsqrt at the end) was measured slower (15.0k vs 12.5k clk / block).
+    double ajj = __shfl_sync(LF_FULL, a[0], 0);
+    if (!(ajj > 0.0)) { bad = 1; ajj = 1.0; }
+    double inv, d;
+    lf_rsqrt_sqrt(ajj, inv, d);
 #pragma unroll
     for (int j = 0; j < 32; j++) {
-        double ajj = __shfl_sync(LF_FULL, a[j], j);
-        if (!(ajj > 0.0)) { if (!bad) bad = j + 1; ajj = 1.0; }
-        double inv, d;
-        lf_rsqrt_sqrt(ajj, inv, d);
         const double l = (lane == j) ? d : a[j] * inv;
         a[j] = l;
         if (lane == 0) invd[j] = inv;
+        if (j + 1 < 32) {
+            const double l1 = __shfl_sync(LF_FULL, l, j + 1);
+            a[j + 1] = fma(-l, l1, a[j + 1]);
+            double nxt = __shfl_sync(LF_FULL, a[j + 1], j + 1);         // next pivot (final on lane j+1)
+            if (!(nxt > 0.0)) { if (!bad) bad = j + 2; nxt = 1.0; }
+            lf_rsqrt_sqrt(nxt, inv, d);
+        }
 #pragma unroll
-        for (int k = j + 1; k < 32; k++) {
+        for (int k = j + 2; k < 32; k++) {
             const double lk = __shfl_sync(LF_FULL, l, k);
             a[k] = fma(-l, lk, a[k]);
         }
