@@ -30,7 +30,8 @@ constexpr unsigned LF_FULL = 0xffffffffu;
 // before rounding) + one Heron correction for the square root; straight-line, ~12 dependent FP64 ops.  (With the pivot chain
 // software-pipelined this beats the library rsqrt()/sqrt() pair; an earlier attempt inside the un-pipelined loop did not.)
 __device__ __forceinline__ void lf_rsqrt_sqrt(double a, double& inv, double& d) {
-    double y = (double)rsqrtf((float)a);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));   // MUFU.RSQ64H on the high word: relative error ~2^-22, no F2F round trip
     double e = fma(-a * y, y, 1.0);
     y = fma(0.5 * y, e, y);
     e = fma(-a * y, y, 1.0);
@@ -58,11 +59,12 @@ __device__ __forceinline__ int lf_warp_chol32(double (&a)[32], double* invd) {
         a[j] = l;
         if (lane == 0) invd[j] = inv;
         if (j + 1 < 32) {
-            const double l1 = __shfl_sync(LF_FULL, l, j + 1);
-            a[j + 1] = fma(-l, l1, a[j + 1]);
-            double nxt = __shfl_sync(LF_FULL, a[j + 1], j + 1);         // next pivot (final on lane j+1)
+            // lane j+1 already owns L_{j+1,j} (its own l): the next pivot a_{j+1,j+1} - l^2 needs ONE shuffle, not two
+            double nxt = __shfl_sync(LF_FULL, fma(-l, l, a[j + 1]), j + 1);
             if (!(nxt > 0.0)) { if (!bad) bad = j + 2; nxt = 1.0; }
             lf_rsqrt_sqrt(nxt, inv, d);
+            const double l1 = __shfl_sync(LF_FULL, l, j + 1);
+            a[j + 1] = fma(-l, l1, a[j + 1]);
         }
 #pragma unroll
         for (int k = j + 2; k < 32; k++) {
