@@ -139,6 +139,9 @@ k_leaf_blocked(double* __restrict__ Awork, double* __restrict__ L, double* __res
     __syncthreads();
     LF_STAMP(1);
 
+    // (Measured and rejected again with this structure: look-ahead -- warp 0 updating and factorising the next diagonal block while
+    //  warps 1-6 finish the trailing update -- and a progressive write-out of L by warp 7: 55.6 us vs 51.2 us; the diagonal warp's
+    //  dependent chain slows down when the other warps issue DMMA/LDS next to it.)
     // Warp 7 computes the inverses of the four diagonal blocks OFF the critical path: block kb's inverse is only needed by the
     // final assembly of the tile inverse, and it depends only on the finished diagonal factor (never touched again) and invd, so it
     // overlaps the panel solves, the trailing updates and the next diagonal factorisations of warps 0-6.  Warps 0-6 synchronise
