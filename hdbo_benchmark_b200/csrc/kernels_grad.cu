@@ -167,9 +167,18 @@ __global__ void k_mll_grad_final(const double* __restrict__ colpart, long long b
         for (int t = 0; t < mtiles; t++) s += colpart[b * bscol + (size_t)t * dpt + k];
         grad[(size_t)b * (d + 3) + k] = s * inv_ls[(size_t)b * d + k];
     }
+    // the two trace-like scalars: block reduction over the nscal partial pairs (one thread summing them serially cost 80 us at
+    // n = 4096: 512 dependent global loads)
+    __shared__ double red[2][8];
+    double a = 0.0, c = 0.0;
+    for (int t = threadIdx.x; t < nscal; t += blockDim.x) { a += scalpart[((size_t)b * nscal + t) * 2]; c += scalpart[((size_t)b * nscal + t) * 2 + 1]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = c; }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        double a = 0.0, c = 0.0;
-        for (int t = 0; t < nscal; t++) { a += scalpart[((size_t)b * nscal + t) * 2]; c += scalpart[((size_t)b * nscal + t) * 2 + 1]; }
+        a = 0.0; c = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { a += red[0][w]; c += red[1][w]; }
         grad[(size_t)b * (d + 3) + d] = 0.5 * a / hyp[b * 4 + 0];
         grad[(size_t)b * (d + 3) + d + 1] = 0.5 * c;
         grad[(size_t)b * (d + 3) + d + 2] = scal[b * 8 + 3];
