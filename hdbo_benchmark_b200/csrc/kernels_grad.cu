@@ -215,9 +215,15 @@ cudaError_t mll_grad(const hdbo_gp* gp, double* Kinv, double* G, double* XsT, do
     GxaParams x{};
     x.G = G; x.XsT = XsT; x.Xs = gp->Xs; x.rowpart = rowpart; x.colpart = colpart;
     x.ldg = np; x.ldt = np; x.ldx = dp; x.n_pad = np; x.mtiles = T; x.ntiles = dpt / 128;
-    int splits = (148 + T * (dpt / 128) * B - 1) / (T * (dpt / 128) * B);
-    splits = splits < 1 ? 1 : (splits > GXA_MAX_SPLITS ? GXA_MAX_SPLITS : splits);
-    if (splits > np / BK) splits = np / BK;
+    // split-K factor: minimise (waves of 148 CTAs) x (k-blocks per CTA); e.g. 64 tiles: 2 splits = one 128-CTA wave of half the
+    // k-range, whereas ceil(148 / 64) = 3 splits would run a second, 30 %-full wave
+    const int tiles = T * (dpt / 128) * B, kblocks = np / BK;
+    int splits = 1;
+    long long best = -1;
+    for (int sp = 1; sp <= GXA_MAX_SPLITS && sp <= kblocks; sp++) {
+        const long long cost = (long long)((tiles * sp + 147) / 148) * ((kblocks + sp - 1) / sp);
+        if (best < 0 || cost < best) { best = cost; splits = sp; }
+    }
     x.splits = splits;
     x.bsG = nn; x.bsT = (long long)dpt * np; x.bsX = (long long)np * dp; x.bsrow = (long long)G_NSEG * np;
     x.bscol = (long long)T * GXA_MAX_SPLITS * dpt;
