@@ -24,6 +24,10 @@ from ._lib import HdboGp, check, ptr
 DEFAULT_CHUNK_ROWS = 148 * 128  # one 128-row tile per SM per column tile
 WORKSPACE_CAP_BYTES = 8 << 30
 I8_MAX_N_PAD = 8192   # int8 mode: int32 group sums stay exact up to this size (csrc/i8.cuh); larger GPs use the FP64 path
+# int8 mode: the variance error is ~2^-48 ||L^-1 row|| in units of the prior, i.e. it grows like (outputscale / noise)^1/2, and on a
+# training point the variance itself is ~noise: relative error ~ c (outputscale / noise)^3/2 2^-48 -- measured 2.3e-6 at a ratio of
+# 1.6e-5, 1.5e-7 at 1e-4.  Below this noise / outputscale ratio the engine keeps the FP64 path (BoTorch's own floor is 1e-4).
+I8_MIN_NOISE_RATIO = 1e-4
 
 
 def _rup(x: int, m: int) -> int:
@@ -83,6 +87,8 @@ class DeviceGP:
             raise ValueError(f"var_mode must be 'f64' or 'i8', got {self.var_mode!r}")
         self._i8_state: Optional[torch.Tensor] = None
         self._i8_dirty = True
+        self._i8_ok = True
+        self.i8_min_noise_ratio = I8_MIN_NOISE_RATIO
         self.desc = HdboGp(
             n=self.n, d=self.d, n_pad=npad, d_pad=dpad, kind=self.kind, batch=B,
             X=ptr(self.X), ldx=self.X.stride(0), y=ptr(self.y), center=ptr(self.center), inv_ls=ptr(self.inv_ls),
@@ -131,6 +137,9 @@ class DeviceGP:
         self.fitted = True
         self.jitter_used = jitter
         self._i8_dirty = True      # int8 mode: the digit images are re-sliced lazily by the next pool evaluation
+        if self.var_mode == "i8":  # (fit() has just synchronised on `info`: one more tiny read)
+            hy = self.hyp[:, :2].cpu()
+            self._i8_ok = bool(((hy[:, 1] + jitter) >= self.i8_min_noise_ratio * hy[:, 0]).all())
         return jitter
 
     # ---- exact int8 variance mode: digit planes of L^-1, once per fit ----
@@ -150,7 +159,7 @@ class DeviceGP:
         return int(self._i8_state[-16:-12].view(torch.int32).item())
 
     def _pool_call(self, Zptr, ldz, m, observation_noise, acq_kind, acq_param, mean, var, acq, bso, ws, stream) -> None:
-        if self.var_mode == "i8" and self.n_pad <= I8_MAX_N_PAD:
+        if self.var_mode == "i8" and self.n_pad <= I8_MAX_N_PAD and self._i8_ok:
             if self._i8_dirty or self._i8_state is None:
                 self.slice_linv()
             check(self.lib.hdbo_posterior_acq_i8(C.byref(self.desc), ptr(self._i8_state), Zptr, ldz, m, int(observation_noise),

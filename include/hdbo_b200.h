@@ -103,7 +103,8 @@ int hdbo_posterior_acq(const hdbo_gp* gp, const double* Z, int64_t ldz, int64_t 
 /* Exact int8 mode (n_pad <= 8192, any batch): the same call as hdbo_posterior_acq, with both GEMMs (Zs Xs^T and V = K* L^-T) computed
  * on the tcgen05 tensor cores from base-256 digit planes (6 x 6 digits, 21 exact int8 GEMMs accumulated in TMEM, FP64
  * recombination; csrc/kernels_i8.cu) instead of FP64 DMMA.  Results agree with hdbo_posterior_acq to ~1e-12 of the prior
- * variance (tests/test_gpu_i8.py).
+ * variance (tests/test_gpu_i8.py); the absolute error grows like (outputscale / noise)^1/2, so for the 1e-6 RELATIVE bar on
+ * candidates that coincide with training points use it when noise >= 1e-4 outputscale (the Python engine enforces this).
  *   hdbo_i8_state_bytes     size of the caller-owned state buffer (128-byte aligned): digit planes of L^-1 + row scales + flag
  *   hdbo_gp_slice_linv      after every hdbo_gp_fit: slices gp->Linv into the state
  *   hdbo_posterior_acq_i8   pool evaluation; `workspace` as for hdbo_posterior_acq (keep_grad_state = 0), 128-byte aligned

@@ -16,11 +16,13 @@ REL = 1e-6           # parity bar of the path (BASELINE.json north_star)
 ABS_VS_F64 = 5e-12   # |var_i8 - var_f64| / outputscale: digit quantisation 2^-49 x conditioning, measured <= 5e-13
 
 
-def _gp(X, y, kind, hyper, dev, mode):
+def _gp(X, y, kind, hyper, dev, mode, force_i8=True):
     from hdbo_benchmark_b200.engine import DeviceGP
 
     ls, os_, nz, mu = hyper
     gp = DeviceGP(X.to(dev), y.to(dev), kind, var_mode=mode)
+    if force_i8:
+        gp.i8_min_noise_ratio = 0.0      # these tests exercise the int8 kernels themselves, also below the engine's noise-ratio guard
     gp.set_hyper(ls.to(dev), os_, nz, mu)
     gp.fit()
     return gp
@@ -288,3 +290,46 @@ def test_i8_results_are_bitwise_deterministic_and_chunk_invariant(cuda_device):
         assert gp.i8_flag() == 0
         del gp
         torch.cuda.empty_cache()
+
+
+def test_i8_random_hyperparameter_sweep_against_f64_mode(cuda_device):
+    """24 random (n, d, lengthscale scale, outputscale, noise, kernel) draws, including very short / very long lengthscales and
+    large outputscales, noise down to 1e-5 of the prior variance.  At noise / outputscale >= 1e-4 (the engine's guard; BoTorch's own
+    noise floor) the int8 path tracks the FP64 path to 1e-9 of the mean scale and, in the variance, to the relative parity bar (1e-6,
+    also where the variance collapses to the noise level on training points) and 5e-11 of the prior variance; below the guard the
+    engine silently keeps the FP64 path (the error grows like 2^-48 ||L^-1 row|| ~ (outputscale / noise)^1/2)."""
+    from hdbo_benchmark_b200 import _lib
+    from hdbo_benchmark_b200.engine import DeviceGP
+
+    g = torch.Generator().manual_seed(123)
+    for trial in range(24):
+        n = int(torch.randint(3, 700, (1,), generator=g))
+        d = int(torch.randint(1, 90, (1,), generator=g))
+        m = int(torch.randint(1, 600, (1,), generator=g))
+        kind = O.MATERN52 if trial % 2 == 0 else O.RBF
+        ls = (10.0 ** (torch.rand(d, generator=g, dtype=torch.float64) * 3.0 - 1.5)) * max(1.0, d ** 0.5 / 3)   # 0.03 .. 30 x sqrt(d)/3
+        os_ = float(10.0 ** (torch.rand(1, generator=g, dtype=torch.float64) * 4.0 - 2.0))                    # 0.01 .. 100
+        nz = float(10.0 ** (torch.rand(1, generator=g, dtype=torch.float64) * 4.0 - 5.0)) * os_               # 1e-5 .. 1e-1 of the prior
+        guarded = nz < 1e-4 * os_                     # below the engine's noise-ratio guard the int8 request falls back to FP64
+        X = torch.rand(n, d, generator=g, dtype=torch.float64)
+        y = torch.randn(n, generator=g, dtype=torch.float64) * os_ ** 0.5
+        Z = torch.rand(m, d, generator=g, dtype=torch.float64)
+        Z[: min(m, n) // 3] = X[: min(m, n) // 3]
+        res = {}
+        for mode in ("f64", "i8"):
+            gp = DeviceGP(X.to(cuda_device), y.to(cuda_device), kind, var_mode=mode)
+            gp.set_hyper(ls.to(cuda_device), os_, nz, 0.1)
+            gp.fit()
+            mean, var, _ = gp.posterior_acq(Z.to(cuda_device), _lib.ACQ_NONE)
+            res[mode] = (mean[0].clone(), var[0].clone())
+            assert gp.i8_flag() == 0
+            if mode == "i8":
+                assert (gp._i8_state is None) == guarded, (trial, nz / os_)
+        if guarded:
+            assert torch.equal(res["i8"][1], res["f64"][1]) and torch.equal(res["i8"][0], res["f64"][0])
+            continue
+        scale_m = float(res["f64"][0].abs().max().clamp_min(os_ ** 0.5))
+        assert float((res["i8"][0] - res["f64"][0]).abs().max()) < 1e-9 * scale_m, (trial, n, d)
+        dv = (res["i8"][1] - res["f64"][1]).abs()
+        assert float(dv.max()) < 5e-11 * os_, (trial, n, d, float(dv.max()) / os_, nz / os_)
+        assert float((dv / res["f64"][1].abs()).max()) < REL, (trial, n, d, nz / os_)
