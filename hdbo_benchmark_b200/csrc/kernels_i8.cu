@@ -198,21 +198,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 // MMA issuer starts the next tile as soon as the epilogue warps have drained TMEM (`tmem_empty`), so TMEM allocation, barrier
 // set-up, pipeline fill and most of the epilogue are off the critical path.
 struct I8Pipe {
-    uint8_t *As, *Bs;
+    uint8_t *As, *Bs, *extra;     // extra: the bytes after the barriers (kernel-specific staging)
     uint32_t full0, empty0, accum, tmem_empty, tmem_base;
 };
 
+template <int STAGES>
 __device__ __forceinline__ I8Pipe i8_pipe_setup(uint8_t* smem_raw, int epilogue_warps) {
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     I8Pipe pp;
     pp.As = base;
-    pp.Bs = base + VT_STAGES * VT_A_STAGE;
-    uint64_t* bars = (uint64_t*)(base + VT_STAGES * (VT_A_STAGE + VT_B_STAGE));
-    pp.full0 = smem_u32(bars); pp.empty0 = smem_u32(bars + VT_STAGES); pp.accum = smem_u32(bars + 2 * VT_STAGES);
-    pp.tmem_empty = smem_u32(bars + 2 * VT_STAGES + 1);
-    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * VT_STAGES + 2);
+    pp.Bs = base + STAGES * VT_A_STAGE;
+    uint64_t* bars = (uint64_t*)(base + STAGES * (VT_A_STAGE + VT_B_STAGE));
+    pp.extra = base + STAGES * (VT_A_STAGE + VT_B_STAGE) + 256;
+    pp.full0 = smem_u32(bars); pp.empty0 = smem_u32(bars + STAGES); pp.accum = smem_u32(bars + 2 * STAGES);
+    pp.tmem_empty = smem_u32(bars + 2 * STAGES + 1);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 2);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < VT_STAGES; s++) { mbar_init(pp.full0 + 8 * s, 1); mbar_init(pp.empty0 + 8 * s, 1); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(pp.full0 + 8 * s, 1); mbar_init(pp.empty0 + 8 * s, 1); }
         mbar_init(pp.accum, 1);
         mbar_init(pp.tmem_empty, epilogue_warps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -235,9 +237,10 @@ __device__ __forceinline__ void i8_pipe_teardown(const I8Pipe& pp) {
 }
 
 // producer (one thread): two bulk copies per k-block, images asrc[kb], bsrc[kb]; kbg = running k-block count of this CTA
+template <int STAGES>
 __device__ __forceinline__ bool i8_pipe_produce(const I8Pipe& pp, const int8_t* asrc, const int8_t* bsrc, int kblocks, uint32_t& kbg, int* flag) {
     for (int kb = 0; kb < kblocks; kb++, kbg++) {
-        const uint32_t s = kbg % VT_STAGES, ph = (kbg / VT_STAGES) & 1;
+        const uint32_t s = kbg % STAGES, ph = (kbg / STAGES) & 1;
         if (!mbar_wait(pp.empty0 + 8 * s, ph ^ 1, flag)) return false;
         mbar_expect_tx(pp.full0 + 8 * s, VT_A_STAGE + VT_B_STAGE);
         bulk_load(smem_u32(pp.As + s * VT_A_STAGE), asrc + (size_t)kb * VT_A_STAGE, VT_A_STAGE, pp.full0 + 8 * s);
@@ -252,12 +255,12 @@ __device__ __forceinline__ bool i8_pipe_produce(const I8Pipe& pp, const int8_t* 
 // k-block: the 4 KB A plane is read from shared memory 8 instead of 21 times (SS-mode operand reads were the limiter of the
 // unmerged version: 192 B/clk needed for N = 64 against 128 B/clk of shared-memory bandwidth).
 // `tile_it` = how many tiles this CTA has finished: the accumulators may be overwritten once the epilogue has drained them.
-template <bool A_SIGNED, bool A_TMEM = false>
+template <int STAGES, bool A_SIGNED, bool A_TMEM = false>
 __device__ __forceinline__ bool i8_pipe_mma(const I8Pipe& pp, int kblocks, uint32_t& kbg, uint32_t tile_it, int* flag) {
     if (tile_it > 0 && !mbar_wait(pp.tmem_empty, (tile_it - 1) & 1, flag)) return false;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     for (int kb = 0; kb < kblocks; kb++, kbg++) {
-        const uint32_t s = kbg % VT_STAGES, ph = (kbg / VT_STAGES) & 1;
+        const uint32_t s = kbg % STAGES, ph = (kbg / STAGES) & 1;
         if (!mbar_wait(pp.full0 + 8 * s, ph, flag)) return false;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a0 = smem_u32(pp.As + s * VT_A_STAGE), b0 = smem_u32(pp.Bs + s * VT_B_STAGE);
@@ -333,24 +336,27 @@ struct CrossI8Params {
 // The epilogue first turns its 16 columns of the 6 accumulator groups into 16 FP64 inner products (registers) and releases
 // TMEM; the FP64-heavy part (distance -> kernel -> digits) then overlaps the MMAs of the CTA's next tile.
 constexpr int CE_WARPS = 16, CE_THREADS = 64 + CE_WARPS * 32;
+constexpr int CE_STAGES = 4;                       // 4-stage operand ring + 48 KB staging of the two output images of a tile
+constexpr int CE_SMEM = CE_STAGES * (VT_A_STAGE + VT_B_STAGE) + 256 + 2 * VT_A_STAGE + 1024;
 template <int KIND>
 __global__ void __launch_bounds__(CE_THREADS, 1) k_cross_i8(CrossI8Params p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ double s_xn[VT_N], s_xs[VT_N], s_al[VT_N], s_ms[3][VT_M];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const I8Pipe pp = i8_pipe_setup(smem_raw, CE_WARPS);
+    const I8Pipe pp = i8_pipe_setup<CE_STAGES>(smem_raw, CE_WARPS);
+    uint8_t* stage_out = pp.extra;                 // [2 k-blocks][6 planes][128 rows][32 B]: the tile's K* digit images, as in global memory
     if (warp == 0 && lane == 0) {
         uint32_t kbg = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
             const int b = t / p.tiles_per_gp, tt = t - b * p.tiles_per_gp, bn = tt % p.ntiles64, bm = tt / p.ntiles64;
             const int8_t* zi = p.Zimg + (size_t)b * p.rows_alloc * p.nkb_d * 32 * I8_S;
             const int8_t* xi = p.Ximg + (size_t)b * p.n_pad * p.nkb_d * 32 * I8_S;
-            if (!i8_pipe_produce(pp, zi + (size_t)bm * p.nkb_d * VT_A_STAGE, xi + (size_t)bn * p.nkb_d * VT_B_STAGE, p.nkb_d, kbg, p.flag)) break;
+            if (!i8_pipe_produce<CE_STAGES>(pp, zi + (size_t)bm * p.nkb_d * VT_A_STAGE, xi + (size_t)bn * p.nkb_d * VT_B_STAGE, p.nkb_d, kbg, p.flag)) break;
         }
     } else if (warp == 1 && lane == 0) {
         uint32_t kbg = 0, it = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, it++)
-            if (!i8_pipe_mma<true>(pp, p.nkb_d, kbg, it, p.flag)) break;
+            if (!i8_pipe_mma<CE_STAGES, true>(pp, p.nkb_d, kbg, it, p.flag)) break;
     }
     __syncwarp();
     if (warp >= 2) {
@@ -380,6 +386,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1) k_cross_i8(CrossI8Params p) {
                 for (int j = 0; j < 16; j++) v[j] = fma(w, (double)(int32_t)rr[j], v[j]);
             }
             i8_pipe_release_tmem(pp);                      // the MMA issuer may start this CTA's next tile
+            if (tid == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous tile's images have left the staging buffer
             asm volatile("bar.sync 1, %0;" ::"n"(CE_WARPS * 32) : "memory");   // s_xn / s_xs / s_al of this tile are in place
             double msum = 0.0;
             uint32_t dg[I8_S][4];                          // 16 columns = one 16-byte half of an image row per digit plane
@@ -405,15 +412,22 @@ __global__ void __launch_bounds__(CE_THREADS, 1) k_cross_i8(CrossI8Params p) {
                 dg[1][jq] = HDBO_GATHER(hi, 0x0040); dg[0][jq] = HDBO_GATHER(hi, 0x0051);
 #undef HDBO_GATHER
             }
-            int8_t* dst = p.Kimg + (size_t)b * p.bsK + ((size_t)bm * p.nkb_n + bn * 2 + (sl >> 1)) * VT_A_STAGE + row * 32 + (((sl & 1) ^ swz) << 4);
+            uint8_t* dst = stage_out + (sl >> 1) * VT_A_STAGE + row * 32 + (((sl & 1) ^ swz) << 4);
 #pragma unroll
             for (int tt = 0; tt < I8_S; tt++)
                 *reinterpret_cast<uint4*>(dst + tt * VT_M * 32) = make_uint4(dg[tt][0], dg[tt][1], dg[tt][2], dg[tt][3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the bulk-copy engine
             if (!ok) msum = __longlong_as_double(0x7ff8000000000000LL);
             if (sl) s_ms[sl - 1][row] = msum;
             asm volatile("bar.sync 1, %0;" ::"n"(CE_WARPS * 32) : "memory");
             if (!sl) p.meanpart[(size_t)b * p.ntiles64 * p.rows_alloc + (size_t)bn * p.rows_pad + grow] = ((msum + s_ms[0][row]) + s_ms[1][row]) + s_ms[2][row];
+            if (tid == 64) {                               // (after the barrier above: every warp's staging writes are done)
+                int8_t* gdst = p.Kimg + (size_t)b * p.bsK + ((size_t)bm * p.nkb_n + bn * 2) * VT_A_STAGE;   // k-blocks 2 bn, 2 bn + 1: contiguous
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(stage_out)), "r"(2 * VT_A_STAGE) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
         }
+        if (tid == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all images written before the CTA exits
     }
     i8_pipe_teardown(pp);
 }
@@ -423,8 +437,8 @@ cudaError_t launch_cross_i8(int kind, const int8_t* Zimg, const int8_t* Ximg, co
                             int rows_pad, int rows_alloc, int n_pad, int d, int batch, int* flag, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_cross_i8<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cross_i8<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(k_cross_i8<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CE_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cross_i8<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CE_SMEM);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
@@ -432,8 +446,8 @@ cudaError_t launch_cross_i8(int kind, const int8_t* Zimg, const int8_t* Ximg, co
     CrossI8Params p{Zimg, Ximg, zscale, xscale, zn, xn, alpha, hyp, Kimg, meanpart, m, n, rows_pad, n_pad / VT_N, ntiles, (d + 31) / 32,
                     n_pad / VT_KB, flag, per_gp, n_pad, rows_alloc, (long long)rows_alloc * n_pad * 8};
     const int grid = ntiles < i8_sm_count() ? ntiles : i8_sm_count();
-    if (kind == 0) k_cross_i8<0><<<grid, CE_THREADS, VT_SMEM, st>>>(p);
-    else k_cross_i8<1><<<grid, CE_THREADS, VT_SMEM, st>>>(p);
+    if (kind == 0) k_cross_i8<0><<<grid, CE_THREADS, CE_SMEM, st>>>(p);
+    else k_cross_i8<1><<<grid, CE_THREADS, CE_SMEM, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -474,13 +488,13 @@ __global__ void __launch_bounds__(320, 1) k_var_i8(VarI8Params p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ double s_part[VT_M];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const I8Pipe pp = i8_pipe_setup(smem_raw, 8);
+    const I8Pipe pp = i8_pipe_setup<VT_STAGES>(smem_raw, 8);
     int b, bm, bn;
     if (warp == 0 && lane == 0) {
         uint32_t kbg = 0;
         for (int wv = 0; wv < p.nwaves; wv++) {
             if (!var_tile(p, wv, b, bm, bn)) continue;
-            if (!i8_pipe_produce(pp, p.Aimg + (size_t)b * p.bsK + (size_t)bm * p.nkb * VT_A_STAGE,
+            if (!i8_pipe_produce<VT_STAGES>(pp, p.Aimg + (size_t)b * p.bsK + (size_t)bm * p.nkb * VT_A_STAGE,
                                  p.Bimg + (size_t)b * I8_S * p.n_pad * p.n_pad + (size_t)bn * p.nkb * VT_B_STAGE,
                                  (bn + 1) * (VT_N / VT_KB), kbg, p.flag)) break;
         }
@@ -488,7 +502,7 @@ __global__ void __launch_bounds__(320, 1) k_var_i8(VarI8Params p) {
         uint32_t kbg = 0, it = 0;
         for (int wv = 0; wv < p.nwaves; wv++) {
             if (!var_tile(p, wv, b, bm, bn)) continue;
-            if (!i8_pipe_mma<false, HDBO_VAR_A_TMEM>(pp, (bn + 1) * (VT_N / VT_KB), kbg, it++, p.flag)) break;
+            if (!i8_pipe_mma<VT_STAGES, false, HDBO_VAR_A_TMEM>(pp, (bn + 1) * (VT_N / VT_KB), kbg, it++, p.flag)) break;
         }
     }
     __syncwarp();
