@@ -9,9 +9,10 @@
 // sum_g 2^-(8g+c) acc_g is rounded (FP64).  Measured against the FP64 path: variance within 1e-12 of the prior variance, mean
 // within 1e-11 relative (tests/test_gpu_i8.py).
 //
-// Kernel shape (both): one CTA per (128 candidates x 64 columns) tile; warp 0 = producer (two 1-D bulk copies per 32-byte k-block
-// bring all 6+6 digit planes), warp 1 = MMA issuer (8 merged MMAs per k-block), remaining warps = epilogue from TMEM.
-// SASS: UTCIMMA / UBLKCP / LDTM / UTCBAR.
+// Kernel shape (both): persistent, one CTA per SM walking a static list of (128 candidates x 64 columns) tiles; warp 0 = producer
+// (two 1-D bulk copies per 32-byte k-block bring all 6+6 digit planes into a ring that keeps running across tiles), warp 1 = MMA
+// issuer (8 merged MMAs per k-block), remaining warps = epilogue from TMEM, which hand TMEM back to the issuer as soon as they have
+// drained it.  SASS: UTCIMMA / UBLKCP / LDTM / UTCBAR.
 #include "kernels.cuh"
 #include "i8.cuh"
 
@@ -22,7 +23,7 @@ namespace hdbo {
 //   image(tile, kb) = [S planes][ROWS rows][32 bytes of k], SWIZZLE_32B applied (16-byte halves of rows 4..7 of every 8 swapped),
 //   stored at ((tile * nkb + kb) * S * ROWS * 32);  ROWS = 128 for the A side (candidates), 64 for the B side.
 // (A 3-D tensor map over plain [S][rows][K] planes works too -- first version -- but its 32-byte box rows are one L2 request each
-// and the L1->XBAR request path saturated at 75 %: profiles/r01_ncu_i8_v1.txt.)
+// and the L1->XBAR request path saturated at 75 %: profiles/r01_ncu_full_i8_v1.raw.csv.)
 
 // position of k-byte `lane` (0..31) of row r inside its 32-byte image row
 __device__ __forceinline__ int img_inrow(int r, int lane) { return (((lane >> 4) ^ ((r >> 2) & 1)) << 4) | (lane & 15); }
