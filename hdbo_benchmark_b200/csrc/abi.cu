@@ -266,7 +266,7 @@ extern "C" int hdbo_posterior_acq(const hdbo_gp* gp, const double* Z, int64_t ld
 
 // ---- exact int8 (tcgen05) variance path: digit planes of L^-1 once per fit, then the pool evaluation ----
 extern "C" size_t hdbo_i8_state_bytes(const hdbo_gp* gp) {
-    if (check_gp(gp) || gp->n_pad > I8_MAX_N_PAD) return 0;   // int32 group sums: see i8.cuh
+    if (check_gp(gp) || gp->n_pad > I8_MAX_N_PAD || gp->d > I8_MAX_D) return 0;   // int32 group sums: see i8.cuh
     return carve_i8(gp, nullptr).bytes;
 }
 
@@ -277,7 +277,7 @@ extern "C" int32_t* hdbo_i8_state_flag(const hdbo_gp* gp, void* i8_state) {
 
 extern "C" int hdbo_gp_slice_linv(const hdbo_gp* gp, void* i8_state, void* stream_) {
     if (int e = check_gp(gp)) return e;
-    if (gp->n_pad > I8_MAX_N_PAD) return -1;
+    if (gp->n_pad > I8_MAX_N_PAD || gp->d > I8_MAX_D) return -1;
     if (!i8_state || ((uintptr_t)i8_state & 127)) return -2;
     cudaStream_t st = (cudaStream_t)stream_;
     I8State s = carve_i8(gp, i8_state);
@@ -292,7 +292,7 @@ extern "C" int hdbo_posterior_acq_i8(const hdbo_gp* gp, void* i8_state, const do
                                      int observation_noise, int acq_kind, double acq_param, double* mean, double* var, double* acq,
                                      int64_t bso, void* workspace, size_t workspace_bytes, void* stream_) {
     if (int e = check_gp(gp)) return e;
-    if (gp->n_pad > I8_MAX_N_PAD) return -1;
+    if (gp->n_pad > I8_MAX_N_PAD || gp->d > I8_MAX_D) return -1;
     if (!i8_state || ((uintptr_t)i8_state & 127)) return -2;
     if (workspace && ((uintptr_t)workspace & 127)) return -13;
     I8State s = carve_i8(gp, i8_state);

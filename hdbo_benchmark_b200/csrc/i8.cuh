@@ -18,6 +18,7 @@ constexpr int I8_SIGNED_FRAC_BITS = 47;
 constexpr int I8_A_IMAGE = I8_S * 128 * 32;   // bytes of one 128-row tile image (128 rows x 32 k) -- layout in kernels_i8.cu
 constexpr int I8_B_IMAGE = I8_S * 64 * 32;    // bytes of one 64-row tile image
 constexpr int I8_MAX_N_PAD = 8192;            // unsigned x signed group sums stay below 2^31: 6 pairs x n x 255 x 128
+constexpr int I8_MAX_D = 16384;               // signed x signed (cross GEMM): 6 pairs x d x 128 x 128 < 2^31
 
 // Balanced base-256 digits without a carry chain: adding 128 to every digit turns them into the plain bytes of X + bias, and
 // b_t = byte_t - 128 = byte_t ^ 0x80 as int8.  Representable range: |X| <= 0x7F7F7F7F7F7F (0.996 2^47) -- see i8_row_exponent.

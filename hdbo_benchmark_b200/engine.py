@@ -28,6 +28,7 @@ I8_MAX_N_PAD = 8192   # int8 mode: int32 group sums stay exact up to this size (
 # training point the variance itself is ~noise: relative error ~ c (outputscale / noise)^3/2 2^-48 -- measured 2.3e-6 at a ratio of
 # 1.6e-5, 1.5e-7 at 1e-4.  Below this noise / outputscale ratio the engine keeps the FP64 path (BoTorch's own floor is 1e-4).
 I8_MIN_NOISE_RATIO = 1e-4
+I8_MAX_D = 16384      # int8 mode: the same bound for the cross GEMM (K = d)
 
 
 def _rup(x: int, m: int) -> int:
@@ -159,7 +160,7 @@ class DeviceGP:
         return int(self._i8_state[-16:-12].view(torch.int32).item())
 
     def _pool_call(self, Zptr, ldz, m, observation_noise, acq_kind, acq_param, mean, var, acq, bso, ws, stream) -> None:
-        if self.var_mode == "i8" and self.n_pad <= I8_MAX_N_PAD and self._i8_ok:
+        if self.var_mode == "i8" and self.n_pad <= I8_MAX_N_PAD and self.d <= I8_MAX_D and self._i8_ok:
             if self._i8_dirty or self._i8_state is None:
                 self.slice_linv()
             check(self.lib.hdbo_posterior_acq_i8(C.byref(self.desc), ptr(self._i8_state), Zptr, ldz, m, int(observation_noise),
