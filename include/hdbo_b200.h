@@ -100,7 +100,7 @@ int hdbo_posterior_acq(const hdbo_gp* gp, const double* Z, int64_t ldz, int64_t 
                        double acq_param, double* mean, double* var, double* acq, int64_t bso, void* workspace,
                        size_t workspace_bytes, void* stream);
 
-/* Exact int8 mode (n_pad <= 8192, any batch): the same call as hdbo_posterior_acq, with both GEMMs (Zs Xs^T and V = K* L^-T) computed
+/* Exact int8 mode (n_pad <= 8192, d <= 16384, any batch): the same call as hdbo_posterior_acq, with both GEMMs (Zs Xs^T and V = K* L^-T) computed
  * on the tcgen05 tensor cores from base-256 digit planes (6 x 6 digits, 21 exact int8 GEMMs accumulated in TMEM, FP64
  * recombination; csrc/kernels_i8.cu) instead of FP64 DMMA.  Results agree with hdbo_posterior_acq to ~1e-12 of the prior
  * variance (tests/test_gpu_i8.py); the absolute error grows like (outputscale / noise)^1/2, so for the 1e-6 RELATIVE bar on
