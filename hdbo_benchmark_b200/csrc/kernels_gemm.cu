@@ -176,25 +176,28 @@ cudaError_t launch_cross(const CrossParams& p, int batch, cudaStream_t stream) {
 // Train covariance, lower tiles only: Khat = outputscale*k(r2) + (noise + jitter) on the diagonal; rows/cols >= n are
 // the identity so that the padded matrix stays SPD and its factor / inverse are block-diagonal with I.  R2 gets the
 // full symmetric squared-distance matrix (diagonal exactly 0, padding 0) when requested (needed by the MLL gradient).
-__global__ void __launch_bounds__(NTHREADS, 1) k_sym_build(SymBuildParams p) {
+// Templated on the tile configuration: few-tile problems (the small n of a BO loop: 6 tiles of 128x128 at n_pad = 384) run on
+// 32x32 / 64x64 CTA tiles so that the FP64 kernel epilogue spreads over the SMs (p.tiles counts tiles of G::TM).
+template <class G>
+__global__ void __launch_bounds__(G::THREADS) k_sym_build(SymBuildParams p) {
     extern __shared__ __align__(16) double smem[];
     int bm, bn;
     lower_tile_decode(blockIdx.x, bm, bn);
     const int b = blockIdx.z;
-    Frag acc; acc.zero();
+    typename G::Frag acc; acc.zero();
     const double* Xs = p.Xs + b * p.bsX;
-    gemm_nt_mainloop(Xs + (size_t)bm * BM * p.ldx, p.ldx, Xs + (size_t)bn * BN * p.ldx, p.ldx, 0, p.kblocks, smem, acc);
+    G::mainloop(Xs + (size_t)bm * G::TM * p.ldx, p.ldx, Xs + (size_t)bn * G::TN * p.ldx, p.ldx, 0, p.kblocks, smem, acc);
     const double os = p.hyp[b * 4 + 0], noise = p.hyp[b * 4 + 1], jitter = p.hyp[b * 4 + 3];
     const double* xn = p.xn + b * p.bsxn;
     double* Kh = p.Khat + b * p.bsK;
     double* R2 = p.R2 ? p.R2 + b * p.bsK : nullptr;
 #pragma unroll
-    for (int mt = 0; mt < 8; mt++) {
-        const int i = bm * BM + frag_row(mt);
+    for (int mt = 0; mt < G::MT; mt++) {
+        const int i = bm * G::TM + G::frag_row(mt);
         const double xi = xn[i];
 #pragma unroll
-        for (int nt = 0; nt < 4; nt++) {
-            const int j0 = bn * BN + frag_col(nt);
+        for (int nt = 0; nt < G::NT; nt++) {
+            const int j0 = bn * G::TN + G::frag_col(nt);
             double kv[2], rv[2];
 #pragma unroll
             for (int e = 0; e < 2; e++) {
@@ -216,16 +219,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_sym_build(SymBuildParams p) {
     }
 }
 
-cudaError_t launch_sym_build(const SymBuildParams& p, int batch, cudaStream_t stream) {
+template <class G>
+static cudaError_t launch_sym_build_cfg(SymBuildParams p, int batch, cudaStream_t stream) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_sym_build, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_sym_build<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
+    p.tiles *= 128 / G::TM;
     dim3 grid(p.tiles * (p.tiles + 1) / 2, 1, batch);
-    k_sym_build<<<grid, NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
+    k_sym_build<G><<<grid, G::THREADS, G::SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
+}
+
+cudaError_t launch_sym_build(const SymBuildParams& p, int batch, cudaStream_t stream) {
+    const long long t128 = (long long)p.tiles * (p.tiles + 1) / 2 * batch;
+    if (t128 >= 148) return launch_sym_build_cfg<G128>(p, batch, stream);
+    if (t128 >= 37) return launch_sym_build_cfg<G64>(p, batch, stream);
+    return launch_sym_build_cfg<G32>(p, batch, stream);
 }
 
 // --------------------------------------------------------------------------------------------------------------
