@@ -15,7 +15,9 @@ def sync_time(fn):
     torch.cuda.synchronize(); t = time.perf_counter(); out = fn(); torch.cuda.synchronize(); return out, (time.perf_counter() - t) * 1e3
 
 
-for n, d in ((310, 128), (1000, 128)):
+import gc
+sizes = [(int(a), 128) for a in sys.argv[1:]] or [(310, 128), (1000, 128)]
+for n, d in sizes:
     g = torch.Generator().manual_seed(0)
     X = torch.rand(n, d, generator=g, dtype=torch.float64)
     y = (torch.sin(3 * X[:, :4].sum(-1)) + 0.1 * torch.randn(n, generator=g, dtype=torch.float64)).unsqueeze(-1)
@@ -27,6 +29,8 @@ for n, d in ((310, 128), (1000, 128)):
             res, ms = sync_time(lambda: fit_gpytorch_mll_scipy(mll, options={"fast_closure": fast}))
             out[name + "_ms"], out[name + "_evals"], out[name + "_ms_per_eval"] = ms, int(res.nfev), ms / max(int(res.nfev), 1)
             out[name + "_neg_mll"] = float(res.fun)
+            del mll
+            gc.collect(); torch.cuda.empty_cache()
         model.eval()
         acqf = A.LogExpectedImprovement(model, best_f=float(y.max()))
         bounds = torch.stack([torch.zeros(d), torch.ones(d)]).double()
