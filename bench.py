@@ -51,6 +51,18 @@ def parse():
     return p.parse_args()
 
 
+def synthetic_problem(n, d, noise=1e-3, seed=0):
+    """The synthetic workload of SURVEY.md §8d (same draws as oracle.gp_oracle.synthetic_problem(ls_mode="prior"); kept here so that
+    the measured arm does not touch oracle/): X ~ U[0,1]^{n x d}, y = standardise(sin(3 sum_{k<4} x_k) + 0.1 eps),
+    l_k = sqrt(d) exp(0.25 xi_k), outputscale 1, noise 1e-3, mean 0."""
+    g0, g1, g2 = (torch.Generator().manual_seed(seed + i) for i in range(3))
+    X = torch.rand(n, d, generator=g0, dtype=torch.float64)
+    y = torch.sin(3.0 * X[:, : min(4, d)].sum(-1)) + 0.1 * torch.randn(n, generator=g1, dtype=torch.float64)
+    y = (y - y.mean()) / y.std()
+    ls = math.sqrt(d) * torch.exp(0.25 * torch.randn(d, generator=g2, dtype=torch.float64))
+    return X, y, ls, 1.0, noise, 0.0
+
+
 def workload_config(args, world):
     return {
         "workload": f"synthetic GP n={args.n}, d={args.d}, ARD Matern-5/2, posterior+LogEI+argmax over a 2^{int(math.log2(args.pool))}"
@@ -187,7 +199,6 @@ def main():
     from hdbo_benchmark_b200.distributed import global_argmax
     from hdbo_benchmark_b200.engine import DEFAULT_CHUNK_ROWS, DeviceGP, _rup
     from hdbo_benchmark_b200.models import mll_gradient
-    from oracle import gp_oracle as O  # synthetic workload generator + cpu_baseline leg only
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -199,7 +210,7 @@ def main():
     lib = _lib.load()
 
     n, d, m = args.n, args.d, args.pool
-    X, y, ls, os_, nz, mu = O.synthetic_problem(n, d)
+    X, y, ls, os_, nz, mu = synthetic_problem(n, d)
     best_f = float(y.max())
     gp = DeviceGP(X.to(dev), y.to(dev), _lib.KERNEL_MATERN52, keep_r2=True, var_mode=args.var_mode)
     gp.set_hyper(ls.to(dev), os_, nz, mu)
@@ -396,6 +407,7 @@ def main():
         if e2e is not None:
             out["e2e"] = e2e
         if not args.no_cpu_baseline:
+            from oracle import gp_oracle as O  # the cpu_baseline leg: the only place the measured arm's process touches oracle/
             st = O.fit_state(X, y, ls, os_, nz, mu, O.MATERN52)
             Zs = Z_host[: args.cpu_sample].clone()
             rate, reps, dt = cpu_reference_rate(args, st, Zs, best_f)
