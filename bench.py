@@ -362,13 +362,14 @@ def main():
             achieved = alg_ops / (var_ms / 1e3) / 1e12 if var_ms > 0 else None
             cross_ops = pairs * float(args.steps) * m * 2.0 * n * (32 * math.ceil(d / 32))
             cross = {"kernel": "k_cross_i8 (Zs Xs^T as 21 int8 digit-pair GEMMs + FP64 distance -> kernel -> digit epilogue)",
-                     "achieved": cross_ops / (cross_ms / 1e3) / 1e12 if cross_ms > 0 else None, "unit": "TOP/s (int8 tensor ops)",
+                     "achieved": cross_ops / (cross_ms / 1e3) / 1e12 if cross_ms > 0 else None, "unit": "TOP/s",
                      "peak": i8_peak_sustained, "share_of_step": cross_ms / ms_total,
                      "note": "epilogue-bound: 60 FP64-pipe ops per K* element, see DESIGN.md"}
             roof = {
                 "kernel": "k_var_i8 (V = K* L^-T as 21 exact int8 digit-pair GEMMs on tcgen05.mma kind::i8, TMEM accumulators, "
                           "triangular k-range, FP64 recombination)",
-                "bound": "tensor", "achieved": achieved, "peak": i8_peak_sustained, "unit": "TOP/s (int8 tensor ops, 2 per MAC)",
+                "bound": "tensor", "achieved": achieved, "peak": i8_peak_sustained, "unit": "TOP/s",
+                "unit_note": "int8 tensor operations per second, 2 per multiply-accumulate (the FP64-equivalent TFLOP/s is given beside it)",
                 "frac": (achieved / i8_peak_sustained) if achieved else None, "traffic": traffic, "launches": int(var_n),
                 "avg_launch_ms": var_ms / max(int(var_n), 1), "share_of_step": var_ms / ms_total,
                 "algorithmic_ops_per_launch": alg_ops / max(int(var_n), 1),
@@ -395,7 +396,7 @@ def main():
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64" if args.var_mode == "f64" else "f64 (variance contraction: exact int8 digit slices on tcgen05, FP64 recombination)",
+            "dtype": "f64" if args.var_mode == "f64" else "f64 (both GEMMs of the step as exact int8 digit slices on tcgen05, FP64 recombination and epilogues)",
             "data": "synthetic", "config": workload_config(args, world), "clocks": clk,
             "gpu_launches": launches * args.steps, "argmax_index": int(best_i),
             "roofline": roof,
