@@ -163,3 +163,24 @@ def test_shard_bounds_cover_everything():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [e - s for s, e in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_bench_workload_generator_matches_the_oracle_generator():
+    """bench.py generates its synthetic workload itself (the measured arm must not touch oracle/); the draws have to stay identical to
+    the oracle's generator, which the parity tests use."""
+    import importlib.util
+    from pathlib import Path
+
+    import torch
+
+    from oracle import gp_oracle as O
+
+    spec = importlib.util.spec_from_file_location("bench_mod", Path(__file__).resolve().parent.parent / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for n, d in ((50, 7), (300, 17)):
+        a, b = bench.synthetic_problem(n, d), O.synthetic_problem(n, d)
+        assert all(torch.equal(x, y) if torch.is_tensor(x) else x == y for x, y in zip(a, b))
+    src = (Path(__file__).resolve().parent.parent / "bench.py").read_text()
+    head = src.split("def cpu_reference_rate")[0]
+    assert "oracle" not in head.replace("oracle.gp_oracle.synthetic_problem", "").replace("oracle/", "")   # no oracle import before the CPU legs
