@@ -183,6 +183,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
                  : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ long long mad_wide(int a, int b, long long c) {     // a * b + c with a 64-bit addend: one IMAD.WIDE
+    long long d;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
@@ -331,19 +343,56 @@ struct CrossI8Params {
     long long bsK;            // bytes between the K* image sets of consecutive GPs
 };
 
-// 576 threads: warp 0 producer, warp 1 MMA issuer, warps 2-17 epilogue (four warps per TMEM lane quarter, 16 columns each: the
-// FP64 kernel evaluation is a long dependent chain per element, so the epilogue needs 4 warps per scheduler to keep the FP64 and
-// ALU pipes busy -- with 8 warps the issue slots were 38 % used, profiles/r01_ncu_i8_v3.txt).
-// The epilogue first turns its 16 columns of the 6 accumulator groups into 16 FP64 inner products (registers) and releases
-// TMEM; the FP64-heavy part (distance -> kernel -> digits) then overlaps the MMAs of the CTA's next tile.
+// 576 threads: warp 0 producer, warp 1 MMA issuer, warps 2-17 epilogue (four warps per TMEM lane quarter, 16 columns each).
+//
+// Measured on B200 (tools/fp64_vs_tc.cu, profiles/r01_fp64_vs_tensor.jsonl): the scalar FP64 pipe is starved while tcgen05.mma is
+// streaming on the same SM (a DFMA stream runs 4-14x slower next to a saturated int8 MMA stream; FFMA and integer work do not
+// care).  The MMAs of the CTA's next tile therefore do NOT hide the FP64 part of this epilogue -- a tile costs MMA time + FP64 time --
+// and every FP64 instruction saved is tile time saved.  The epilogue is written for a minimal FP64 count (26 per K* element; the
+// first version needed 44 plus 13 conversion-pipe instructions):
+//   * the 6 accumulator groups are combined as two 48-bit integers (3 IMAD.WIDE each), dropped into the mantissa of 1.5 2^52 and
+//     recovered with one FP64 subtraction each -- no I2F;
+//   * x = KF r^2 = KF(|z|^2 + |x|^2) - 2 KF 2^(ez + ex) G with the power-of-two column scale ADDED TO THE EXPONENT FIELD of the row
+//     constant (integer add), KF = 5 for Matern-5/2 folded into the norms so that a = sqrt(x), k = (1 + a + x/3) exp(-a);
+//   * clamps are integer min / max on the high word; the floor x0 is where k = 1 - 2^-48 (the largest digit string: what a zero
+//     distance gave before, too), the ceiling keeps exp() out of the underflow range, so neither needs a special case; padding
+//     rows / columns get a huge norm instead of a select (k < 1e-270: zero digits, no visible mean contribution);
+//   * sqrt: 22-bit seed + one cubic correction (5 FP64), exp: 64-entry table + degree-5 polynomial (10 FP64)  (fast_math.cuh);
+//   * outputscale folded into alpha; rint(k 2^48) read from the mantissa of k 2^48 + 2^52.
+// The epilogue first turns its 16 columns into 16 FP64 inner products (registers) and releases TMEM.
 constexpr int CE_WARPS = 16, CE_THREADS = 64 + CE_WARPS * 32;
 constexpr int CE_STAGES = 4;                       // 4-stage operand ring + 48 KB staging of the two output images of a tile
 constexpr int CE_SMEM = CE_STAGES * (VT_A_STAGE + VT_B_STAGE) + 256 + 2 * VT_A_STAGE + 1024;
+
+// 16 columns of the 6 weight groups (group g at TMEM column g * VT_N, weight 2^-(8g + W0)) -> 16 doubles.  Groups 3h .. 3h+2 carry
+// relative weights 1, 2^-8, 2^-16: summed as a 48-bit integer (|sum| < 2^48 because |group| < 2^31), converted through the
+// mantissa of 1.5 2^52.  4 FP64 instructions per value (the I2F / DFMA form needs 6 + 6 conversions).
+template <int W0>
+__device__ __forceinline__ void i8_recombine16(uint32_t taddr, double (&v)[16]) {
+#pragma unroll
+    for (int h = 1; h >= 0; h--) {
+        uint32_t r0[16], r1[16], r2[16];
+        tmem_ld16_nowait(taddr + (3 * h) * VT_N, r0);
+        tmem_ld16_nowait(taddr + (3 * h + 1) * VT_N, r1);
+        tmem_ld16_nowait(taddr + (3 * h + 2) * VT_N, r2);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const long long s48 = mad_wide((int32_t)r0[j], 65536, mad_wide((int32_t)r1[j], 256, mad_wide((int32_t)r2[j], 1, 0x4338000000000000LL)));
+            const double dv = __longlong_as_double(s48) - 6755399441055744.0;
+            v[j] = h ? dv * i8_pow2(-(40 + W0)) : fma(dv, i8_pow2(-(16 + W0)), v[j]);
+        }
+    }
+}
+
 template <int KIND>
-__global__ void __launch_bounds__(CE_THREADS, 1) k_cross_i8(CrossI8Params p) {
+__global__ void __launch_bounds__(CE_THREADS, 1) k_cross_i8(CrossI8Params p) {   // (18 warps are allocated as 20: 96 registers is the cap)
     extern __shared__ uint8_t smem_raw[];
-    __shared__ double s_xn[VT_N], s_xs[VT_N], s_al[VT_N], s_ms[3][VT_M];
+    __shared__ double s_xn[VT_N], s_al[VT_N], s_ms[3][VT_M], s_tab[64];
+    __shared__ int s_xe[VT_N];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr double KF = (KIND == 0) ? 5.0 : 1.0; // Matern-5/2 works on x = 5 r^2
+    if (tid < 64) s_tab[tid] = EXP2_TAB64[tid];    // (the barrier inside i8_pipe_setup publishes it)
     const I8Pipe pp = i8_pipe_setup<CE_STAGES>(smem_raw, CE_WARPS);
     uint8_t* stage_out = pp.extra;                 // [2 k-blocks][6 planes][128 rows][32 B]: the tile's K* digit images, as in global memory
     if (warp == 0 && lane == 0) {
@@ -363,32 +412,25 @@ __global__ void __launch_bounds__(CE_THREADS, 1) k_cross_i8(CrossI8Params p) {
     if (warp >= 2) {
         const int q = warp & 3, sl = (warp - 2) >> 2, row = q * 32 + lane;   // sl: 16-column slice of the tile
         const int swz = (row >> 2) & 1;
+        const uint32_t stage_dst = smem_u32(stage_out) + (sl >> 1) * VT_A_STAGE + row * 32 + (((sl & 1) ^ swz) << 4);
         uint32_t it = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, it++) {
             const int b = t / p.tiles_per_gp, tt = t - b * p.tiles_per_gp, bn = tt % p.ntiles64, bm = tt / p.ntiles64, grow = bm * VT_M + row;
-            const double os = p.hyp[b * 4];
             if (tid >= 64 && tid < 64 + VT_N) {            // (the previous tile's readers passed the s_ms barrier below)
                 const size_t c = (size_t)b * p.n_pad + bn * VT_N + tid - 64;
-                s_xn[tid - 64] = p.xn[c]; s_xs[tid - 64] = p.xscale[c]; s_al[tid - 64] = p.alpha[c];
+                const bool cv = bn * VT_N + tid - 64 < p.n;
+                s_xn[tid - 64] = cv ? KF * p.xn[c] : 1e300;
+                s_xe[tid - 64] = __double2hiint(p.xscale[c]) - 0x3FF00000;
+                s_al[tid - 64] = cv ? p.hyp[b * 4] * p.alpha[c] : 0.0;
             }
             const size_t zr = (size_t)b * p.rows_alloc + grow;
-            const double znr = p.zn[zr], m2sz = -2.0 * p.zscale[zr];
-            const bool rowvalid = grow < p.m;
+            const double znr = (grow < p.m) ? KF * p.zn[zr] : 1e300, m2sz = -2.0 * KF * p.zscale[zr];
             const bool ok = i8_pipe_wait_accum(pp, it, p.flag);
-            double v[16];
-#pragma unroll
-            for (int j = 0; j < 16; j++) v[j] = 0.0;
-#pragma unroll
-            for (int g = I8_S - 1; g >= 0; g--) {          // smallest weights first; signed x signed: 2^-(8g+14)
-                uint32_t rr[16];
-                tmem_ld16(pp.tmem_base + ((uint32_t)(q * 32) << 16) + g * VT_N + sl * 16, rr);
-                const double w = i8_pow2(-(8 * g + 14));
-#pragma unroll
-                for (int j = 0; j < 16; j++) v[j] = fma(w, (double)(int32_t)rr[j], v[j]);
-            }
+            double v[16];                                  // G = (z / 2^ez) . (x / 2^ex); signed x signed digits: group weights 2^-(8g + 14)
+            i8_recombine16<14>(pp.tmem_base + ((uint32_t)(q * 32) << 16) + sl * 16, v);
             i8_pipe_release_tmem(pp);                      // the MMA issuer may start this CTA's next tile
             if (tid == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous tile's images have left the staging buffer
-            asm volatile("bar.sync 1, %0;" ::"n"(CE_WARPS * 32) : "memory");   // s_xn / s_xs / s_al of this tile are in place
+            asm volatile("bar.sync 1, %0;" ::"n"(CE_WARPS * 32) : "memory");   // s_xn / s_xe / s_al of this tile are in place
             double msum = 0.0;
             uint32_t dg[I8_S][4];                          // 16 columns = one 16-byte half of an image row per digit plane
 #pragma unroll
@@ -397,14 +439,21 @@ __global__ void __launch_bounds__(CE_THREADS, 1) k_cross_i8(CrossI8Params p) {
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     const int cl = sl * 16 + jq * 4 + e;
-                    const double r2 = fmax(fma(v[jq * 4 + e] * m2sz, s_xs[cl], znr + s_xn[cl]), 0.0);
-                    double k, dk;
-                    kernel_eval(KIND, r2, k, dk);
-                    const bool valid = rowvalid && (bn * VT_N + cl) < p.n;      // padding rows / columns are exact zeros
-                    const double kq = valid ? k : 0.0;
-                    msum = fma(os * kq, s_al[cl], msum);
-                    const unsigned long long X = min(__double2ull_rn(kq * 281474976710656.0), 0xFFFFFFFFFFFFULL);   // rint(k 2^48)
-                    lo[e] = (unsigned)X; hi[e] = (unsigned)(X >> 32);
+                    const double c = __hiloint2double(__double2hiint(m2sz) + s_xe[cl], __double2loint(m2sz));
+                    const double xr = fma(v[jq * 4 + e], c, znr + s_xn[cl]);
+                    constexpr int HI_MIN = (KIND == 0) ? 0x3D180000 : 0x3D000000;   // 6 2^-48 (Matern: k = 1 - x/6), 2^-47 (RBF: k = 1 - x/2)
+                    constexpr int HI_MAX = (KIND == 0) ? 0x41186A00 : 0x4095E000;   // 4e5 (a <= 633), 1400 (t >= -700)
+                    const double x = __hiloint2double(max(min(__double2hiint(xr), HI_MAX), HI_MIN), __double2loint(xr));
+                    double kq;
+                    if (KIND == 0) {
+                        const double a = sqrt_pos_cubic(x);
+                        kq = fma(x, 3.33333333333333314830e-01, 1.0 + a) * exp_neg_tab_inrange(-a, s_tab);
+                    } else {
+                        kq = exp_neg_tab_inrange(-0.5 * x, s_tab);
+                    }
+                    msum = fma(kq, s_al[cl], msum);
+                    const double qd = fma(kq, 281474976710656.0, 4503599627370496.0);      // mantissa = rint(k 2^48) <= 2^48 - 1
+                    lo[e] = (unsigned)__double2loint(qd); hi[e] = (unsigned)__double2hiint(qd) & 0xFFFFu;
                 }
                 // byte b of the four values -> one word (3 PRMT each)
 #define HDBO_GATHER(SRC, SEL) __byte_perm(__byte_perm(SRC[0], SRC[1], SEL), __byte_perm(SRC[2], SRC[3], SEL), 0x5410)
@@ -413,10 +462,9 @@ __global__ void __launch_bounds__(CE_THREADS, 1) k_cross_i8(CrossI8Params p) {
                 dg[1][jq] = HDBO_GATHER(hi, 0x0040); dg[0][jq] = HDBO_GATHER(hi, 0x0051);
 #undef HDBO_GATHER
             }
-            uint8_t* dst = stage_out + (sl >> 1) * VT_A_STAGE + row * 32 + (((sl & 1) ^ swz) << 4);
 #pragma unroll
             for (int tt = 0; tt < I8_S; tt++)
-                *reinterpret_cast<uint4*>(dst + tt * VT_M * 32) = make_uint4(dg[tt][0], dg[tt][1], dg[tt][2], dg[tt][3]);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_dst + tt * VT_M * 32), "r"(dg[tt][0]), "r"(dg[tt][1]), "r"(dg[tt][2]), "r"(dg[tt][3]) : "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the bulk-copy engine
             if (!ok) msum = __longlong_as_double(0x7ff8000000000000LL);
             if (sl) s_ms[sl - 1][row] = msum;
@@ -514,16 +562,15 @@ __global__ void __launch_bounds__(320, 1) k_var_i8(VarI8Params p) {
             if (!var_tile(p, wv, b, bm, bn)) continue;
             const double os = p.hyp[b * 4];
             const bool ok = i8_pipe_wait_accum(pp, it++, p.flag);
+            // unsigned x signed digits: group weights 2^-(8g + 15).  Integer recombination (i8_recombine16): the tensor pipe idles until
+            // TMEM is released, and 192 I2F per thread on the 16-lane conversion pipe were most of that time
             double v[32];
-#pragma unroll
-            for (int j = 0; j < 32; j++) v[j] = 0.0;
-#pragma unroll
-            for (int g = I8_S - 1; g >= 0; g--) {      // smallest weights first; unsigned x signed: 2^-(8g+15)
-                uint32_t r[32];
-                tmem_ld32(pp.tmem_base + ((uint32_t)(q * 32) << 16) + g * VT_N + ch * 32, r);
-                const double w = i8_pow2(-(8 * g + 15));
-#pragma unroll
-                for (int j = 0; j < 32; j++) v[j] = fma(w, (double)(int32_t)r[j], v[j]);
+            {
+                double (&v0)[16] = *reinterpret_cast<double (*)[16]>(&v[0]);
+                double (&v1)[16] = *reinterpret_cast<double (*)[16]>(&v[16]);
+                const uint32_t ta = pp.tmem_base + ((uint32_t)(q * 32) << 16) + ch * 32;
+                i8_recombine16<15>(ta, v0);
+                i8_recombine16<15>(ta + 16, v1);
             }
             i8_pipe_release_tmem(pp);
             const double* cs = p.colscale + (size_t)b * p.n_pad + bn * VT_N + ch * 32;
