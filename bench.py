@@ -364,7 +364,8 @@ def main():
             cross = {"kernel": "k_cross_i8 (Zs Xs^T as 21 int8 digit-pair GEMMs + FP64 distance -> kernel -> digit epilogue)",
                      "achieved": cross_ops / (cross_ms / 1e3) / 1e12 if cross_ms > 0 else None, "unit": "TOP/s",
                      "peak": i8_peak_sustained, "share_of_step": cross_ms / ms_total,
-                     "note": "epilogue-bound: 60 FP64-pipe ops per K* element, see DESIGN.md"}
+                     "note": "tile time = MMA time + epilogue FP64 time (the FP64 pipe is starved while tcgen05.mma streams: "
+                             "profiles/r01_fp64_vs_tensor.jsonl); 26 FP64 instructions per K* element, see DESIGN.md 2b"}
             roof = {
                 "kernel": "k_var_i8 (V = K* L^-T as 21 exact int8 digit-pair GEMMs on tcgen05.mma kind::i8, TMEM accumulators, "
                           "triangular k-range, FP64 recombination)",
