@@ -76,6 +76,9 @@ _SIGNATURES = {
                                 C.c_double, C.c_double, C.c_int, C.c_int, _dp]),
     "hdbo_cdist": (C.c_int, [_dp, C.c_int64, C.c_int, C.c_int, _dp, _dp, _dp, _dp]),
     "hdbo_test_math": (C.c_int, [_dp, C.c_int64, _dp, _dp, _dp]),
+    "hdbo_test_math_lean": (C.c_int, [_dp, C.c_int64, _dp, _dp, _dp]),
+    "hdbo_linear_f32": (C.c_int, [_dp, C.c_int64, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, C.c_int32, _dp, C.c_int64, C.c_int32, _dp]),
+    "hdbo_argmax_tokens_f32": (C.c_int, [_dp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _dp, _dp]),
     "hdbo_profile_enable": (C.c_int, [C.c_int]),
     "hdbo_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "hdbo_fp64_peak_probe": (C.c_int, [_dp, C.c_int, C.c_int, C.POINTER(C.c_double), _dp]),

@@ -5,6 +5,7 @@
 #include "elem.cuh"
 #include "grad.cuh"
 #include "i8.cuh"
+#include "mlp.cuh"
 #include "lbfgs.cuh"
 
 #include <cstdlib>
@@ -345,6 +346,34 @@ extern "C" int hdbo_test_math(const double* x, int64_t n, double* sqrt_out, doub
     if (!x) return -1;
     if (n < 0) return -2;
     TRY_CUDA(launch_test_math(x, n, sqrt_out, exp_out, (cudaStream_t)stream_));
+    return 0;
+}
+
+extern "C" int hdbo_linear_f32(const float* X, int64_t ldx, int32_t b, int32_t K, const float* W, const float* bias, const float* scale,
+                               const float* shift, int32_t relu, float* Y, int64_t ldy, int32_t N, void* stream_) {
+    if (!X) return -1;
+    if (b < 0) return -3;
+    if (K <= 0 || ldx < K) return -4;
+    if (!W) return -5;
+    if (!Y) return -10;
+    if (N < 0 || ldy < N) return -12;
+    TRY_CUDA(launch_linear_f32(X, ldx, b, K, W, bias, scale, shift, relu, Y, ldy, N, (cudaStream_t)stream_));
+    return 0;
+}
+
+extern "C" int hdbo_argmax_tokens_f32(const float* logits, int64_t ld, int32_t b, int32_t L, int32_t A, int32_t* tokens, void* stream_) {
+    if (!logits) return -1;
+    if (b < 0) return -3;
+    if (L <= 0 || A <= 0 || ld < (int64_t)L * A) return -2;
+    if (!tokens) return -6;
+    TRY_CUDA(launch_argmax_tokens_f32(logits, ld, b, L, A, tokens, (cudaStream_t)stream_));
+    return 0;
+}
+
+extern "C" int hdbo_test_math_lean(const double* x, int64_t n, double* sqrt_out, double* exp_out, void* stream_) {
+    if (!x) return -1;
+    if (n < 0) return -2;
+    TRY_CUDA(launch_test_math_lean(x, n, sqrt_out, exp_out, (cudaStream_t)stream_));
     return 0;
 }
 

@@ -80,6 +80,7 @@ cudaError_t launch_finalize_acq(const double* meanpart, const double* varpart, l
 cudaError_t launch_acq_elem(const double* mean, const double* var, long long m, int acq_kind, double acq_param, double* acq,
                             double* dmean, double* dvar, cudaStream_t stream);
 cudaError_t launch_test_math(const double* x, long long n, double* s, double* e, cudaStream_t st);
+cudaError_t launch_test_math_lean(const double* x, long long n, double* s, double* e, cudaStream_t st);
 cudaError_t launch_argmax(const double* v, long long m, void* work, double* out_val, long long* out_idx, cudaStream_t stream);
 
 }  // namespace hdbo

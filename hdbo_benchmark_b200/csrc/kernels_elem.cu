@@ -264,6 +264,21 @@ __global__ void k_test_math(const double* __restrict__ x, long long n, double* _
     if (s) s[i] = sqrt_pos(fmin(fmax(x[i], 1e-30), 1e30));
     if (e) e[i] = exp_nonpos(-fabs(x[i]));
 }
+// the FP64-lean forms of the int8 cross kernel: sqrt (clamped to [1e-30, 1e300]) and exp(-|x|) with |x| clamped to 700
+__global__ void k_test_math_lean(const double* __restrict__ x, long long n, double* __restrict__ s, double* __restrict__ e) {
+    __shared__ double tab[64];
+    if (threadIdx.x < 64) tab[threadIdx.x] = EXP2_TAB64[threadIdx.x];
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (s) s[i] = sqrt_pos_cubic(fmin(fmax(x[i], 1e-30), 1e300));
+    if (e) e[i] = exp_neg_tab_inrange(-fmin(fabs(x[i]), 700.0) - 0.0, tab);
+}
+cudaError_t launch_test_math_lean(const double* x, long long n, double* s, double* e, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_test_math_lean<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n, s, e);
+    return cudaGetLastError();
+}
 cudaError_t launch_test_math(const double* x, long long n, double* s, double* e, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     k_test_math<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n, s, e);

@@ -160,6 +160,8 @@ int hdbo_cdist(const double* X, int64_t ldx, int n, int d, double* Xs, double* x
 /* Test hook: sqrt_out[i] = sqrt(clamp(x[i], 1e-30, 1e30)), exp_out[i] = exp(-|x[i]|) computed with the branch-free device
  * routines the kernel epilogues use (csrc/fast_math.cuh); either output may be NULL. */
 int hdbo_test_math(const double* x, int64_t n, double* sqrt_out, double* exp_out, void* stream);
+/* Same for the FP64-lean forms of the int8 cross kernel (cubic sqrt correction; table-based exp, |x| clamped to 700). */
+int hdbo_test_math_lean(const double* x, int64_t n, double* sqrt_out, double* exp_out, void* stream);
 
 /* Opt-in profiling for bench.py: while enabled, CUDA events are recorded on the caller's stream around the two GEMM
  * phases of the posterior (class 0 = cross-kernel build, class 1 = variance contraction).  collect() synchronises on
@@ -194,6 +196,19 @@ typedef struct hdbo_lbfgs {
 } hdbo_lbfgs;
 int hdbo_lbfgs_propose(const hdbo_lbfgs* s, void* stream);
 int hdbo_lbfgs_accept(const hdbo_lbfgs* s, void* stream);
+
+/* ---- VAE decode next to the hot path -------------------------------------------------------------------
+ * Replaces: one Linear (+ eval-mode BatchNorm1d + ReLU; Dropout is the identity in eval mode) of the decoder / encoder
+ * nn.Sequential of the reference's latent-space models (src/hdbo_benchmark/generative_models/vae_selfies.py:48-81), FP32 like
+ * the reference:   Y[r][n] = act((X[r] . W[n] + bias[n]) * scale[n] + shift[n]),  r < b, n < N
+ * W [N][K] row-major (torch nn.Linear.weight), bias / scale / shift [N] or NULL (scale = gamma / sqrt(running_var + eps),
+ * shift = beta - running_mean * scale: ATen's eval-mode batch norm), relu != 0 applies max(., 0).  X [b][ldx], Y [b][ldy]. */
+int hdbo_linear_f32(const float* X, int64_t ldx, int32_t b, int32_t K, const float* W, const float* bias, const float* scale,
+                    const float* shift, int32_t relu, float* Y, int64_t ldy, int32_t N, void* stream);
+
+/* Replaces: np.argmax(logits.reshape(b, L, A), axis=-1) in VAESelfies._logits_to_string_array (vae_selfies.py:241-247):
+ * tokens [b][L] (int32), first index on ties; logits [b][ld] finite FP32 with position p at columns p*A .. p*A+A-1. */
+int hdbo_argmax_tokens_f32(const float* logits, int64_t ld, int32_t b, int32_t L, int32_t A, int32_t* tokens, void* stream);
 
 /* Same for the int8 tensor pipe: `sms` CTAs issue resident-operand tcgen05.mma kind::i8 (M128 N256 K32) only; *ops_out (HOST) =
  * integer operations performed (2 per multiply-accumulate).  flag: device int32, set if the completion wait timed out. */

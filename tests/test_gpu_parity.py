@@ -172,6 +172,27 @@ def test_branch_free_sqrt_exp_match_the_library(cuda_device):
     assert float(e[~big].abs().max()) < 1e-299 and bool((e >= 0).all())
 
 
+def test_fp64_lean_sqrt_exp_of_the_int8_cross_kernel(cuda_device):
+    """sqrt_pos_cubic / exp_neg_tab_inrange (csrc/fast_math.cuh; 5 and 10 FP64 instructions) against torch's float64 sqrt / exp."""
+    from hdbo_benchmark_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(1)
+    x = torch.cat([
+        torch.rand(200000, generator=g, dtype=torch.float64) * 60.0,
+        10.0 ** (torch.rand(100000, generator=g, dtype=torch.float64) * 330.0 - 30.0),   # 1e-30 .. 1e300
+        torch.tensor([0.0, 1e-30, 2.13e-14, 1.0, 2.0, 4.0, 632.4, 699.9, 700.0, 4e5, 1e300], dtype=torch.float64),
+    ]).to(cuda_device)
+    s = torch.empty_like(x)
+    e = torch.empty_like(x)
+    _lib.check(lib.hdbo_test_math_lean(x.data_ptr(), x.numel(), s.data_ptr(), e.data_ptr(), torch.cuda.current_stream().cuda_stream), "math")
+    want_s = x.clamp(1e-30, 1e300).sqrt()
+    assert float(((s - want_s).abs() / want_s).max()) < 4e-16
+    want_e = torch.exp(-x.clamp(max=700.0))
+    assert float(((e - want_e).abs() / want_e).max()) < 1e-15
+    assert bool((e > 0).all()) and bool((e <= 1).all())
+
+
 def test_cholesky_failure_reports_info_and_jitter_recovers(cuda_device):
     from hdbo_benchmark_b200.engine import DeviceGP, NotPSDError
 
