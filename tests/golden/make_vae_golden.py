@@ -16,21 +16,21 @@ LATENT, SEQ, ALPHA = 8, 6, 11
 def build(seed: int = 0):
     torch.manual_seed(seed)
     width = SEQ * ALPHA
-    decoder = nn.Sequential(nn.Linear(LATENT, 16), nn.BatchNorm1d(16), nn.ReLU(), nn.Dropout(0.2),
-                            nn.Linear(16, 40), nn.BatchNorm1d(40), nn.ReLU(), nn.Dropout(0.2),
-                            nn.Linear(40, 52), nn.BatchNorm1d(52), nn.ReLU(), nn.Dropout(0.2),
-                            nn.Linear(52, width))
-    encoder = nn.Sequential(nn.Linear(width, 52), nn.BatchNorm1d(52), nn.ReLU(), nn.Dropout(0.2),
-                            nn.Linear(52, 16), nn.BatchNorm1d(16), nn.ReLU(), nn.Dropout(0.2))
-    encoder_mu = nn.Linear(16, LATENT)
+    decoder = nn.Sequential(nn.Linear(LATENT, 16, dtype=torch.float32), nn.BatchNorm1d(16, dtype=torch.float32), nn.ReLU(), nn.Dropout(0.2),
+                            nn.Linear(16, 40, dtype=torch.float32), nn.BatchNorm1d(40, dtype=torch.float32), nn.ReLU(), nn.Dropout(0.2),
+                            nn.Linear(40, 52, dtype=torch.float32), nn.BatchNorm1d(52, dtype=torch.float32), nn.ReLU(), nn.Dropout(0.2),
+                            nn.Linear(52, width, dtype=torch.float32))
+    encoder = nn.Sequential(nn.Linear(width, 52, dtype=torch.float32), nn.BatchNorm1d(52, dtype=torch.float32), nn.ReLU(), nn.Dropout(0.2),
+                            nn.Linear(52, 16, dtype=torch.float32), nn.BatchNorm1d(16, dtype=torch.float32), nn.ReLU(), nn.Dropout(0.2))
+    encoder_mu = nn.Linear(16, LATENT, dtype=torch.float32)
     g = torch.Generator().manual_seed(seed + 1)
     for seq in (decoder, encoder):
         for m in seq:
             if isinstance(m, nn.BatchNorm1d):   # as after training: running statistics and affine parameters away from (0, 1, 1, 0)
-                m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.3)
-                m.running_var.copy_(torch.rand(m.num_features, generator=g) * 1.5 + 0.25)
-                m.weight.data.copy_(torch.rand(m.num_features, generator=g) + 0.5)
-                m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.2)
+                m.running_mean.copy_(torch.randn(m.num_features, generator=g, dtype=torch.float32) * 0.3)
+                m.running_var.copy_(torch.rand(m.num_features, generator=g, dtype=torch.float32) * 1.5 + 0.25)
+                m.weight.data.copy_(torch.rand(m.num_features, generator=g, dtype=torch.float32) + 0.5)
+                m.bias.data.copy_(torch.randn(m.num_features, generator=g, dtype=torch.float32) * 0.2)
     for m in (decoder, encoder, encoder_mu):
         m.eval()
     return decoder, encoder, encoder_mu
@@ -39,7 +39,7 @@ def build(seed: int = 0):
 def main():
     decoder, encoder, encoder_mu = build()
     g = torch.Generator().manual_seed(7)
-    z = torch.randn(23, LATENT, generator=g)
+    z = torch.randn(23, LATENT, generator=g, dtype=torch.float32)
     with torch.no_grad():
         logits = decoder(z)
         tokens = logits.reshape(-1, SEQ, ALPHA).argmax(-1)

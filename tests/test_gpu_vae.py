@@ -19,9 +19,9 @@ def _decoder(latent, widths, out, seed):
     torch.manual_seed(seed)
     mods, k = [], latent
     for w in widths:
-        mods += [nn.Linear(k, w), nn.BatchNorm1d(w), nn.ReLU(), nn.Dropout(0.2)]
+        mods += [nn.Linear(k, w, dtype=torch.float32), nn.BatchNorm1d(w, dtype=torch.float32), nn.ReLU(), nn.Dropout(0.2)]
         k = w
-    mods.append(nn.Linear(k, out))
+    mods.append(nn.Linear(k, out, dtype=torch.float32))
     seq = nn.Sequential(*mods)
     for m in seq:
         if isinstance(m, nn.BatchNorm1d):
@@ -37,7 +37,7 @@ def test_decode_at_the_reference_shape_matches_the_oracle(cuda_device, b):
     dec = _decoder(128, [256, 1024, 2048], L * A, seed=11)
     alphabet = {f"[t{i}]": i for i in range(A)}
     vae = DeviceVAE(DeviceMLP.from_sequential(dec, cuda_device), alphabet, L)
-    z = torch.randn(b, 128, generator=torch.Generator().manual_seed(b))
+    z = torch.randn(b, 128, generator=torch.Generator().manual_seed(b), dtype=torch.float32)
     want = V.mlp_forward(V.layers_from_torch_sequential(dec), z.numpy())
     got = vae.decode_logits(z).reshape(b, -1).cpu().numpy()
     scale = np.abs(want).max()

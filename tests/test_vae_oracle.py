@@ -23,13 +23,13 @@ def test_oracle_matches_torch_nn_eval_mode_at_the_reference_shape():
     """latent 128 -> 256 -> 1024 -> 2048 -> 70 x 64 logits, random weights / running statistics."""
     torch.manual_seed(3)
     L, A = 70, 64
-    dec = nn.Sequential(nn.Linear(128, 256), nn.BatchNorm1d(256), nn.ReLU(), nn.Dropout(0.2), nn.Linear(256, 1024), nn.BatchNorm1d(1024), nn.ReLU(),
-                        nn.Dropout(0.2), nn.Linear(1024, 2048), nn.BatchNorm1d(2048), nn.ReLU(), nn.Dropout(0.2), nn.Linear(2048, L * A))
+    dec = nn.Sequential(nn.Linear(128, 256, dtype=torch.float32), nn.BatchNorm1d(256, dtype=torch.float32), nn.ReLU(), nn.Dropout(0.2), nn.Linear(256, 1024, dtype=torch.float32), nn.BatchNorm1d(1024, dtype=torch.float32), nn.ReLU(),
+                        nn.Dropout(0.2), nn.Linear(1024, 2048, dtype=torch.float32), nn.BatchNorm1d(2048, dtype=torch.float32), nn.ReLU(), nn.Dropout(0.2), nn.Linear(2048, L * A, dtype=torch.float32))
     for m in dec:
         if isinstance(m, nn.BatchNorm1d):
             m.running_mean.normal_(0, 0.2); m.running_var.uniform_(0.3, 1.7); m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.1)
     dec.eval()
-    z = torch.randn(9, 128)
+    z = torch.randn(9, 128, dtype=torch.float32)
     with torch.no_grad():
         want = dec(z).numpy()
     got = V.mlp_forward(V.layers_from_torch_sequential(dec), z.numpy())
