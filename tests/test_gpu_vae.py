@@ -110,9 +110,9 @@ def test_linear_without_bias_or_batchnorm_and_strided_io(cuda_device):
     lib = _lib.load()
     g = torch.Generator().manual_seed(5)
     b, K, N = 5, 36, 21
-    Xp = torch.randn(b, K + 4, generator=g).to(cuda_device)              # ldx > K
-    W = torch.randn(N, K, generator=g).to(cuda_device)
-    Yp = torch.full((b, N + 3), 7.0, device=cuda_device)                 # ldy > N: the padding must stay untouched
+    Xp = torch.randn(b, K + 4, generator=g, dtype=torch.float32).to(cuda_device)              # ldx > K
+    W = torch.randn(N, K, generator=g, dtype=torch.float32).to(cuda_device)
+    Yp = torch.full((b, N + 3), 7.0, dtype=torch.float32, device=cuda_device)                 # ldy > N: the padding must stay untouched
     _lib.check(lib.hdbo_linear_f32(Xp.data_ptr(), Xp.stride(0), b, K, W.data_ptr(), 0, 0, 0, 1, Yp.data_ptr(), Yp.stride(0), N,
                                    torch.cuda.current_stream().cuda_stream), "linear")
     want = np.maximum(Xp[:, :K].cpu().numpy().astype(np.float64) @ W.cpu().numpy().astype(np.float64).T, 0.0)
