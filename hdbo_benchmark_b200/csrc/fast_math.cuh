@@ -47,33 +47,6 @@ __device__ __forceinline__ double exp_nonpos(double t) {
     return (n < -1021) ? 0.0 : __longlong_as_double(bits);
 }
 
-// Same function with the range reduction kept on the FP64 pipe: n = round(t / ln 2) comes out of the mantissa of t log2(e) + 1.5 2^52
-// (FRND.F64 and F2I.F64 run on the 16-lane conversion pipe).
-__device__ __forceinline__ double exp_nonpos_magic(double t) {
-    t = fmax(t, -740.0);
-    const double nm = fma(t, 1.4426950408889634074, 6755399441055744.0);
-    const int n = __double2loint(nm);                                   // in [-1068, 0]
-    const double nf = nm - 6755399441055744.0;
-    double f = fma(nf, -6.93147180369123816490e-01, t);
-    f = fma(nf, -1.90821492927058770002e-10, f);
-    double p = 1.6059043836821614599e-10;
-    p = fma(p, f, 2.0876756987868098979e-09);
-    p = fma(p, f, 2.5052108385441718775e-08);
-    p = fma(p, f, 2.7557319223985890653e-07);
-    p = fma(p, f, 2.7557319223985892511e-06);
-    p = fma(p, f, 2.4801587301587301566e-05);
-    p = fma(p, f, 1.9841269841269841253e-04);
-    p = fma(p, f, 1.3888888888888889419e-03);
-    p = fma(p, f, 8.3333333333333332177e-03);
-    p = fma(p, f, 4.1666666666666664354e-02);
-    p = fma(p, f, 1.6666666666666665741e-01);
-    p = fma(p, f, 0.5);
-    p = fma(p, f, 1.0);
-    p = fma(p, f, 1.0);
-    const int hi = __double2hiint(p) + (n << 20);
-    return (n < -1021) ? 0.0 : __hiloint2double(hi, __double2loint(p));
-}
-
 // ---- the FP64-lean forms used by the int8 cross kernel -----------------------------------------------------------------------
 // On B200 the scalar FP64 pipe does not run while tcgen05.mma is streaming on the same SM (tools/fp64_vs_tc.cu: a DFMA stream takes
 // 4-14x longer next to a saturated int8 MMA stream, FFMA / integer work is unaffected), so in a kernel that feeds the tensor cores
