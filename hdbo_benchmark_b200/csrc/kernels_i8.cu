@@ -455,7 +455,8 @@ __global__ void __launch_bounds__(CE_THREADS, 1) k_cross_i8(CrossI8Params p) {  
             for (int tt = 0; tt < I8_S; tt++)
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_dst + tt * VT_M * 32), "r"(dg[tt][0]), "r"(dg[tt][1]), "r"(dg[tt][2]), "r"(dg[tt][3]) : "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the bulk-copy engine
-            if (!ok) msum = __longlong_as_double(0x7ff8000000000000LL);
+            // (the integer clamps swallow NaN: a candidate row with a NaN coordinate -- NaN norm -- gets a NaN mean, as on the FP64 path)
+            if (!ok || znr != znr) msum = __longlong_as_double(0x7ff8000000000000LL);
             if (sl) s_ms[sl - 1][row] = msum;
             asm volatile("bar.sync 1, %0;" ::"n"(CE_WARPS * 32) : "memory");
             if (!sl) p.meanpart[(size_t)b * p.ntiles64 * p.rows_alloc + (size_t)bn * p.rows_pad + grow] = ((msum + s_ms[0][row]) + s_ms[1][row]) + s_ms[2][row];

@@ -333,3 +333,19 @@ def test_i8_random_hyperparameter_sweep_against_f64_mode(cuda_device):
         dv = (res["i8"][1] - res["f64"][1]).abs()
         assert float(dv.max()) < 5e-11 * os_, (trial, n, d, float(dv.max()) / os_, nz / os_)
         assert float((dv / res["f64"][1].abs()).max()) < REL, (trial, n, d, nz / os_)
+
+
+def test_nan_candidate_gives_nan_mean_and_acquisition(cuda_device):
+    """The integer clamps of the cross epilogue must not turn a NaN coordinate into a finite prediction."""
+    from hdbo_benchmark_b200 import _lib
+    from hdbo_benchmark_b200.engine import DeviceGP
+
+    X, y, ls, os_, nz, mu = O.synthetic_problem(200, 12)
+    gp = DeviceGP(X.to(cuda_device), y.to(cuda_device), O.MATERN52, var_mode="i8")
+    gp.set_hyper(ls.to(cuda_device), os_, nz, mu); gp.fit()
+    Z = torch.rand(300, 12, dtype=torch.float64, device=cuda_device)
+    Z[17, 3] = float("nan")
+    mean, var, acq = gp.posterior_acq(Z, _lib.ACQ_LOGEI, float(y.max()))
+    assert bool(torch.isnan(mean[0, 17])) and bool(torch.isnan(acq[0, 17]))
+    keep = torch.ones(300, dtype=torch.bool, device=cuda_device); keep[17] = False
+    assert bool(torch.isfinite(mean[0, keep]).all()) and bool(torch.isfinite(acq[0, keep]).all()) and gp.i8_flag() == 0
