@@ -4,7 +4,7 @@
 //   k_lbfgs_propose   projected gradient -> two-loop recursion over the (s, y) ring -> direction on the free variables ->
 //                     T trial points  clip(x + 2^-j dir)  (a whole backtracking line search, evaluated in ONE batched f/g call)
 //   [caller]          f and gradient at the R x T trial points (hdbo_posterior_fwd / hdbo_acq_elementwise / hdbo_posterior_bwd)
-//   k_lbfgs_accept    first trial that satisfies the Armijo condition along the projected path (else the best decreasing one),
+//   k_lbfgs_accept    best trial that satisfies the Armijo condition along the projected path (else the best decreasing one),
 //                     curvature-checked ring update, convergence flags (projected-gradient sup-norm, relative decrease, maxiter)
 // so the host enqueues a handful of launches per iteration and never reads a value back until it polls the `done` flags.
 #include "kernels.cuh"
@@ -55,7 +55,7 @@ __device__ __forceinline__ double proj_grad(double x, double g, double lo, doubl
 }
 }  // namespace
 
-// meta[r] = {count, head, done, iters}
+// meta[r] = {count, head, done (1 converged, 2 stalled), iters}
 __global__ void __launch_bounds__(LB_THREADS) k_lbfgs_propose(LbfgsParams p) {
     extern __shared__ double sm[];
     double* q = sm;                 // [D] working vector of the two-loop recursion
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(LB_THREADS) k_lbfgs_propose(LbfgsParams p) {
     const double* g = p.g + (size_t)r * D;
     int* meta = p.meta + 4 * r;
     double* Xt = p.Xt + (size_t)r * p.T * D;
-    if (meta[2]) {                  // converged: keep the trial evaluations harmless
+    if (meta[2] > 0) {              // finished: keep the trial evaluations harmless
         for (int j = 0; j < p.T; j++)
             for (int i = tid; i < D; i += LB_THREADS) Xt[(size_t)j * D + i] = x[i];
         return;
@@ -134,21 +134,24 @@ __global__ void __launch_bounds__(LB_THREADS) k_lbfgs_accept(LbfgsParams p) {
     __shared__ int s_pick;
     const int r = blockIdx.x, D = p.D, M = p.M, T = p.T, tid = threadIdx.x;
     int* meta = p.meta + 4 * r;
-    if (meta[2]) return;
+    if (meta[2] > 0) return;
     double* x = p.x + (size_t)r * D;
     double* g = p.g + (size_t)r * D;
     const double* Xt = p.Xt + (size_t)r * T * D;
     const double* gt = p.gt + (size_t)r * T * D;
     const double* ft = p.ft + (size_t)r * T;
     const double f0 = p.f[r];
-    // first trial that satisfies Armijo along the projected path:  f_j <= f0 + c1 g.(x_j - x)
+    // the T trials were evaluated together, so take the BEST one that satisfies Armijo along the projected path,
+    // f_j <= f0 + c1 g.(x_j - x), not the first: with only backtracking, a badly scaled direction (few / skipped curvature pairs)
+    // yields a full step with a tiny decrease and a false ftol stop; scipy's L-BFGS-B avoids that with a strong-Wolfe search
     int pick = -1;
-    for (int j = 0; j < T && pick < 0; j++) {
+    double bestf = f0;
+    for (int j = 0; j < T; j++) {
         double d = 0.0;
         for (int i = tid; i < D; i += LB_THREADS) d += g[i] * (Xt[(size_t)j * D + i] - x[i]);
         d = block_sum(d, red);
         const double fj = ft[j];
-        if (isfinite(fj) && fj <= f0 + 1e-4 * d && d < 0.0) pick = j;
+        if (isfinite(fj) && d < 0.0 && fj <= f0 + 1e-4 * d && fj < bestf) { bestf = fj; pick = j; }
     }
     if (pick < 0) {                                          // fall back to the best strictly decreasing trial
         double best = f0;
@@ -189,7 +192,8 @@ __global__ void __launch_bounds__(LB_THREADS) k_lbfgs_accept(LbfgsParams p) {
     if (tid == 0) {
         const double f1 = ft[pick];
         p.f[r] = f1;
-        p.step[r] = (pick == 0) ? fmin(1.0, 2.0 * p.step[r]) : p.step[r] * exp2(-(double)(pick - 1));   // next first trial
+        // next first trial: twice the accepted step, so that the trial grid {2a, a, a/2, ...} brackets the scale that just worked
+        p.step[r] = fmin(fmax(p.step[r] * exp2(1.0 - (double)pick), 1e-20), 1e6);
         const int it = ++meta[3];
         const double rel = (f0 - f1) / fmax(fmax(fabs(f0), fabs(f1)), 1.0);
         if (pgmax <= p.gtol || rel <= p.ftol || it >= p.maxiter) meta[2] = 1;

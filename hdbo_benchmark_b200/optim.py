@@ -223,7 +223,7 @@ def gen_candidates_device(initial_conditions: torch.Tensor, acquisition_function
         for _ in range(min(check_every, maxiter - done_iters)):
             graph.replay() if graph is not None else iteration()
             done_iters += 1
-        if bool((meta[:, 2] != 0).all()):
+        if bool((meta[:, 2] > 0).all()):
             break
     if not bool(torch.isfinite(f).all()):
         raise RuntimeError("acquisition value is not finite")

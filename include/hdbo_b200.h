@@ -179,7 +179,7 @@ int hdbo_fp64_peak_probe(double* scratch, int iters, int sms, double* flops_out,
  * float64-ndarray round trip dominates `next_candidate()` once the acquisition itself takes microseconds.
  * One iteration = hdbo_lbfgs_propose (direction from the (s, y) ring, T trial points clip(x + 2^-j dir) of a backtracking line
  * search) -> the caller evaluates value + gradient at the R x T trial points (hdbo_posterior_fwd / hdbo_acq_elementwise /
- * hdbo_posterior_bwd) into ft / gt -> hdbo_lbfgs_accept (Armijo pick, ring update, convergence flags in meta).  No host
+ * hdbo_posterior_bwd) into ft / gt -> hdbo_lbfgs_accept (best Armijo trial, ring update, convergence flags in meta).  No host
  * synchronisation is needed until the caller polls meta[r][2].  Initial state: x, f, g at the starting points, meta zeroed,
  * step = 1. */
 typedef struct hdbo_lbfgs {
