@@ -402,6 +402,12 @@ def main():
             "gpu_launches": launches * args.steps, "argmax_index": int(best_i),
             "roofline": roof,
             "mll_fit_grad_ms": min(mll_ms),
+            # the second metric of BASELINE.json against its own roofline: n^3 + 3 n^2 d FP64 flops on the DMMA ceiling
+            "mll_roofline": {"bound": "tensor", "unit": "TFLOP/s", "algorithmic_flops": float(args.n) ** 3 + 3.0 * float(args.n) ** 2 * args.d,
+                             "achieved": (float(args.n) ** 3 + 3.0 * float(args.n) ** 2 * args.d) / (min(mll_ms) * 1e-3) / 1e12, "peak": peak,
+                             "frac": (float(args.n) ** 3 + 3.0 * float(args.n) ** 2 * args.d) / (min(mll_ms) * 1e-3) / 1e12 / peak,
+                             "note": "a dependency chain, not a throughput limit: 32 leaves + 114 small GEMMs per evaluation run on a few SMs "
+                                     "(2.7 ms) next to 2.4 ms of large GEMMs at 28-32 TF/s; DESIGN.md 8 (next steps)"},
         }
         if mode_check is not None:
             out["var_mode_check"] = mode_check
