@@ -41,6 +41,7 @@ def parse():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--n", type=int, default=4096)
+    p.add_argument("--no-mll-batched", action="store_true", help="skip the batched (4 hyper-parameter vectors) MLL timing")
     p.add_argument("--d", type=int, default=256)
     p.add_argument("--pool", type=int, default=1 << 20, help="candidates per GPU per step")
     p.add_argument("--cpu-sample", type=int, default=8192, help="candidates per CPU-baseline batch")
@@ -229,6 +230,28 @@ def main():
         e0.record(); mll_once(); e1.record(); torch.cuda.synchronize()
         mll_ms.append(e0.elapsed_time(e1))
     gp.fit(need_r2=False)
+    # the same evaluation as the device fit runs it (fit.fit_gpytorch_mll_device): the trial points of one line search = one batched
+    # fit + gradient, so the latency-bound leaf chains of the members overlap.  Reported per member; rank 0 only.
+    mll_batched = None
+    if rank == 0 and not args.no_mll_batched:
+        Bm = 4
+        gpb = DeviceGP(X.to(dev), y.to(dev), _lib.KERNEL_MATERN52, batch=Bm, keep_r2=True)
+        scale = torch.linspace(0.9, 1.1, Bm, dtype=torch.float64).unsqueeze(1)
+        gpb.set_hyper((ls.unsqueeze(0) * scale).to(dev), os_, nz, mu)
+        def mll_b():
+            gpb.fit_once(need_r2=True)
+            return mll_gradient(gpb)
+        for _ in range(2):
+            mll_b()
+        torch.cuda.synchronize()
+        tb = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); mll_b(); e1.record(); torch.cuda.synchronize()
+            tb.append(e0.elapsed_time(e1))
+        mll_batched = {"batch": Bm, "ms_per_batch": min(tb), "ms_per_member": min(tb) / Bm}
+        del gpb
+        torch.cuda.empty_cache()
 
     # ---- candidate pool of this rank: scrambled Sobol, fast-forwarded to the rank's shard ----
     eng = torch.quasirandom.SobolEngine(d, scramble=True, seed=3)
@@ -409,6 +432,12 @@ def main():
                              "note": "a dependency chain, not a throughput limit: 32 leaves + 114 small GEMMs per evaluation run on a few SMs "
                                      "(2.7 ms) next to 2.4 ms of large GEMMs at 28-32 TF/s; DESIGN.md 8 (next steps)"},
         }
+        if mll_batched is not None:
+            fl_m = float(args.n) ** 3 + 3.0 * float(args.n) ** 2 * args.d
+            mll_batched.update({"achieved_tflops": fl_m / (mll_batched["ms_per_member"] * 1e-3) / 1e12,
+                                "frac_of_fp64_dmma_peak": fl_m / (mll_batched["ms_per_member"] * 1e-3) / 1e12 / peak,
+                                "note": "the trial points of one line search of the device fit = one batched fit + gradient; the leaf chains overlap"})
+            out["mll_fit_grad_batched"] = mll_batched
         if mode_check is not None:
             out["var_mode_check"] = mode_check
             out["fp64_dmma_mode"] = f64_mode
