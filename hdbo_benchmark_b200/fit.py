@@ -333,7 +333,12 @@ def fit_gpytorch_mll_device(mll, options: Optional[Dict] = None, bounds=None):
             return None
         blocks.append((role, off, sz, cf, pf))
     d, D, n = meta_np.d, meta_np.nx, meta_np.n
-    T = int(options.get("line_search_trials", 8 if n <= 1024 else 4))   # measured: 2-4 trial steps stop early on ARD fits (n = 1000: 0.56 vs 0.35)
+    # The batched line search pays off while one fit is latency-bound (8 members cost about one).  Measured at d = 128: n = 310 85 ms
+    # vs 677 ms (scipy, fast closure), n = 1000 327 vs 869 ms, but n = 4096 -- compute-bound, every iteration costs T evaluations --
+    # 2.2 s vs 0.9 s: above `device_max_n` the scipy path runs.
+    if n > int(options.get("device_max_n", 1536)):
+        return None
+    T = int(options.get("line_search_trials", 8))   # measured: 2-4 trial steps stop early on ARD fits (n = 1000: -mll/n 0.56 vs 0.35)
     M = int(options.get("maxcor", 10))
     maxiter = int(options.get("maxiter", 2000))
     gp = DeviceGP(model.train_inputs[0], model.train_targets, model._base_kernel.kind, batch=T, keep_r2=True)
