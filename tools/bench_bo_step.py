@@ -34,7 +34,7 @@ for n, d in sizes:
         # batched-trial L-BFGS on the device (8 line-search points per iteration), then the scipy polish from its answer
         m2 = SingleTaskGP(X, y)
         mll2 = ExactMarginalLogLikelihood(m2.likelihood, m2)
-        res, ms = sync_time(lambda: fit_gpytorch_mll_device(mll2, options={}))
+        res, ms = sync_time(lambda: fit_gpytorch_mll_device(mll2, options={"device_max_n": 10 ** 9}))   # (measure it at every n)
         out["fit_device_ms"], out["fit_device_iters"], out["fit_device_neg_mll"] = ms, int(res.nit), float(res.fun)
         res, ms2 = sync_time(lambda: fit_gpytorch_mll_scipy(mll2, options={}))
         out["fit_device_polish_ms"], out["fit_device_polish_evals"], out["fit_device_polished_neg_mll"] = ms2, int(res.nfev), float(res.fun)
