@@ -29,7 +29,7 @@ def _decoder(latent, widths, out, seed):
     return seq.eval()
 
 
-@pytest.mark.parametrize("b", [1, 3, 8, 17, 100])
+@pytest.mark.parametrize("b", [1, 3, 8, 17, 100, 160])
 def test_decode_at_the_reference_shape_matches_the_oracle(cuda_device, b):
     from hdbo_benchmark_b200.vae_decode import DeviceMLP, DeviceVAE
 
@@ -118,3 +118,24 @@ def test_linear_without_bias_or_batchnorm_and_strided_io(cuda_device):
     want = np.maximum(Xp[:, :K].cpu().numpy().astype(np.float64) @ W.cpu().numpy().astype(np.float64).T, 0.0)
     assert np.abs(Yp[:, :N].cpu().numpy() - want).max() < 1e-5 * np.abs(want).max()
     assert bool((Yp[:, N:] == 7.0).all())
+
+
+@pytest.mark.parametrize("b,K,N", [(150, 36, 21), (128, 16, 64), (257, 100, 130)])
+def test_tiled_layer_kernel_on_ragged_shapes(cuda_device, b, K, N):
+    """>= 128 rows take the shared-memory tiled kernel: partial tiles in every dimension, K not a multiple of the 16-deep k-step."""
+    from hdbo_benchmark_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(b + K + N)
+    X = torch.randn(b, K, generator=g, dtype=torch.float32).to(cuda_device)
+    W = torch.randn(N, K, generator=g, dtype=torch.float32).to(cuda_device)
+    bias = torch.randn(N, generator=g, dtype=torch.float32).to(cuda_device)
+    sc = (torch.rand(N, generator=g, dtype=torch.float32) + 0.5).to(cuda_device)
+    sh = torch.randn(N, generator=g, dtype=torch.float32).to(cuda_device)
+    Y = torch.full((b, N + 2), -5.0, dtype=torch.float32, device=cuda_device)
+    _lib.check(lib.hdbo_linear_f32(X.data_ptr(), X.stride(0), b, K, W.data_ptr(), bias.data_ptr(), sc.data_ptr(), sh.data_ptr(), 1, Y.data_ptr(),
+                                   Y.stride(0), N, torch.cuda.current_stream().cuda_stream), "linear")
+    want = np.maximum((X.cpu().numpy().astype(np.float64) @ W.cpu().numpy().astype(np.float64).T + bias.cpu().numpy()) * sc.cpu().numpy()
+                      + sh.cpu().numpy(), 0.0)
+    assert np.abs(Y[:, :N].cpu().numpy() - want).max() < 1e-5 * max(1.0, np.abs(want).max())
+    assert bool((Y[:, N:] == -5.0).all())
