@@ -38,7 +38,8 @@ struct GemmParams {
 // kernel value k(r^2) and derivative dk/dr^2 for unit outputscale.  kind: 0 Matern-5/2, 1 RBF.
 __device__ __forceinline__ void kernel_eval(int kind, double r2, double& k, double& dk) {
     // branch-free sqrt / exp (fast_math.cuh) so that the unrolled epilogues interleave their independent elements; the FP64-lean
-    // forms (15 instead of 27 FP64 instructions, no conversion-pipe work): scalar FP64 and DMMA do not overlap on B200 either (MLL 5.60 -> 5.54 ms, FP64-mode pool +0.7 %)
+    // forms (15 instead of 27 FP64 instructions, no conversion-pipe work): an epilogue runs after its CTA's DMMA mainloop, so its
+    // instruction count is tile time (measured: MLL 5.60 -> 5.54 ms, FP64-mode pool +0.7 %)
     if (kind == 0) {
         const double r = sqrt_pos_cubic(fmin(fmax(r2, 1e-30), 1e30));
         const double e = exp_neg_tab(-SQRT5 * r, EXP2_TAB64);      // (64-entry table through L1)
