@@ -197,3 +197,52 @@ def test_priors_match_torch_distributions():
     assert abs(O.gamma_log_prob(x, 3.0, 6.0) - want) < 1e-12
     want = torch.distributions.LogNormal(1.2, 0.8).log_prob(x).sum()
     assert abs(O.lognormal_log_prob(x, 1.2, 0.8) - want) < 1e-12
+
+
+def test_acquisition_properties_hypothesis():
+    """EI >= 0, EI and LogEI monotone in the mean, LogEI = log EI where EI is representable, UCB monotone in both."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(mu=st.floats(-5, 5), dmu=st.floats(1e-6, 3), var=st.floats(1e-10, 25), best=st.floats(-5, 5), beta=st.floats(0, 9))
+    def check(mu, dmu, var, best, beta):
+        m = torch.tensor([mu, mu + dmu], dtype=torch.float64)
+        v = torch.tensor([var, var], dtype=torch.float64)
+        ei = O.expected_improvement(m, v, best)
+        lei = O.log_expected_improvement(m, v, best)
+        assert bool((ei >= 0).all()) and ei[1] >= ei[0] and lei[1] >= lei[0] - 1e-12
+        if ei[0] > 1e-250:
+            assert abs(float(lei[0]) - math.log(float(ei[0]))) < 1e-8 * max(1.0, abs(float(lei[0])))
+        u = O.upper_confidence_bound(m, v, beta)
+        u2 = O.upper_confidence_bound(m, 2 * v, beta)
+        assert u[1] > u[0] and bool((u2 >= u - 1e-15).all())
+
+    check()
+
+
+def test_posterior_variance_properties_hypothesis():
+    """Variance is non-negative, at most the prior variance, and ~noise-limited at the training points; invariant to a shift of
+    inputs and candidates."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(seed=st.integers(0, 10_000), kind=st.sampled_from([O.MATERN52, O.RBF]), lognoise=st.floats(-4, -1))
+    def check(seed, kind, lognoise):
+        g = torch.Generator().manual_seed(seed)
+        n, d = 30, 5
+        X = torch.rand(n, d, generator=g, dtype=torch.float64)
+        y = torch.randn(n, generator=g, dtype=torch.float64)
+        ls = 0.5 + torch.rand(d, generator=g, dtype=torch.float64)
+        os_, noise = 1.7, 10.0 ** lognoise
+        st_ = O.fit_state(X, y, ls, os_, noise, 0.1, kind)
+        Z = torch.rand(40, d, generator=g, dtype=torch.float64)
+        m, v = O.posterior(st_, Z)
+        assert bool((v >= -1e-10).all()) and bool((v <= os_ + 1e-10).all())
+        _, vt = O.posterior(st_, X)
+        assert bool((vt <= noise + 1e-8).all())            # var(f | y) at a training point is below the noise level
+        sh = torch.full((1, d), 2.5, dtype=torch.float64)
+        m2, v2 = O.posterior(O.fit_state(X + sh, y, ls, os_, noise, 0.1, kind), Z + sh)
+        torch.testing.assert_close(m, m2, rtol=0, atol=1e-8)
+        torch.testing.assert_close(v, v2, rtol=0, atol=1e-8)
+
+    check()
