@@ -11,6 +11,7 @@ import os
 from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libhdbo_b200.so"
+DEV_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libhdbo_b200_dev.so"
 
 KERNEL_MATERN52 = 0
 KERNEL_RBF = 1
@@ -29,7 +30,17 @@ class HdboGp(C.Structure):
         ("X", _dp), ("ldx", C.c_int64), ("y", _dp), ("center", _dp), ("inv_ls", _dp), ("hyp", _dp),
         ("Xs", _dp), ("xn", _dp), ("R2", _dp), ("Awork", _dp), ("L", _dp), ("Linv", _dp), ("Linvt", _dp),
         ("w", _dp), ("alpha", _dp), ("scal", _dp), ("info", _dp),
+        ("timeline", C.c_void_p),   # HOST pointer to a caller-owned HdboTimeline, or NULL
     ]
+
+
+class HdboTimeline(C.Structure):
+    """Mirror of `struct hdbo_timeline`: caller-owned CUDA events the entry points record around their phases."""
+
+    _fields_ = [("events", C.POINTER(C.c_void_p)), ("phase", C.POINTER(C.c_int32)), ("capacity", C.c_int32), ("used", C.c_int32)]
+
+
+PHASE_NAMES = ("cross", "var", "prep", "finalize", "fit_build", "fit_factor", "fit_solve", "mll_grad", "bwd")
 
 
 class HdboError(RuntimeError):
@@ -60,7 +71,6 @@ _SIGNATURES = {
                                         _dp, _dp, _dp, C.c_int64, _dp, C.c_size_t, _dp]),
     "hdbo_lbfgs_propose": (C.c_int, [C.POINTER(HdboLbfgs), _dp]),
     "hdbo_lbfgs_accept": (C.c_int, [C.POINTER(HdboLbfgs), _dp]),
-    "hdbo_i8_peak_probe": (C.c_int, [_dp, C.c_int, C.c_int, C.POINTER(C.c_double), _dp]),
     "hdbo_i8_state_flag": (C.c_void_p, [C.POINTER(HdboGp), _dp]),
     "hdbo_posterior_fwd": (C.c_int, [C.POINTER(HdboGp), _dp, C.c_int64, C.c_int64, C.c_int, _dp, _dp, C.c_int64,
                                      _dp, C.c_size_t, _dp]),
@@ -71,20 +81,27 @@ _SIGNATURES = {
     "hdbo_acq_elementwise": (C.c_int, [_dp, _dp, C.c_int64, C.c_int, C.c_double, _dp, _dp, _dp, _dp]),
     "hdbo_qei": (C.c_int, [_dp, _dp, _dp, C.c_int64, C.c_int, C.c_int64, C.c_double, C.c_double, _dp, _dp, _dp, _dp,
                            _dp]),
+    "hdbo_sobol_draw": (C.c_int, [_dp, _dp, C.c_int, C.c_int64, C.c_int64, _dp, _dp, _dp, C.c_int64, _dp]),
+    "hdbo_mvn_sample": (C.c_int, [_dp, _dp, _dp, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_double, _dp, _dp, _dp]),
     "hdbo_argmax": (C.c_int, [_dp, C.c_int64, _dp, _dp, _dp, _dp]),
     "hdbo_dgemm_nt": (C.c_int, [_dp, C.c_int64, _dp, C.c_int64, _dp, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                 C.c_double, C.c_double, C.c_int, C.c_int, _dp]),
     "hdbo_cdist": (C.c_int, [_dp, C.c_int64, C.c_int, C.c_int, _dp, _dp, _dp, _dp]),
-    "hdbo_test_math": (C.c_int, [_dp, C.c_int64, _dp, _dp, _dp]),
-    "hdbo_test_math_lean": (C.c_int, [_dp, C.c_int64, _dp, _dp, _dp]),
     "hdbo_linear_f32": (C.c_int, [_dp, C.c_int64, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, C.c_int32, _dp, C.c_int64, C.c_int32, _dp]),
     "hdbo_argmax_tokens_f32": (C.c_int, [_dp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _dp, _dp]),
-    "hdbo_profile_enable": (C.c_int, [C.c_int]),
-    "hdbo_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
-    "hdbo_fp64_peak_probe": (C.c_int, [_dp, C.c_int, C.c_int, C.POINTER(C.c_double), _dp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+# libhdbo_b200_dev.so (include/hdbo_b200_dev.h): test / measurement hooks, never loaded by the product path
+_DEV_SIGNATURES = {
+    "hdbo_test_math": (C.c_int, [_dp, C.c_int64, _dp, _dp, _dp]),
+    "hdbo_test_math_lean": (C.c_int, [_dp, C.c_int64, _dp, _dp, _dp]),
+    "hdbo_fp64_peak_probe": (C.c_int, [_dp, C.c_int, C.c_int, C.POINTER(C.c_double), _dp]),
+    "hdbo_i8_peak_probe": (C.c_int, [_dp, C.c_int, C.c_int, C.POINTER(C.c_double), _dp]),
+}
+DEV_EXPORTED_SYMBOLS = tuple(_DEV_SIGNATURES)
+_dev = None
 
 _lib = None
 
@@ -111,6 +128,26 @@ def load() -> C.CDLL:
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    return lib
+
+
+def load_dev() -> C.CDLL:
+    """Load the developer-hook library (tests and bench.py only)."""
+    global _dev
+    if _dev is not None:
+        return _dev
+    path = Path(os.environ.get("HDBO_B200_DEV_LIB", DEV_LIB_PATH))
+    if not path.exists():
+        raise HdboError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(str(path))
+    for name, (res, args) in _DEV_SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            raise HdboError(f"{path} does not export {name}; rebuild it")
+        fn.restype = res
+        fn.argtypes = args
+    _dev = lib
     return lib
 
 

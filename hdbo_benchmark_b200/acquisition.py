@@ -110,6 +110,8 @@ class AnalyticAcquisitionFunction(AcquisitionFunction):
         scale, shift = self._scale_shift()
         sign = 1.0 if self.maximize else -1.0
         param = self._std_param(scale, shift, sign)
+        if self._host_pool_supported(X, sign):
+            return self._forward_host_pool(X, param, scale, shift * sign)
         Xd, out_device, out_dtype = model._prep_X(X)
         flat = Xd.reshape(X.shape[0], X.shape[-1])
         gp = model._device_gp()
@@ -124,6 +126,41 @@ class AnalyticAcquisitionFunction(AcquisitionFunction):
         a = self._finish(a, scale, shift * sign)  # [B, b]
         a = (_logmeanexp(a, 0) if self._log else a.mean(0)) if a.shape[0] > 1 else a[0]
         return a.to(out_device, out_dtype)
+
+
+    # -- large no-grad pools that live in HOST memory (the raw-sample screening of optimize_acqf driven from CPU tensors) ----------
+    HOST_POOL_MIN = 1 << 15
+
+    def _host_pool_supported(self, X, sign) -> bool:
+        from .models import Normalize
+        if X.is_cuda or X.dtype != torch.float64 or X.shape[0] < self.HOST_POOL_MIN or sign < 0:
+            return False
+        if torch.is_grad_enabled() and X.requires_grad:
+            return False
+        model = self.model
+        it = getattr(model, "input_transform", None)
+        return not getattr(model, "_is_fully_bayesian", False) and (it is None or isinstance(it, Normalize))
+
+    def _forward_host_pool(self, X, param, scale, shift):
+        """acqf(X) for a CPU tensor X [b, 1, d]: the candidates are streamed to the device slab by slab on a copy stream while the
+        previous slab is evaluated (`DeviceGP.posterior_acq_host`), the values come back through pinned memory; the result is a CPU
+        tensor like the input (BoTorch returns values on the input's device)."""
+        model = self.model
+        gp = model._device_gp()
+        flat = X.detach().reshape(X.shape[0], X.shape[-1])
+        if flat.stride(-1) != 1:
+            flat = flat.contiguous()
+        it = getattr(model, "input_transform", None)
+        tf = None
+        if it is not None:
+            off, coef = it.offset.to(gp.device, torch.float64), it.coefficient.to(gp.device, torch.float64)
+            tf = lambda slab: slab.sub_(off).div_(coef)
+        a, _, _ = gp.posterior_acq_host(flat, self._kind, param, slab_transform=tf)
+        a = self._finish(a.reshape(1, -1), scale, shift)[0]
+        out = torch.empty(a.shape[0], dtype=torch.float64, pin_memory=True)
+        out.copy_(a, non_blocking=True)
+        torch.cuda.current_stream(gp.device).synchronize()
+        return out
 
 
 class ExpectedImprovement(AnalyticAcquisitionFunction):

@@ -25,7 +25,17 @@ static int check_gp(const hdbo_gp* gp) {
     return 0;
 }
 
-extern "C" int hdbo_version(void) { return 100; }
+extern "C" int hdbo_version(void) { return 200; }
+
+// ---- opt-in timing: CUDA events of a CALLER-OWNED timeline (hdbo_gp.timeline, may be NULL) recorded on the caller's stream around
+// the phases of an entry point.  The library keeps no state of its own: the caller creates the events and reads them back.
+static inline void tl_mark(const hdbo_gp* gp, int phase, cudaStream_t st) {
+    hdbo_timeline* tl = gp->timeline;
+    if (!tl || !tl->events || tl->used >= tl->capacity) return;
+    if (tl->phase) tl->phase[tl->used] = phase;
+    cudaEventRecord((cudaEvent_t)tl->events[tl->used++], st);
+}
+
 
 // ------------------------------------------------------------------------------------------------------------
 extern "C" int hdbo_gp_fit(const hdbo_gp* gp, int need_r2, void* stream_) {
@@ -41,6 +51,7 @@ extern "C" int hdbo_gp_fit_downdated(const hdbo_gp* gp, int need_r2, const doubl
     const int np = gp->n_pad, dp = gp->d_pad, B = gp->batch;
     const long long nn = (long long)np * np;
     TRY_CUDA(cudaMemsetAsync(gp->info, 0, sizeof(int32_t) * B, st));
+    tl_mark(gp, HDBO_PHASE_FIT_BUILD, st);
     TRY_CUDA(launch_scale_inputs(gp->X, (int)gp->ldx, 0, gp->n, gp->d, gp->center, gp->inv_ls, gp->d, gp->Xs, dp, np,
                                  (long long)np * dp, gp->xn, np, B, st));
     SymBuildParams sb{};
@@ -55,55 +66,20 @@ extern "C" int hdbo_gp_fit_downdated(const hdbo_gp* gp, int need_r2, const doubl
         g.krange = KR_FULL; g.lower_only = 1; g.alpha = -1.0; g.beta = 1.0;
         TRY_CUDA(launch_gemm_nt(g, 1, st));
     }
+    tl_mark(gp, HDBO_PHASE_FIT_BUILD, st);
+    tl_mark(gp, HDBO_PHASE_FIT_FACTOR, st);
     TRY_CUDA(chol_inverse(gp->Awork, gp->L, gp->Linv, gp->Linvt, np, nn, np / 128, gp->n, gp->info, B, st));
+    tl_mark(gp, HDBO_PHASE_FIT_FACTOR, st);
+    tl_mark(gp, HDBO_PHASE_FIT_SOLVE, st);
     // w = Linv (y - m);  alpha = Linv^T w
     TRY_CUDA(launch_tri_matvec(gp->Linv, np, nn, np, 0, nullptr, 0, gp->y, gp->n, gp->hyp, gp->w, np, B, st));
     TRY_CUDA(launch_tri_matvec(gp->Linvt, np, nn, np, 1, gp->w, np, nullptr, gp->n, gp->hyp, gp->alpha, np, B, st));
     TRY_CUDA(launch_fit_scalars(gp->L, np, nn, gp->w, gp->alpha, np, gp->n, np, gp->scal, B, st));
+    tl_mark(gp, HDBO_PHASE_FIT_SOLVE, st);
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// ---- opt-in profiling: CUDA events around the GEMM phases of the posterior, recorded on the caller's stream ----
-namespace {
-constexpr int PROF_CLASSES = 2;   // 0 = cross-kernel build (k_cross), 1 = variance contraction (k_var / k_var_i8)
-struct Prof {
-    bool on = false;
-    std::vector<cudaEvent_t> ev[PROF_CLASSES];   // pairs: start, stop
-    size_t used[PROF_CLASSES] = {0, 0};
-} g_prof;
-void prof_mark(int cls, cudaStream_t st) {
-    if (!g_prof.on) return;
-    if (g_prof.used[cls] == g_prof.ev[cls].size()) {
-        cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return;
-        g_prof.ev[cls].push_back(e);
-    }
-    cudaEventRecord(g_prof.ev[cls][g_prof.used[cls]++], st);
-}
-}  // namespace
-
-extern "C" int hdbo_profile_enable(int on) {
-    g_prof.on = on != 0;
-    for (int c = 0; c < PROF_CLASSES; c++) g_prof.used[c] = 0;
-    return 0;
-}
-
-extern "C" int hdbo_profile_collect(double* ms_by_class, int64_t* launches_by_class) {
-    for (int c = 0; c < PROF_CLASSES; c++) {
-        double tot = 0.0; int64_t cnt = 0;
-        for (size_t i = 0; i + 1 < g_prof.used[c]; i += 2) {
-            float ms = 0.f;
-            if (cudaEventSynchronize(g_prof.ev[c][i + 1]) != cudaSuccess) return (int)cudaGetLastError();
-            if (cudaEventElapsedTime(&ms, g_prof.ev[c][i], g_prof.ev[c][i + 1]) != cudaSuccess) return (int)cudaGetLastError();
-            tot += ms; cnt++;
-        }
-        if (ms_by_class) ms_by_class[c] = tot;
-        if (launches_by_class) launches_by_class[c] = cnt;
-        g_prof.used[c] = 0;
-    }
-    return 0;
-}
-
 namespace {
 struct PostWs {
     double *Zs, *zn, *Kstar, *meanpart, *varpart, *DK, *V, *T, *XsT;
@@ -165,16 +141,18 @@ cudaError_t posterior_chunk(const hdbo_gp* gp, const PostWs& w, int64_t rows_all
     if (i8) {
         // whole chunk on the int8 tensor cores: candidate digit images -> K* digit images + mean partials -> variance partials
         int8_t* Kimg = reinterpret_cast<int8_t*>(w.Kstar);   // tile images: 6 bytes per element of the 8-byte K* slab
+        tl_mark(gp, HDBO_PHASE_PREP, st);
         e = launch_slice_rows(128, Z, ldz, (int)mc, rp, gp->d, gp->center, gp->inv_ls, w.Zdig, w.zscale, w.zn, rows_alloc, B, st);
+        tl_mark(gp, HDBO_PHASE_PREP, st);
         if (e != cudaSuccess) return e;
-        prof_mark(0, st);
+        tl_mark(gp, HDBO_PHASE_CROSS, st);
         e = launch_cross_i8(gp->kind, w.Zdig, i8->Xdig, w.zscale, i8->xscale, w.zn, gp->xn, gp->alpha, gp->hyp, Kimg, w.meanpart,
                             (int)mc, gp->n, rp, (int)rows_alloc, np, gp->d, B, i8->flag, st);
-        prof_mark(0, st);
+        tl_mark(gp, HDBO_PHASE_CROSS, st);
         if (e != cudaSuccess) return e;
-        prof_mark(1, st);
+        tl_mark(gp, HDBO_PHASE_VAR, st);
         e = launch_var_i8(Kimg, rp, (int)rows_alloc, i8->digits, i8->scale, gp->hyp, np, w.varpart, B, i8->flag, st);
-        prof_mark(1, st);
+        tl_mark(gp, HDBO_PHASE_VAR, st);
         return e;
     }
     CrossParams c{};
@@ -184,12 +162,14 @@ cudaError_t posterior_chunk(const hdbo_gp* gp, const PostWs& w, int64_t rows_all
     c.bsZ = (long long)rows_alloc * dp; c.bsX = (long long)np * dp; c.bszn = rows_alloc; c.bsxn = np; c.bsalpha = np;
     c.bsK = (long long)rows_alloc * np; c.bsmp = 2LL * nt * rows_alloc;
     c.m = (int)mc; c.n = gp->n; c.mtiles = mt; c.ntiles = nt; c.kblocks = dp / BK; c.kind = gp->kind;
+    tl_mark(gp, HDBO_PHASE_PREP, st);
     e = launch_scale_inputs(Z, (int)ldz, 0, (int)mc, gp->d, gp->center, gp->inv_ls, gp->d, w.Zs, dp, rp,
                             (long long)rows_alloc * dp, w.zn, rows_alloc, B, st);
+    tl_mark(gp, HDBO_PHASE_PREP, st);
     if (e != cudaSuccess) return e;
-    prof_mark(0, st);
+    tl_mark(gp, HDBO_PHASE_CROSS, st);
     e = launch_cross(c, B, st);
-    prof_mark(0, st);
+    tl_mark(gp, HDBO_PHASE_CROSS, st);
     if (e != cudaSuccess) return e;
     if (var_tiles) *var_tiles = nt;
     if (keep && var_tiles && (long long)mt * nt * B < 148) {
@@ -199,10 +179,10 @@ cudaError_t posterior_chunk(const hdbo_gp* gp, const PostWs& w, int64_t rows_all
         g.A = w.Kstar; g.B = gp->Linv; g.C = w.V; g.Ct = nullptr;
         g.lda = g.ldb = g.ldc = np; g.bsA = (long long)rows_alloc * np; g.bsB = (long long)np * np; g.bsC = (long long)rows_alloc * np;
         g.mtiles = mt; g.ntiles = nt; g.kblocks = np / BK; g.krange = KR_LE_N; g.lower_only = 0; g.alpha = 1.0; g.beta = 0.0;
-        prof_mark(1, st);
+        tl_mark(gp, HDBO_PHASE_VAR, st);
         e = launch_gemm_nt(g, B, st);
         if (e == cudaSuccess) e = launch_row_sumsq(w.V, np, (long long)rows_alloc * np, rp, np, w.varpart, 2LL * nt * rows_alloc, B, st);
-        prof_mark(1, st);
+        tl_mark(gp, HDBO_PHASE_VAR, st);
         *var_tiles = 1;
         return e;
     }
@@ -211,9 +191,9 @@ cudaError_t posterior_chunk(const hdbo_gp* gp, const PostWs& w, int64_t rows_all
     v.ldk = np; v.ldl = np; v.ldv = np;
     v.bsK = (long long)rows_alloc * np; v.bsL = (long long)np * np; v.bsV = (long long)rows_alloc * np;
     v.bsvp = 2LL * nt * rows_alloc; v.mtiles = mt; v.ntiles = nt;
-    prof_mark(1, st);
+    tl_mark(gp, HDBO_PHASE_VAR, st);
     e = launch_var(v, B, st);
-    prof_mark(1, st);
+    tl_mark(gp, HDBO_PHASE_VAR, st);
     return e;
 }
 }  // namespace
@@ -251,9 +231,11 @@ static int posterior_acq_impl(const hdbo_gp* gp, const I8State* i8, const double
     for (int64_t off = 0; off < m; off += rows) {
         const int64_t mc = (m - off < rows) ? (m - off) : rows;
         TRY_CUDA(posterior_chunk(gp, w, rows, Z + off * ldz, ldz, mc, 0, st, i8));
+        tl_mark(gp, HDBO_PHASE_FINALIZE, st);
         TRY_CUDA(launch_finalize_acq(w.meanpart, w.varpart, (long long)nt * rows, i8 ? 2 * nt : nt, i8 ? 2 * nt : nt, (int)rup(mc, 128), (int)mc, gp->hyp,
                                      observation_noise, acq_kind, acq_param, mean ? mean + off : nullptr,
                                      var ? var + off : nullptr, (acq && acq_kind >= 0) ? acq + off : nullptr, bso, B, st));
+        tl_mark(gp, HDBO_PHASE_FINALIZE, st);
     }
     return 0;
 }
@@ -327,25 +309,12 @@ extern "C" int hdbo_lbfgs_accept(const hdbo_lbfgs* s, void* stream_) {
     return 0;
 }
 
-extern "C" int hdbo_i8_peak_probe(int32_t* flag, int iters, int sms, double* ops_out, void* stream_) {
-    if (!flag || iters <= 0 || sms <= 0) return -1;
-    TRY_CUDA(launch_i8_peak(iters, sms, flag, ops_out, (cudaStream_t)stream_));
-    return 0;
-}
-
 extern "C" int hdbo_acq_elementwise(const double* mean, const double* var, int64_t m, int acq_kind, double acq_param,
                                     double* acq, double* dmean, double* dvar, void* stream_) {
     if (!mean || !var) return -1;
     if (m < 0) return -3;
     if (acq_kind < 0 || acq_kind > 4) return -4;
     TRY_CUDA(launch_acq_elem(mean, var, m, acq_kind, acq_param, acq, dmean, dvar, (cudaStream_t)stream_));
-    return 0;
-}
-
-extern "C" int hdbo_test_math(const double* x, int64_t n, double* sqrt_out, double* exp_out, void* stream_) {
-    if (!x) return -1;
-    if (n < 0) return -2;
-    TRY_CUDA(launch_test_math(x, n, sqrt_out, exp_out, (cudaStream_t)stream_));
     return 0;
 }
 
@@ -367,13 +336,6 @@ extern "C" int hdbo_argmax_tokens_f32(const float* logits, int64_t ld, int32_t b
     if (L <= 0 || A <= 0 || ld < (int64_t)L * A) return -2;
     if (!tokens) return -6;
     TRY_CUDA(launch_argmax_tokens_f32(logits, ld, b, L, A, tokens, (cudaStream_t)stream_));
-    return 0;
-}
-
-extern "C" int hdbo_test_math_lean(const double* x, int64_t n, double* sqrt_out, double* exp_out, void* stream_) {
-    if (!x) return -1;
-    if (n < 0) return -2;
-    TRY_CUDA(launch_test_math_lean(x, n, sqrt_out, exp_out, (cudaStream_t)stream_));
     return 0;
 }
 
@@ -409,7 +371,9 @@ extern "C" int hdbo_mll_grad(const hdbo_gp* gp, double* Kinv, double* G, double*
     if (!XsT) return -4;
     if (!part) return -5;
     if (!grad) return -6;
+    tl_mark(gp, HDBO_PHASE_MLL_GRAD, (cudaStream_t)stream_);
     TRY_CUDA(mll_grad(gp, Kinv, G, XsT, part, grad, (cudaStream_t)stream_));
+    tl_mark(gp, HDBO_PHASE_MLL_GRAD, (cudaStream_t)stream_);
     return 0;
 }
 
@@ -463,7 +427,9 @@ extern "C" int hdbo_posterior_bwd(const hdbo_gp* gp, int64_t m, int q, const dou
     if (!workspace || carve(gp, rows, 1, nullptr).bytes > workspace_bytes) return -12;
     PostWs w = carve(gp, rows, 1, workspace);
     BwdBuffers b{w.Zs, w.Kstar, w.DK, w.V, w.T, w.XsT, w.meanpart};
+    tl_mark(gp, HDBO_PHASE_BWD, (cudaStream_t)stream_);
     TRY_CUDA(posterior_bwd(gp, b, rows, m, q, gmean, gvar, gSigma, bsg, bsS, dZ, (int)lddz, bsdz, (cudaStream_t)stream_));
+    tl_mark(gp, HDBO_PHASE_BWD, (cudaStream_t)stream_);
     return 0;
 }
 
@@ -481,6 +447,31 @@ extern "C" int hdbo_qei(const double* mean, const double* Sigma, const double* b
     return 0;
 }
 
+extern "C" int hdbo_sobol_draw(const int32_t* state_t, const int32_t* shift, int dim, int64_t first, int64_t m, const double* lower,
+                               const double* range, double* out, int64_t ld, void* stream_) {
+    if (!state_t) return -1;
+    if (!shift) return -2;
+    if (dim <= 0) return -3;
+    if (first < 0 || first + m > (1LL << 30)) return -4;
+    if (m < 0) return -5;
+    if (!out || ld < dim) return -8;
+    TRY_CUDA(launch_sobol_draw(state_t, shift, dim, first, m, lower, range, out, ld, (cudaStream_t)stream_));
+    return 0;
+}
+
+extern "C" int hdbo_mvn_sample(const double* mean, const double* Sigma, const double* z, int64_t R, int q, int64_t S, int z_per_r,
+                               double jitter, double* out, int32_t* info, void* stream_) {
+    if (!mean) return -1;
+    if (!Sigma) return -2;
+    if (!z) return -3;
+    if (R < 0) return -4;
+    if (q < 1 || q > 8) return -5;
+    if (S < 0) return -6;
+    if (!out) return -9;
+    TRY_CUDA(launch_mvn_sample(mean, Sigma, z, R, q, S, z_per_r, jitter, out, info, (cudaStream_t)stream_));
+    return 0;
+}
+
 extern "C" int hdbo_cdist(const double* X, int64_t ldx, int n, int d, double* Xs, double* xn, double* D_pad, void* stream_) {
     if (!X || ldx < d) return -1;
     if (n <= 0 || d <= 0) return -3;
@@ -494,30 +485,5 @@ extern "C" int hdbo_cdist(const double* X, int64_t ldx, int n, int d, double* Xs
     g.lower_only = 0; g.alpha = 1.0; g.beta = 0.0;
     TRY_CUDA(launch_gemm_nt(g, 1, st));
     TRY_CUDA(launch_cdist_finish(D_pad, np, xn, np, st));
-    return 0;
-}
-
-// ---- FP64 tensor (DMMA.8x8x4) issue-ceiling probe: the denominator of every FP64 roofline fraction ----
-__global__ void __launch_bounds__(512) k_dmma_peak(double* out, int iters) {
-    double a = threadIdx.x * 1e-9, b = threadIdx.x * 2e-9;
-    double c[8][2];
-#pragma unroll
-    for (int j = 0; j < 8; j++) { c[j][0] = 0; c[j][1] = 0; }
-    for (int i = 0; i < iters; i++) {
-#pragma unroll
-        for (int j = 0; j < 8; j++) dmma884(c[j][0], c[j][1], a, b);
-    }
-    double s = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) s += c[j][0] + c[j][1];
-    if (s == 12345.678) out[0] = s;
-}
-
-extern "C" int hdbo_fp64_peak_probe(double* scratch, int iters, int sms, double* flops_out, void* stream_) {
-    if (!scratch) return -1;
-    if (iters <= 0 || sms <= 0) return -2;
-    k_dmma_peak<<<sms, 512, 0, (cudaStream_t)stream_>>>(scratch, iters);
-    TRY_CUDA(cudaGetLastError());
-    if (flops_out) *flops_out = 2.0 * 256 * 8 * (double)iters * 16 * sms;   /* host pointer */
     return 0;
 }

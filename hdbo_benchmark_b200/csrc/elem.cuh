@@ -79,8 +79,9 @@ cudaError_t launch_finalize_acq(const double* meanpart, const double* varpart, l
                                 cudaStream_t stream);
 cudaError_t launch_acq_elem(const double* mean, const double* var, long long m, int acq_kind, double acq_param, double* acq,
                             double* dmean, double* dvar, cudaStream_t stream);
-cudaError_t launch_test_math(const double* x, long long n, double* s, double* e, cudaStream_t st);
-cudaError_t launch_test_math_lean(const double* x, long long n, double* s, double* e, cudaStream_t st);
 cudaError_t launch_argmax(const double* v, long long m, void* work, double* out_val, long long* out_idx, cudaStream_t stream);
+
+cudaError_t launch_sobol_draw(const int* state_t, const int* shift, int dim, long long k0, long long m, const double* lower,
+                              const double* range, double* out, long long ld, cudaStream_t stream);
 
 }  // namespace hdbo

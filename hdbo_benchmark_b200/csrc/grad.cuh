@@ -23,4 +23,7 @@ cudaError_t launch_qei(const double* mean, const double* Sigma, const double* ba
                        double best_f, double jitter, double* value, double* gmean, double* gSigma, int32_t* info,
                        cudaStream_t st);
 
+cudaError_t launch_mvn_sample(const double* mean, const double* Sigma, const double* z, long long R, int q, long long S,
+                              int z_per_r, double jitter, double* out, int32_t* info, cudaStream_t st);
+
 }  // namespace hdbo

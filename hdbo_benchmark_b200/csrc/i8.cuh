@@ -50,6 +50,5 @@ cudaError_t launch_cross_i8(int kind, const int8_t* Zimg, const int8_t* Ximg, co
                             int rows_pad, int rows_alloc, int n_pad, int d, int batch, int* flag, cudaStream_t st);
 cudaError_t launch_var_i8(const int8_t* Aimg, int rows_pad, int rows_alloc, const int8_t* Bimg, const double* colscale, const double* hyp,
                           int n_pad, double* varpart, int batch, int* flag, cudaStream_t st);
-cudaError_t launch_i8_peak(int iters, int sms, int* flag, double* ops_out, cudaStream_t st);
 
 }  // namespace hdbo

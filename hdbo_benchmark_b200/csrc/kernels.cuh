@@ -6,7 +6,21 @@
 #include "../../include/hdbo_b200.h"
 #include "fast_math.cuh"
 
+#include <atomic>
+
 namespace hdbo {
+
+// The > 48 KB dynamic-shared-memory opt-in (cudaFuncSetAttribute) is a PER-DEVICE function attribute: a process that uses a second
+// GPU after the first must set it again there.  One bit per device ordinal, checked against the calling thread's current device.
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> done{0};
+    bool pending(int& dev) {
+        dev = 0;
+        cudaGetDevice(&dev);
+        return dev >= 64 || !((done.load(std::memory_order_acquire) >> dev) & 1ull);
+    }
+    void mark(int dev) { if (dev < 64) done.fetch_or(1ull << dev, std::memory_order_release); }
+};
 
 constexpr double SQRT5 = 2.23606797749978969640917366873128;
 constexpr double INV_SQRT_2 = 0.70710678118654752440084436210485;

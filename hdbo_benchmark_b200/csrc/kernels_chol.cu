@@ -27,11 +27,11 @@ static cudaError_t launch_leaf(double* Awork, double* L, double* Linv, double* L
                                int32_t* info, int batch, cudaStream_t stream) {
     // A warp-specialised, look-ahead ("pipelined") variant of the leaf was built and measured slower (82-104 us vs 72 us):
     // with one CTA per SM and each role running its own long unrolled code path the warps thrash the instruction cache.
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once; int attr_dev;
+    if (attr_once.pending(attr_dev)) {
         cudaError_t e = cudaFuncSetAttribute(k_leaf_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_once.mark(attr_dev);
     }
     k_leaf_blocked<<<batch, LF_THREADS, LF_SMEM_BYTES, stream>>>(Awork, L, Linv, Linvt, ld, bs, tile, info);
     return cudaGetLastError();

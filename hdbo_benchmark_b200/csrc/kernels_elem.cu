@@ -121,16 +121,38 @@ cudaError_t launch_fit_scalars(const double* L, int ld, long long bsL, const dou
 // ------------------------------------------------------------------------------------------------------------
 // Per candidate: mean = m0 + sum_t meanpart[t][i]; var = outputscale - sum_t varpart[t][i] (+ noise);
 // acquisition value (A5) and, if requested, d acq / d mean and d acq / d var.
-__global__ void k_finalize_acq(const double* __restrict__ meanpart, const double* __restrict__ varpart, long long bsp,
-                               int ntiles, int ntiles_var, int rows_pad, int m, const double* __restrict__ hyp, int observation_noise,
-                               int acq_kind, double acq_param, double* __restrict__ mean_out,
-                               double* __restrict__ var_out, double* __restrict__ acq_out, long long bso) {
+// HBM-bound (16 B x ntiles per candidate): 64 candidates x 4 tile slices per CTA so that a 18 944-candidate chunk fills the SMs
+// (296 CTAs) and every thread keeps 4 independent loads in flight; the 4 slice sums are combined through shared memory in a fixed
+// order (deterministic, independent of the chunking).
+constexpr int FIN_CAND = 64, FIN_SLICES = 4;
+__global__ void __launch_bounds__(FIN_CAND * FIN_SLICES)
+k_finalize_acq(const double* __restrict__ meanpart, const double* __restrict__ varpart, long long bsp,
+               int ntiles, int ntiles_var, int rows_pad, int m, const double* __restrict__ hyp, int observation_noise,
+               int acq_kind, double acq_param, double* __restrict__ mean_out,
+               double* __restrict__ var_out, double* __restrict__ acq_out, long long bso) {
+    __shared__ double red[2][FIN_SLICES][FIN_CAND];
     const int b = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    double sm = 0.0, sv = 0.0;
-    for (int t = 0; t < ntiles; t++) sm += meanpart[b * 2 * bsp + (size_t)t * rows_pad + i];
-    for (int t = 0; t < ntiles_var; t++) sv += varpart[b * 2 * bsp + (size_t)t * rows_pad + i];
+    const int c = threadIdx.x % FIN_CAND, sl = threadIdx.x / FIN_CAND;
+    const int i = blockIdx.x * FIN_CAND + c;
+    const bool live = i < m;
+    auto slice_sum = [&](const double* part, int nt) {
+        const int per = (nt + FIN_SLICES - 1) / FIN_SLICES, t0 = sl * per, t1 = min(nt, t0 + per);
+        const double* p = part + b * 2 * bsp + i;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int t = t0;
+        for (; t + 3 < t1; t += 4) {
+            s0 += p[(size_t)t * rows_pad]; s1 += p[(size_t)(t + 1) * rows_pad];
+            s2 += p[(size_t)(t + 2) * rows_pad]; s3 += p[(size_t)(t + 3) * rows_pad];
+        }
+        for (; t < t1; t++) s0 += p[(size_t)t * rows_pad];
+        return (s0 + s1) + (s2 + s3);
+    };
+    red[0][sl][c] = live ? slice_sum(meanpart, ntiles) : 0.0;
+    red[1][sl][c] = live ? slice_sum(varpart, ntiles_var) : 0.0;
+    __syncthreads();
+    if (sl != 0 || !live) return;
+    const double sm = (red[0][0][c] + red[0][1][c]) + (red[0][2][c] + red[0][3][c]);
+    const double sv = (red[1][0][c] + red[1][1][c]) + (red[1][2][c] + red[1][3][c]);
     const double os = hyp[b * 4 + 0], noise = hyp[b * 4 + 1], m0 = hyp[b * 4 + 2];
     const double mean = m0 + sm;
     double var = os - sv;
@@ -148,9 +170,9 @@ cudaError_t launch_finalize_acq(const double* meanpart, const double* varpart, l
                                 int m, const double* hyp, int observation_noise, int acq_kind, double acq_param,
                                 double* mean_out, double* var_out, double* acq_out, long long bso, int batch,
                                 cudaStream_t stream) {
-    dim3 grid((m + 255) / 256, batch);
-    k_finalize_acq<<<grid, 256, 0, stream>>>(meanpart, varpart, bsp, ntiles, ntiles_var, rows_pad, m, hyp, observation_noise,
-                                            acq_kind, acq_param, mean_out, var_out, acq_out, bso);
+    dim3 grid((m + FIN_CAND - 1) / FIN_CAND, batch);
+    k_finalize_acq<<<grid, FIN_CAND * FIN_SLICES, 0, stream>>>(meanpart, varpart, bsp, ntiles, ntiles_var, rows_pad, m, hyp,
+                                                              observation_noise, acq_kind, acq_param, mean_out, var_out, acq_out, bso);
     return cudaGetLastError();
 }
 
@@ -257,31 +279,47 @@ cudaError_t launch_argmax(const double* v, long long m, void* work, double* out_
     return cudaGetLastError();
 }
 
-// test hook: the branch-free sqrt / exp of fast_math.cuh evaluated on arrays (tests compare with the library functions)
-__global__ void k_test_math(const double* __restrict__ x, long long n, double* __restrict__ s, double* __restrict__ e) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (s) s[i] = sqrt_pos(fmin(fmax(x[i], 1e-30), 1e30));
-    if (e) e[i] = exp_nonpos(-fabs(x[i]));
+// ------------------------------------------------------------------------------------------------------------
+// Scrambled-Sobol raw samples on the device (the pool `gen_batch_initial_conditions` scores), bit-identical to
+// torch.quasirandom.SobolEngine: point k = shift ^ XOR_{b in bits(gray(k))} state[b], value = quasi 2^-30, then lower + range * u
+// with separate roundings (what `lower + rng * u` does on the host).  One thread per dimension and run of 64 consecutive points:
+// the start of a run costs popcount(gray) loads, every further point ONE xor with state[ctz(k)] (bits 0..5 live in registers);
+// consecutive threads = consecutive dimensions, so every store instruction writes whole 128-byte lines.  HBM-bound: 8 B/element.
+// torch quirk kept: when a draw starts at point 0, that point is rounded to FP32 before the cast (SobolEngine._first_point).
+constexpr int SOBOL_RUN = 64;
+__global__ void __launch_bounds__(128) k_sobol_draw(const int* __restrict__ state_t /* [30][dim] */, const int* __restrict__ shift,
+                                                    int dim, long long k0, long long m, const double* __restrict__ lower,
+                                                    const double* __restrict__ range, double* __restrict__ out, long long ld) {
+    const int j = blockIdx.y * blockDim.x + threadIdx.x;
+    if (j >= dim) return;
+    const long long run0 = (k0 / SOBOL_RUN + blockIdx.x) * SOBOL_RUN;       // absolute index of this run's first point (aligned)
+    int low[6];
+#pragma unroll
+    for (int b = 0; b < 6; b++) low[b] = state_t[(size_t)b * dim + j];
+    unsigned long long g = (unsigned long long)run0 ^ ((unsigned long long)run0 >> 1);
+    int quasi = shift[j];
+    for (int b = 0; g != 0 && b < 30; b++, g >>= 1)
+        if (g & 1ull) quasi ^= state_t[(size_t)b * dim + j];
+    const double lo = lower ? lower[j] : 0.0, rg = range ? range[j] : 1.0;
+#pragma unroll
+    for (int i = 0; i < SOBOL_RUN; i++) {
+        const long long k = run0 + i;
+        // gray(k) ^ gray(k-1) = bit ctz(k) = ctz(i) inside an aligned run: a compile-time register index after the full unroll
+        if (i > 0) quasi ^= low[(i & 1) ? 0 : (i & 2) ? 1 : (i & 4) ? 2 : (i & 8) ? 3 : (i & 16) ? 4 : 5];
+        if (k >= k0 && k < k0 + m) {
+            double u = (double)quasi * 9.313225746154785e-10;                 // 2^-30, exact
+            if (k == 0) u = (double)((float)quasi * 9.313225746154785e-10f);
+            out[(size_t)(k - k0) * ld + j] = __dadd_rn(lo, __dmul_rn(rg, u));
+        }
+    }
 }
-// the FP64-lean forms of the int8 cross kernel: sqrt (clamped to [1e-30, 1e300]) and exp(-|x|) with |x| clamped to 700
-__global__ void k_test_math_lean(const double* __restrict__ x, long long n, double* __restrict__ s, double* __restrict__ e) {
-    __shared__ double tab[64];
-    if (threadIdx.x < 64) tab[threadIdx.x] = EXP2_TAB64[threadIdx.x];
-    __syncthreads();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (s) s[i] = sqrt_pos_cubic(fmin(fmax(x[i], 1e-30), 1e300));
-    if (e) e[i] = exp_neg_tab_inrange(-fmin(fabs(x[i]), 700.0) - 0.0, tab);
-}
-cudaError_t launch_test_math_lean(const double* x, long long n, double* s, double* e, cudaStream_t st) {
-    if (n == 0) return cudaSuccess;
-    k_test_math_lean<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n, s, e);
-    return cudaGetLastError();
-}
-cudaError_t launch_test_math(const double* x, long long n, double* s, double* e, cudaStream_t st) {
-    if (n == 0) return cudaSuccess;
-    k_test_math<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n, s, e);
+
+cudaError_t launch_sobol_draw(const int* state_t, const int* shift, int dim, long long k0, long long m, const double* lower,
+                              const double* range, double* out, long long ld, cudaStream_t stream) {
+    if (m == 0) return cudaSuccess;
+    const long long runs = (k0 + m - 1) / SOBOL_RUN - k0 / SOBOL_RUN + 1;
+    dim3 grid((unsigned)runs, (dim + 127) / 128);
+    k_sobol_draw<<<grid, 128, 0, stream>>>(state_t, shift, dim, k0, m, lower, range, out, ld);
     return cudaGetLastError();
 }
 

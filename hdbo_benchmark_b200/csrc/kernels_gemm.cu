@@ -77,11 +77,11 @@ __global__ void __launch_bounds__(G::THREADS) k_gemm_nt(GemmParams p) {
 
 template <class G>
 static cudaError_t launch_gemm_cfg(GemmParams p, int batch, cudaStream_t stream) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once; int attr_dev;
+    if (attr_once.pending(attr_dev)) {
         cudaError_t e = cudaFuncSetAttribute(k_gemm_nt<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_once.mark(attr_dev);
     }
     p.mtiles *= 128 / G::TM;
     p.ntiles *= 128 / G::TN;
@@ -159,12 +159,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cross(CrossParams p) {
 }
 
 cudaError_t launch_cross(const CrossParams& p, int batch, cudaStream_t stream) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once; int attr_dev;
+    if (attr_once.pending(attr_dev)) {
         cudaError_t e = cudaFuncSetAttribute(k_cross<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cross<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_once.mark(attr_dev);
     }
     dim3 grid(p.mtiles, p.ntiles, batch);
     if (p.kind == 0) k_cross<0><<<grid, NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
@@ -221,11 +221,11 @@ __global__ void __launch_bounds__(G::THREADS) k_sym_build(SymBuildParams p) {
 
 template <class G>
 static cudaError_t launch_sym_build_cfg(SymBuildParams p, int batch, cudaStream_t stream) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once; int attr_dev;
+    if (attr_once.pending(attr_dev)) {
         cudaError_t e = cudaFuncSetAttribute(k_sym_build<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_once.mark(attr_dev);
     }
     p.tiles *= 128 / G::TM;
     dim3 grid(p.tiles * (p.tiles + 1) / 2, 1, batch);
@@ -274,11 +274,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_var(VarParams p) {
 }
 
 cudaError_t launch_var(const VarParams& p, int batch, cudaStream_t stream) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once; int attr_dev;
+    if (attr_once.pending(attr_dev)) {
         cudaError_t e = cudaFuncSetAttribute(k_var, cudaFuncAttributeMaxDynamicSharedMemorySize, GVAR::SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_once.mark(attr_dev);
     }
     dim3 grid(p.mtiles, p.ntiles, batch);
     k_var<<<grid, NTHREADS, GVAR::SMEM_BYTES, stream>>>(p);

@@ -207,10 +207,10 @@ cudaError_t mll_grad(const hdbo_gp* gp, double* Kinv, double* G, double* XsT, do
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if ((e = launch_transpose(gp->Xs, dp, (long long)np * dp, np, dp, XsT, np, (long long)dpt * np, dpt, B, st)) != cudaSuccess)
         return e;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once; int attr_dev;
+    if (attr_once.pending(attr_dev)) {
         if ((e = cudaFuncSetAttribute(k_gxa, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES)) != cudaSuccess) return e;
-        attr_done = true;
+        attr_once.mark(attr_dev);
     }
     GxaParams x{};
     x.G = G; x.XsT = XsT; x.Xs = gp->Xs; x.rowpart = rowpart; x.colpart = colpart;
@@ -445,10 +445,10 @@ cudaError_t posterior_bwd(const hdbo_gp* gp, const BwdBuffers& w, int64_t rows_a
         }
         return cudaSuccess;
     }
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once; int attr_dev;
+    if (attr_once.pending(attr_dev)) {
         if ((e = cudaFuncSetAttribute(k_dz, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES)) != cudaSuccess) return e;
-        attr_done = true;
+        attr_once.mark(attr_dev);
     }
     DzParams p{};
     p.Cm = w.Kstar; p.XsT = w.XsT; p.Zs = w.Zs; p.csum = w.csum; p.inv_ls = gp->inv_ls; p.dZ = dZ;

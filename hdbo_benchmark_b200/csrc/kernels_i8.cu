@@ -15,6 +15,7 @@
 // drained it.  SASS: UTCIMMA / UBLKCP / LDTM / UTCBAR.
 #include "kernels.cuh"
 #include "i8.cuh"
+#include "tc05.cuh"
 
 namespace hdbo {
 
@@ -122,69 +123,6 @@ static_assert(I8_S * VT_N + 2 * I8_S * 8 <= 512, "weight groups + double-buffere
 #define HDBO_VAR_A_TMEM false   // measured: A planes via tcgen05.cp + TS-mode MMAs are exact but 20 % SLOWER (31.6 -> 38.1 ms per 2^18 pool)
 #endif
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// bounded wait: a protocol bug becomes a NaN result (flag) instead of a hung GPU
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* flag) {
-    for (long i = 0; i < 20000000L; i++) {
-        uint32_t ok;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (ok) return true;
-    }
-    atomicExch(flag, 1);
-    return false;
-}
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-// K-major operand with 32-byte rows, SWIZZLE_32B (layout type 6): 8-row groups 256 B apart (SBO = 16 x 16 B), LBO = 1,
-// descriptor version 1 (sm_100)
-__device__ __forceinline__ uint64_t make_desc_sw32(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)16 << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)6 << 61;
-    return d;
-}
-// M = 128, N = n, K-major 8-bit operands (A signed or unsigned, B signed), D = S32
-__device__ __forceinline__ constexpr uint32_t idesc_i8(int n, bool a_signed) {
-    return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(VT_M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_i8(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// A operand from TMEM (TS mode): no shared-memory read for A at MMA time
-__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
-                 ::"r"(tmem_c), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// shared memory -> TMEM: 128 rows x 256 bits (one digit plane of one k-block = 8 TMEM columns)
-__device__ __forceinline__ void utccp_128x256b(uint32_t tmem_dst, uint64_t sdesc) {
-    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_dst), "l"(sdesc) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ long long mad_wide(int a, int b, long long c) {     // a * b + c with a 64-bit addend: one IMAD.WIDE
-    long long d;
-    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -299,13 +237,10 @@ __device__ __forceinline__ void i8_pipe_release_tmem(const I8Pipe& pp) {
     if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pp.tmem_empty) : "memory");
 }
 
-static int i8_sm_count() {
-    static int sms = [] {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        return n;
-    }();
-    return sms;
+static int i8_sm_count() {   // SM count of the calling thread's CURRENT device (a process may drive several GPUs)
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    return n;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -474,12 +409,12 @@ __global__ void __launch_bounds__(CE_THREADS, 1) k_cross_i8(CrossI8Params p) {  
 cudaError_t launch_cross_i8(int kind, const int8_t* Zimg, const int8_t* Ximg, const double* zscale, const double* xscale, const double* zn,
                             const double* xn, const double* alpha, const double* hyp, int8_t* Kimg, double* meanpart, int m, int n,
                             int rows_pad, int rows_alloc, int n_pad, int d, int batch, int* flag, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once; int attr_dev;
+    if (attr_once.pending(attr_dev)) {
         cudaError_t e = cudaFuncSetAttribute(k_cross_i8<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CE_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cross_i8<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CE_SMEM);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_once.mark(attr_dev);
     }
     const int per_gp = (rows_pad / VT_M) * (n_pad / VT_N), ntiles = per_gp * batch;
     CrossI8Params p{Zimg, Ximg, zscale, xscale, zn, xn, alpha, hyp, Kimg, meanpart, m, n, rows_pad, n_pad / VT_N, ntiles, (d + 31) / 32,
@@ -580,11 +515,11 @@ __global__ void __launch_bounds__(320, 1) k_var_i8(VarI8Params p) {
 // Aimg: K* digit images for rows_pad / 128 row tiles; Bimg: L^-1 digit images (layout at the top of this file)
 cudaError_t launch_var_i8(const int8_t* Aimg, int rows_pad, int rows_alloc, const int8_t* Bimg, const double* colscale, const double* hyp,
                           int n_pad, double* varpart, int batch, int* flag, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once; int attr_dev;
+    if (attr_once.pending(attr_dev)) {
         cudaError_t e = cudaFuncSetAttribute(k_var_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_once.mark(attr_dev);
     }
     const int mt = rows_pad / VT_M, nt = n_pad / VT_N, groups = (nt + VT_GN - 1) / VT_GN;
     const int per_gp = mt * VT_GN * groups, nslots = per_gp * batch;
@@ -593,47 +528,6 @@ cudaError_t launch_var_i8(const int8_t* Aimg, int rows_pad, int rows_alloc, cons
     VarI8Params p{Aimg, Bimg, colscale, hyp, varpart, rows_pad, nt, mt, n_pad / VT_KB, nslots, (nslots + grid - 1) / grid, flag,
                   per_gp, n_pad, rows_alloc, (long long)rows_alloc * n_pad * 8};
     k_var_i8<<<grid, 320, VT_SMEM, st>>>(p);
-    return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// int8 tensor-pipe ceiling, measured live (bench.py roofline denominator): every CTA issues `iters` x 8 resident-operand MMAs
-// (M = 128, N = 256, K = 32, pseudo-random digits in shared memory, no global traffic) and waits for the last commit.
-__global__ void __launch_bounds__(128, 1) k_i8_peak(int iters, int* flag) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* bar = (uint64_t*)(base + 16384);
-    uint32_t* tmem_slot = (uint32_t*)(bar + 1);
-    const int tid = threadIdx.x, warp = tid >> 5;
-    for (int i = tid; i < 4096; i += 128) ((uint32_t*)base)[i] = (uint32_t)(i * 2654435761u) & 0x3f3f3f3fu;   // digits in [0, 63]
-    if (tid == 0) { mbar_init(smem_u32(bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes above -> visible to the tensor core
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
-    if (tid == 0) {
-        const uint64_t ad = make_desc_sw32(smem_u32(base)), bd = make_desc_sw32(smem_u32(base + 4096));
-        for (int it = 0; it < iters; it++) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) umma_i8(tmem_base + (j & 1) * 256, ad, bd, idesc_i8(256, true), (uint32_t)(it != 0));
-        }
-        umma_commit(smem_u32(bar));
-        mbar_wait(smem_u32(bar), 0, flag);
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-}
-
-cudaError_t launch_i8_peak(int iters, int sms, int* flag, double* ops_out, cudaStream_t st) {
-    constexpr int SM = 16384 + 64 + 1024;
-    k_i8_peak<<<sms, 128, SM, st>>>(iters, flag);
-    if (ops_out) *ops_out = 2.0 * 128 * 256 * 32 * 8.0 * iters * sms;
     return cudaGetLastError();
 }
 

@@ -131,10 +131,13 @@ __global__ void __launch_bounds__(LB_THREADS) k_lbfgs_propose(LbfgsParams p) {
 
 __global__ void __launch_bounds__(LB_THREADS) k_lbfgs_accept(LbfgsParams p) {
     __shared__ double red[16];
-    __shared__ int s_pick;
+    __shared__ int s_pick, s_head;
     const int r = blockIdx.x, D = p.D, M = p.M, T = p.T, tid = threadIdx.x;
     int* meta = p.meta + 4 * r;
     if (meta[2] > 0) return;
+    // ring slot of the next curvature pair: read ONCE by thread 0 and shared, so that no late warp can see the meta[] that thread 0
+    // rewrites further down (a warp that read the updated meta would have copied its part of (s, y) into the wrong slot)
+    if (tid == 0) s_head = (meta[0] == 0) ? 0 : (meta[1] + 1) % M;
     double* x = p.x + (size_t)r * D;
     double* g = p.g + (size_t)r * D;
     const double* Xt = p.Xt + (size_t)r * T * D;
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(LB_THREADS) k_lbfgs_accept(LbfgsParams p) {
     for (int i = tid; i < D; i += LB_THREADS) { const double s = xn[i] - x[i], y = gn[i] - g[i]; sy += s * y; yy += y * y; }
     sy = block_sum(sy, red); yy = block_sum(yy, red);
     if (sy > 2.220446049250313e-16 * yy && sy > 0.0) {
-        const int head = (meta[0] == 0) ? 0 : (meta[1] + 1) % M;
+        const int head = s_head;     // (published by the barriers of block_sum above)
         double* S = p.S + ((size_t)r * M + head) * D;
         double* Y = p.Y + ((size_t)r * M + head) * D;
         for (int i = tid; i < D; i += LB_THREADS) { S[i] = xn[i] - x[i]; Y[i] = gn[i] - g[i]; }
@@ -203,11 +206,9 @@ __global__ void __launch_bounds__(LB_THREADS) k_lbfgs_accept(LbfgsParams p) {
 cudaError_t launch_lbfgs_propose(const LbfgsParams& p, cudaStream_t st) {
     if (p.R == 0) return cudaSuccess;
     const size_t smem = (size_t)(p.D + 16 + p.M) * sizeof(double);
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
+    if (smem > 48 * 1024) {   // per-device attribute, microseconds: set it whenever it is needed rather than remembering it per process
         cudaError_t e = cudaFuncSetAttribute(k_lbfgs_propose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        smem_set = smem;
     }
     k_lbfgs_propose<<<p.R, LB_THREADS, smem, st>>>(p);
     return cudaGetLastError();

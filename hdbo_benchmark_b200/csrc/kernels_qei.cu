@@ -135,4 +135,64 @@ cudaError_t launch_qei(const double* mean, const double* Sigma, const double* ba
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Joint posterior samples of q <= 8 points: out[s][r][:] = mean[r] + chol(Sigma[r] + jitter I) z[s][r or 0][:]
+// (GPyTorchPosterior.rsample_from_base_samples on the q x q factor).  One thread per (s, r): the q x q factorisation is ~q^3/3
+// flops, cheaper to redo in registers than to stage.
+template <int Q>
+__global__ void k_mvn_sample(const double* __restrict__ mean, const double* __restrict__ Sigma, const double* __restrict__ z,
+                             long long R, long long S, int z_per_r, double jitter, double* __restrict__ out,
+                             int32_t* __restrict__ info) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= R * S) return;
+    const long long r = t % R, s = t / R;
+    double L[Q][Q];
+#pragma unroll
+    for (int i = 0; i < Q; i++)
+#pragma unroll
+        for (int j = 0; j < Q; j++) L[i][j] = Sigma[(r * Q + i) * Q + j];
+    int bad = 0;
+#pragma unroll
+    for (int j = 0; j < Q; j++) {
+        double djj = L[j][j] + jitter;
+#pragma unroll
+        for (int k = 0; k < j; k++) djj -= L[j][k] * L[j][k];
+        if (!(djj > 0.0)) { if (!bad) bad = j + 1; djj = 1.0; }
+        const double l = sqrt(djj), il = 1.0 / l;
+        L[j][j] = l;
+#pragma unroll
+        for (int i = j + 1; i < Q; i++) {
+            double v = L[i][j];
+#pragma unroll
+            for (int k = 0; k < j; k++) v -= L[i][k] * L[j][k];
+            L[i][j] = v * il;
+        }
+    }
+    if (info && s == 0) info[r] = bad;
+    const double* zz = z + (z_per_r ? (s * R + r) : s) * Q;
+    double zv[Q];
+#pragma unroll
+    for (int k = 0; k < Q; k++) zv[k] = zz[k];
+#pragma unroll
+    for (int j = 0; j < Q; j++) {
+        double v = mean[r * Q + j];
+#pragma unroll
+        for (int k = 0; k <= j; k++) v = fma(L[j][k], zv[k], v);
+        out[(s * R + r) * Q + j] = v;
+    }
+}
+
+cudaError_t launch_mvn_sample(const double* mean, const double* Sigma, const double* z, long long R, int q, long long S,
+                              int z_per_r, double jitter, double* out, int32_t* info, cudaStream_t st) {
+    if (R * S == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((R * S + 127) / 128);
+#define QCASE(Q) case Q: k_mvn_sample<Q><<<grid, 128, 0, st>>>(mean, Sigma, z, R, S, z_per_r, jitter, out, info); break;
+    switch (q) {
+        QCASE(1) QCASE(2) QCASE(3) QCASE(4) QCASE(5) QCASE(6) QCASE(7) QCASE(8)
+        default: return cudaErrorInvalidValue;
+    }
+#undef QCASE
+    return cudaGetLastError();
+}
+
 }  // namespace hdbo

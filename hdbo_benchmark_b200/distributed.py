@@ -76,3 +76,58 @@ def sharded_pool_argmax(evaluate_slice, total: int, group=None):
     s, e = shard_bounds(total, rank, world)
     _, v, i = evaluate_slice(s, e)
     return global_argmax(v, i, s, group)
+
+
+# ---- the other two shard axes: SAAS hyper-parameter samples and multi-start restarts ------------------------------
+def strided_indices(total: int, rank: int, world: int) -> torch.Tensor:
+    """Restart shard r::P (SURVEY 8e): restart i is optimised by rank i mod P; no data-path exchange until the final arg-max."""
+    return torch.arange(rank, total, world)
+
+
+def mixture_moments(mean: torch.Tensor, var: torch.Tensor, num_samples_total: int, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Gaussian-mixture mean / variance over ALL S hyper-parameter samples from this rank's slice of them.
+
+    mean / var: [S_local, m] per-sample posterior moments of the rank's samples (botorch fully-Bayesian posteriors keep the MCMC
+    dimension; the mixture is  E = mean_s mu_s,  V = mean_s (var_s + mu_s^2) - E^2).  The exchange is ONE all-reduce (sum) of the
+    stacked [2, m] partial sums -- 16 bytes per candidate, independent of S -- instead of an all-gather of S x m moments."""
+    part = torch.stack([mean.sum(0), (var + mean * mean).sum(0)])
+    if is_distributed():
+        dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+    e = part[0] / num_samples_total
+    return e, part[1] / num_samples_total - e * e
+
+
+def mixture_log_acq(log_acq: torch.Tensor, num_samples_total: int, group=None) -> torch.Tensor:
+    """log mean_s exp(log_acq_s) over all S samples (LogEI of a fully Bayesian model) from the rank's [S_local, m] slice:
+    all-reduce(max) for the stabiliser, all-reduce(sum) of the shifted exponentials."""
+    mx = log_acq.max(dim=0).values
+    if is_distributed():
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    safe = torch.where(torch.isfinite(mx), mx, torch.zeros_like(mx))
+    s = torch.exp(log_acq - safe).sum(0)
+    if is_distributed():
+        dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+    return torch.log(s / num_samples_total) + safe
+
+
+def best_restart(local_vals: torch.Tensor, local_X: torch.Tensor, local_ids: torch.Tensor, group=None):
+    """Best (value, restart id, X [q, d]) over all ranks' restarts; ties -> smallest restart id.  One all-gather of
+    (value, id) pairs (16 B / rank) + one broadcast of the winning X from its owner."""
+    i = torch.argmax(local_vals) if local_vals.numel() else None
+    val = local_vals[i].reshape(1).to(torch.float64) if i is not None else torch.full((1,), float("-inf"), dtype=torch.float64,
+                                                                                      device=local_X.device)
+    rid = local_ids[i].reshape(1).to(torch.float64).to(val.device) if i is not None else torch.full_like(val, float("inf"))
+    if not is_distributed():
+        return val[0], int(rid[0]), local_X[i]
+    world = dist.get_world_size(group)
+    pair = torch.cat([val, rid])
+    gathered = [torch.empty_like(pair) for _ in range(world)]
+    dist.all_gather(gathered, pair, group=group)
+    allp = torch.stack(gathered)
+    best = allp[:, 0].max()
+    ids = torch.where(allp[:, 0] == best, allp[:, 1], torch.full_like(allp[:, 1], float("inf")))
+    win = int(ids.min().item())
+    owner = win % world                      # strided shard: restart id -> owner rank
+    X = local_X[i].clone() if (i is not None and int(rid[0]) == win) else torch.empty_like(local_X[0])
+    dist.broadcast(X, src=owner, group=group)
+    return best, win, X

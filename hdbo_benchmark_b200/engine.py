@@ -29,6 +29,7 @@ I8_MAX_N_PAD = 8192   # int8 mode: int32 group sums stay exact up to this size (
 # 1.6e-5, 1.5e-7 at 1e-4.  Below this noise / outputscale ratio the engine keeps the FP64 path (BoTorch's own floor is 1e-4).
 I8_MIN_NOISE_RATIO = 1e-4
 I8_MAX_D = 16384      # int8 mode: the same bound for the cross GEMM (K = d)
+I8_DEFAULT_MIN_POOL = 1024
 
 
 def _rup(x: int, m: int) -> int:
@@ -44,15 +45,31 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on_gp_device(fn):
+    """Run a DeviceGP method with the GP's device current: kernel launches and `_stream()` follow the CUDA current device, which
+    need not be the device the model lives on (HDBO_TORCH_DEVICE=cuda:1 in a process whose current device is cuda:0)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+    return wrapped
+
+
 class DeviceGP:
     def __init__(self, X: torch.Tensor, y: torch.Tensor, kind: int, batch: int = 1, keep_r2: bool = False,
                  var_mode: Optional[str] = None):
-        """var_mode: "f64" (FP64 DMMA variance contraction, the default) or "i8" (exact digit-sliced int8 contraction on the
-        tcgen05 tensor cores for the no-grad pool evaluation, n_pad <= 8192).  Default from $HDBO_VAR_MODE."""
+        """var_mode: "i8" (the default: both GEMMs of the no-grad pool evaluation as exact digit-sliced int8 contractions on the
+        tcgen05 tensor cores; applies when n_pad <= 8192, d <= 16384 and noise >= 1e-4 outputscale -- BoTorch's own noise floor for
+        standardised targets -- and silently keeps the FP64 DMMA path otherwise) or "f64" (always FP64 DMMA).  $HDBO_VAR_MODE
+        overrides the default."""
         if not X.is_cuda:
             raise _lib.HdboError("DeviceGP needs CUDA tensors: the hot path has no CPU implementation")
         self.lib = _lib.load()
-        self.device = X.device
+        self.device = torch.device("cuda", X.device.index if X.device.index is not None else torch.cuda.current_device())
         self.X = X.detach().to(torch.float64).contiguous()
         self.y = y.detach().to(torch.float64).reshape(-1).contiguous()
         self.n, self.d = self.X.shape
@@ -83,7 +100,11 @@ class DeviceGP:
         self._argmax_work = torch.zeros(8192, dtype=torch.uint8, device=self.device)
         self.fitted = False
         self.jitter_used = 0.0
-        self.var_mode = (var_mode or os.environ.get("HDBO_VAR_MODE", "f64")).lower()
+        explicit = var_mode or os.environ.get("HDBO_VAR_MODE")
+        self.var_mode = (explicit or "i8").lower()
+        # defaulted mode: pools below this many candidates stay on the FP64 kernels (their small-tile variants win there, and a BO
+        # loop that refits between a handful of posterior calls never pays for slicing L^-1 into digit planes)
+        self.i8_min_pool = 0 if explicit else I8_DEFAULT_MIN_POOL
         if self.var_mode not in ("f64", "i8"):
             raise ValueError(f"var_mode must be 'f64' or 'i8', got {self.var_mode!r}")
         self._i8_state: Optional[torch.Tensor] = None
@@ -95,8 +116,45 @@ class DeviceGP:
             X=ptr(self.X), ldx=self.X.stride(0), y=ptr(self.y), center=ptr(self.center), inv_ls=ptr(self.inv_ls),
             hyp=ptr(self.hyp), Xs=ptr(self.Xs), xn=ptr(self.xn), R2=ptr(self.R2), Awork=ptr(self.Awork), L=ptr(self.L),
             Linv=ptr(self.Linv), Linvt=ptr(self.Linvt), w=ptr(self.w), alpha=ptr(self.alpha), scal=ptr(self.scal),
-            info=ptr(self.info),
+            info=ptr(self.info), timeline=None,
         )
+        self._timeline = None
+
+    # ---- caller-owned timeline: CUDA events recorded by the library around its phases (bench.py's per-kernel figures) ----
+    @_on_gp_device
+    def attach_timeline(self, capacity: int = 4096) -> None:
+        """Create `capacity` timing events (owned here, i.e. by the caller of the C ABI) and hand them to the library."""
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(capacity)]
+        for e in evs:
+            e.record()      # torch creates the cudaEvent_t lazily: force it so that the raw handle exists
+        handles = (C.c_void_p * capacity)(*[e.cuda_event for e in evs])
+        phases = (C.c_int32 * capacity)()
+        tl = _lib.HdboTimeline(events=C.cast(handles, C.POINTER(C.c_void_p)), phase=C.cast(phases, C.POINTER(C.c_int32)),
+                               capacity=capacity, used=0)
+        self._timeline = (tl, evs, handles, phases)
+        self.desc.timeline = C.cast(C.pointer(tl), C.c_void_p)
+
+    def detach_timeline(self) -> None:
+        self.desc.timeline = None
+        self._timeline = None
+
+    def reset_timeline(self) -> None:
+        if self._timeline is not None:
+            self._timeline[0].used = 0
+
+    def collect_timeline(self) -> dict:
+        """{phase name: (total ms, launches)} of everything recorded since the last reset.  Synchronises."""
+        out = {}
+        if self._timeline is None:
+            return out
+        tl, evs, _, phases = self._timeline
+        torch.cuda.synchronize(self.device)
+        for i in range(0, tl.used - 1, 2):
+            name = _lib.PHASE_NAMES[phases[i]]
+            ms, cnt = out.get(name, (0.0, 0))
+            out[name] = (ms + evs[i].elapsed_time(evs[i + 1]), cnt + 1)
+        tl.used = 0
+        return out
 
     # ---- hyper-parameters (device tensors; no host sync) ----
     def set_hyper(self, lengthscale, outputscale, noise, mean, jitter: float = 0.0) -> None:
@@ -115,11 +173,13 @@ class DeviceGP:
         self.fitted = False
 
     # ---- A1 + A2: kernel build, Cholesky, inverse, alpha, logdet ----
+    @_on_gp_device
     def fit_once(self, need_r2: Optional[bool] = None) -> None:
         need = self.keep_r2 if need_r2 is None else need_r2
         check(self.lib.hdbo_gp_fit(C.byref(self.desc), int(bool(need)), _stream()), "hdbo_gp_fit")
         self._i8_dirty = True
 
+    @_on_gp_device
     def fit(self, need_r2: Optional[bool] = None, max_tries: int = 3) -> float:
         """Factorise with the psd_safe_cholesky jitter schedule (1e-8 * 10**i, i < max_tries).  One host sync."""
         self.fit_once(need_r2)
@@ -144,6 +204,7 @@ class DeviceGP:
         return jitter
 
     # ---- exact int8 variance mode: digit planes of L^-1, once per fit ----
+    @_on_gp_device
     def slice_linv(self) -> None:
         if self._i8_state is None:
             need = self.lib.hdbo_i8_state_bytes(C.byref(self.desc))
@@ -160,7 +221,8 @@ class DeviceGP:
         return int(self._i8_state[-16:-12].view(torch.int32).item())
 
     def _pool_call(self, Zptr, ldz, m, observation_noise, acq_kind, acq_param, mean, var, acq, bso, ws, stream) -> None:
-        if self.var_mode == "i8" and self.n_pad <= I8_MAX_N_PAD and self.d <= I8_MAX_D and self._i8_ok:
+        if (self.var_mode == "i8" and self.n_pad <= I8_MAX_N_PAD and self.d <= I8_MAX_D and self._i8_ok
+                and m * self.batch >= self.i8_min_pool):
             if self._i8_dirty or self._i8_state is None:
                 self.slice_linv()
             check(self.lib.hdbo_posterior_acq_i8(C.byref(self.desc), ptr(self._i8_state), Zptr, ldz, m, int(observation_noise),
@@ -182,6 +244,7 @@ class DeviceGP:
         return self._ws
 
     # ---- A4 + A5: posterior mean / variance / acquisition over a candidate pool (no grad) ----
+    @_on_gp_device
     def posterior_acq(self, Z: torch.Tensor, acq_kind: int = _lib.ACQ_NONE, acq_param: float = 0.0,
                       observation_noise: bool = False, want_mean: bool = True, want_var: bool = True,
                       chunk_rows: int = DEFAULT_CHUNK_ROWS, out: Optional[dict] = None):
@@ -204,11 +267,14 @@ class DeviceGP:
                         _stream())
         return mean, var, acq
 
+    @_on_gp_device
     def posterior_acq_host(self, Z_host: torch.Tensor, acq_kind: int, acq_param: float, out_host: Optional[torch.Tensor] = None,
-                           copy_rows: int = 1 << 17, chunk_rows: int = DEFAULT_CHUNK_ROWS):
+                           copy_rows: int = 2 * DEFAULT_CHUNK_ROWS, chunk_rows: int = DEFAULT_CHUNK_ROWS, slab_transform=None):
         """End-to-end pool evaluation from HOST memory (pinned for full overlap): candidates are streamed to the device in
         `copy_rows` slabs on a copy stream (double-buffered) while the previous slab is evaluated; the acquisition values
-        [m] come back to `out_host` and the arg-max (value, index) is reduced on the device.  batch == 1 only."""
+        [m] come back to `out_host` and the arg-max (value, index) is reduced on the device.  batch == 1 only.
+        `slab_transform` (optional): in-place map applied to each slab on the device before it is evaluated (the model's input
+        transform when the call comes through the BoTorch surface)."""
         assert self.fitted and self.batch == 1
         m, d = Z_host.shape
         f64 = dict(dtype=torch.float64, device=self.device)
@@ -234,6 +300,8 @@ class DeviceGP:
                 slab[:mc].copy_(Z_host[off:off + mc], non_blocking=True)
                 ready[i % 2].record(self._copy_stream)
             main.wait_event(ready[i % 2])
+            if slab_transform is not None:
+                slab_transform(slab[:mc])
             self._pool_call(ptr(slab), slab.stride(0), mc, 0, acq_kind, acq_param, 0, 0, acq.data_ptr() + off * 8, m, ws,
                             main.cuda_stream)
             free[i % 2].record(main)
@@ -243,6 +311,7 @@ class DeviceGP:
         return acq, val, idx
 
     # ---- A4 + A5 + A6 without the autograd tape: acquisition value and d/dZ for m points (device L-BFGS inner loop) ----
+    @_on_gp_device
     def acq_value_grad(self, Z: torch.Tensor, acq_kind: int, acq_param: float, sign: float = 1.0, bufs: Optional[dict] = None):
         """Z [m, d] float64 contiguous on the device -> (acq [m], dacq/dZ [m, d]); `sign` = -1 evaluates the acquisition of
         the negated mean (minimisation problems).  `bufs` (a dict the caller keeps) caches workspace and outputs across calls."""
@@ -269,6 +338,7 @@ class DeviceGP:
                                      ptr(b["ws"]), b["ws"].numel(), st), "hdbo_posterior_bwd")
         return b["acq"], b["dZ"]
 
+    @_on_gp_device
     def argmax(self, v: torch.Tensor):
         v = v.reshape(-1)
         out_val = torch.empty(1, dtype=torch.float64, device=self.device)

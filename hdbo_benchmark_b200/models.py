@@ -52,17 +52,19 @@ class Standardize(nn.Module):
             raise NotImplementedError("single-output models only")
         self.register_buffer("means", torch.zeros(1, 1, dtype=torch.float64))
         self.register_buffer("stdvs", torch.ones(1, 1, dtype=torch.float64))
+        self.register_buffer("_stdvs_sq", torch.ones(1, 1, dtype=torch.float64))      # BoTorch's buffer names: checkpoints round-trip
+        self.register_buffer("_is_trained", torch.tensor(False))
         self._min_stdv = min_stdv
-        self._is_trained = False
 
     def forward(self, Y):
         Y = Y.to(torch.float64)
-        if self.training or not self._is_trained:
+        if self.training or not bool(self._is_trained):
             stdvs = Y.std(dim=-2, keepdim=True) if Y.shape[-2] > 1 else torch.ones_like(Y[..., :1, :])
             stdvs = stdvs.where(stdvs >= self._min_stdv, torch.ones_like(stdvs))
             self.means = Y.mean(dim=-2, keepdim=True).to(self.means.device)
             self.stdvs = stdvs.to(self.stdvs.device)
-            self._is_trained = True
+            self._stdvs_sq = self.stdvs.pow(2)
+            self._is_trained = torch.tensor(True, device=self.means.device)
         return (Y - self.means.to(Y.device)) / self.stdvs.to(Y.device)
 
     def untransform_moments(self, mean, var):
@@ -252,6 +254,11 @@ class ExactGPBase(nn.Module):
     def posterior(self, X, observation_noise: bool = False, posterior_transform=None, **kwargs) -> GPPosterior:
         """X: [b, q, d] (or [q, d]) -> posterior with .mean / .variance of shape [b, q, 1]."""
         Xd, out_device, out_dtype = self._prep_X(X)
+        post = self._posterior_from_transformed(Xd, bool(observation_noise), out_device, out_dtype)
+        return posterior_transform(post) if posterior_transform is not None else post
+
+    def _posterior_from_transformed(self, Xd, observation_noise: bool, out_device, out_dtype) -> GPPosterior:
+        """Xd: already on the compute device and through the input transform."""
         squeeze_b = Xd.dim() == 2
         if squeeze_b:
             Xd = Xd.unsqueeze(0)
@@ -272,8 +279,7 @@ class ExactGPBase(nn.Module):
                 var = torch.diagonal(Sigma, dim1=-2, dim2=-1).reshape(gp.batch, b * q)
         else:
             mean, var, _ = gp.posterior_acq(flat, _lib.ACQ_NONE, 0.0, observation_noise=bool(observation_noise))
-        post = GPPosterior(self, flat, mean, var, Sigma, b, q, squeeze_b, out_device, out_dtype, bool(observation_noise))
-        return posterior_transform(post) if posterior_transform is not None else post
+        return GPPosterior(self, flat, mean, var, Sigma, b, q, squeeze_b, out_device, out_dtype, bool(observation_noise))
 
     def forward(self, X):
         if self.training:
@@ -284,14 +290,30 @@ class ExactGPBase(nn.Module):
         return self.forward(X)
 
     def condition_on_observations(self, X, Y, **kwargs):
-        Xn = torch.cat([self._train_X_raw, torch.as_tensor(X).to(self._dev, torch.float64).reshape(-1, self._train_X_raw.shape[-1])])
-        Yraw = self.train_targets.unsqueeze(-1)
+        """A new model on the augmented data with the SAME hyper-parameters (botorch `Model.condition_on_observations`).
+        BoTorch semantics: the new observations go through the EXISTING, already-trained transforms (eval mode: Standardize keeps
+        its means / stdvs, a learned-bounds Normalize keeps its bounds); nothing is re-learned, so predictions of the conditioned
+        model un-transform with the same statistics its targets were standardised with.  The transforms are deep-copied: the
+        original model is never mutated."""
+        import copy
+        d = self._train_X_raw.shape[-1]
+        Xraw_new = torch.as_tensor(X).to(self._dev, torch.float64).reshape(-1, d)
+        Ynew = torch.as_tensor(Y).to(self._dev, torch.float64).reshape(-1, 1)
+        Xt_new = self.input_transform(Xraw_new) if self.input_transform is not None else Xraw_new
         if self.outcome_transform is not None:
             m, s = self.outcome_transform.means.reshape(()), self.outcome_transform.stdvs.reshape(())
-            Yraw = Yraw * s + m
-        Yn = torch.cat([Yraw, torch.as_tensor(Y).to(self._dev, torch.float64).reshape(-1, 1)])
-        new = type(self)(Xn, Yn, **self._ctor_kwargs())
-        new.load_state_dict(self.state_dict(), strict=False)
+            Ynew = (Ynew - m) / s
+        kw = self._ctor_kwargs()
+        kw["outcome_transform"] = None
+        kw["input_transform"] = None
+        new = type(self)(torch.cat([self.train_inputs[0], Xt_new]), torch.cat([self.train_targets.unsqueeze(-1), Ynew]), **kw)
+        new.outcome_transform = copy.deepcopy(self.outcome_transform)
+        new.input_transform = copy.deepcopy(self.input_transform)
+        new._train_X_raw = torch.cat([self._train_X_raw, Xraw_new])
+        new._io_device, new._io_dtype = self._io_device, self._io_dtype
+        hyper = {k: v for k, v in self.state_dict().items()
+                 if not (k.startswith("outcome_transform.") or k.startswith("input_transform."))}
+        new.load_state_dict(hyper, strict=False)
         return new
 
     def _ctor_kwargs(self):
@@ -343,7 +365,8 @@ class SingleTaskGP(ExactGPBase):
         return dict(likelihood=copy.deepcopy(self.likelihood), covar_module=copy.deepcopy(self.covar_module),
                     mean_module=copy.deepcopy(self.mean_module),
                     outcome_transform=copy.deepcopy(self.outcome_transform) if self.outcome_transform is not None else None,
-                    input_transform=self.input_transform, legacy_defaults=self._legacy)
+                    input_transform=copy.deepcopy(self.input_transform) if self.input_transform is not None else None,
+                    legacy_defaults=self._legacy)
 
 
 # ------------------------------------------------------------------------------------------------------

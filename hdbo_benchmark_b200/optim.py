@@ -80,7 +80,8 @@ def gen_batch_initial_conditions(acq_function, bounds, q: int, num_restarts: int
     dev = _compute_device(acq_function)
     bounds = torch.as_tensor(bounds, dtype=torch.float64)
     seed = options.get("seed")
-    X_rnd = draw_sobol_samples(bounds, n=raw_samples, q=q, seed=seed, stream=options.get("sobol_stream")).to(dev)
+    # raw samples are generated on the device (bit-identical to torch's SobolEngine): no host loop, no 2 GB host-to-device copy
+    X_rnd = draw_sobol_samples(bounds, n=raw_samples, q=q, seed=seed, stream=options.get("sobol_stream"), device=dev)
     batch_limit = options.get("init_batch_limit", options.get("batch_limit", 1 << 20))
     with torch.no_grad():
         Y_rnd = torch.cat([acq_function(X_rnd[i:i + batch_limit]).to(dev, torch.float64)

@@ -7,6 +7,7 @@ the tiny q x q factors only (torch ops on the device; the n-sized work is alread
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import Optional
 
 import torch
@@ -107,19 +108,43 @@ class GPPosterior:
     def mvn(self):
         return self
 
+    def with_observation_noise(self, noise=None):
+        """The predictive distribution of y = f + eps: what `likelihood(model(x))` returns in GPyTorch.  Re-issues the posterior with
+        the model's own noise added to the variances / the diagonal of the joint covariance."""
+        if self._observation_noise:
+            return self
+        X = self._Z.reshape(self._b, self._q, -1)
+        return self._model._posterior_from_transformed(X[0] if self._squeeze_b else X, True, self._out_device, self._out_dtype)
+
     # ---- sampling -----------------------------------------------------------------------------------
     def rsample_from_base_samples(self, sample_shape, base_samples):
-        """base_samples: sample_shape x [b] x q x 1 standard normal draws -> samples sample_shape x b x q x 1."""
-        S = self._joint_cov_std()[0] if self._B == 1 else self._joint_cov_std()
-        mean = self._mean_std.reshape(self._B, self._b, self._q)
-        mean = mean[0] if self._B == 1 else mean
-        q = self._q
-        L = torch.linalg.cholesky(S + 1e-8 * torch.eye(q, dtype=S.dtype, device=S.device))
-        z = base_samples.to(S.device, torch.float64).squeeze(-1)
-        while z.dim() < mean.dim() + len(sample_shape):
+        """base_samples: sample_shape x [b] x q x 1 standard normal draws -> samples sample_shape x b x q x 1.
+        The q x q Cholesky factors (jitter 1e-8) and mean + L z run in `hdbo_mvn_sample` (q <= 8)."""
+        from ._lib import check, load, ptr
+        from .engine import _stream
+        sample_shape = torch.Size(sample_shape)
+        q, B, b = self._q, self._B, self._b
+        Sig = self._joint_cov_std().reshape(B * b, q, q).contiguous()
+        mean = self._mean_std.reshape(B * b, q).contiguous()
+        dev = mean.device
+        z = torch.as_tensor(base_samples).to(dev, torch.float64)
+        if z.dim() and z.shape[-1] == 1 and z.dim() > len(sample_shape) + 1:
+            z = z.squeeze(-1)
+        S = int(math.prod(sample_shape)) if len(sample_shape) else 1
+        lead = (B, b) if B > 1 else (b,)
+        z = z.reshape(*sample_shape, *z.shape[len(sample_shape):])
+        # broadcast the per-group dimensions that the caller left out or gave as 1
+        while z.dim() < len(sample_shape) + len(lead) + 1:
             z = z.unsqueeze(len(sample_shape))
-        samples = mean + (L @ z.unsqueeze(-1)).squeeze(-1)
-        samples = samples * self._scale + self._shift
+        shared = all(int(x) == 1 for x in z.shape[len(sample_shape):-1])
+        if shared:
+            zz = z.reshape(S, q).contiguous()
+        else:
+            zz = z.expand(*sample_shape, *lead, q).reshape(S, B * b, q).contiguous()
+        out = torch.empty(S, B * b, q, dtype=torch.float64, device=dev)
+        check(load().hdbo_mvn_sample(ptr(mean), ptr(Sig), ptr(zz), B * b, q, S, 0 if shared else 1, 1e-8, ptr(out), 0, _stream()),
+              "hdbo_mvn_sample")
+        samples = out.reshape(*sample_shape, *lead, q) * self._scale + self._shift
         return samples.unsqueeze(-1).to(self._out_device, self._out_dtype)
 
     def rsample(self, sample_shape: Optional[torch.Size] = None):

@@ -41,11 +41,72 @@ def _sobol_unit_points(dim: int, n: int, seed: Optional[int], stream: Optional[i
     return eng.draw(n, dtype=torch.float64)
 
 
-def draw_sobol_samples(bounds: torch.Tensor, n: int, q: int, seed: Optional[int] = None, stream: Optional[int] = None) -> torch.Tensor:
-    """n x q x d scrambled-Sobol points inside `bounds` (2 x d); one (q*d)-dimensional engine as in BoTorch."""
+class DeviceSobol:
+    """A torch.quasirandom.SobolEngine whose points are generated in HBM by `hdbo_sobol_draw` (bit-identical to the host engine).
+
+    The (scrambled) direction numbers and the digital shift come from torch's own engine -- so seeds mean what they mean upstream --
+    and are uploaded once (30 x dim int32); a draw of m points is then one HBM-bound kernel (8 B per element) instead of a
+    single-threaded host loop plus a host-to-device copy: the 2^20 x 256 raw-sample pool of `optimize_acqf` takes seconds on the
+    host.  Same stateful interface: `draw(n)` continues the sequence, `fast_forward(n)` skips, `reset()` rewinds."""
+
+    def __init__(self, dimension: int, scramble: bool = True, seed: Optional[int] = None, device=None):
+        eng = torch.quasirandom.SobolEngine(dimension, scramble=scramble, seed=seed)
+        self.dimension = dimension
+        self.device = torch.device(device if device is not None else "cuda")
+        self.state_t = eng.sobolstate.t().contiguous().to(torch.int32).to(self.device)
+        self.shift = eng.shift.to(torch.int32).to(self.device)
+        self.num_generated = 0
+
+    def reset(self):
+        self.num_generated = 0
+        return self
+
+    def fast_forward(self, n: int):
+        self.num_generated += int(n)
+        return self
+
+    def draw(self, n: int = 1, lower: Optional[torch.Tensor] = None, rng: Optional[torch.Tensor] = None,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """n x dimension float64 points on the device; `lower` / `rng` [dimension] map the unit cube to lower + rng * u."""
+        from . import _lib
+        from ._lib import check, ptr
+        if out is None:
+            out = torch.empty(n, self.dimension, dtype=torch.float64, device=self.device)
+        assert out.is_cuda and out.dtype == torch.float64 and out.shape == (n, self.dimension) and out.stride(1) == 1
+        with torch.cuda.device(self.device):
+            check(_lib.load().hdbo_sobol_draw(ptr(self.state_t), ptr(self.shift), self.dimension, self.num_generated, n,
+                                              ptr(lower), ptr(rng), ptr(out), out.stride(0),
+                                              torch.cuda.current_stream().cuda_stream), "hdbo_sobol_draw")
+        self.num_generated += n
+        return out
+
+
+_DEVICE_ENGINES = {}
+
+
+def _device_sobol_points(dim: int, n: int, seed: Optional[int], stream: Optional[int], device, lower, rng) -> torch.Tensor:
+    """Device twin of `_sobol_unit_points`: same seed / stream semantics, points generated in HBM (nothing to cache but the engine
+    state: a seeded draw restarts the sequence at point 0)."""
+    if stream is not None:
+        eng = _cached(_DEVICE_ENGINES, ("stream", dim, stream, str(device)), lambda: DeviceSobol(dim, True, stream, device))
+    elif seed is not None:
+        eng = _cached(_DEVICE_ENGINES, ("seed", dim, seed, str(device)), lambda: DeviceSobol(dim, True, seed, device)).reset()
+    else:
+        eng = _cached(_DEVICE_ENGINES, (dim, None, str(device)), lambda: DeviceSobol(dim, True, None, device))
+    return eng.draw(n, lower, rng)
+
+
+def draw_sobol_samples(bounds: torch.Tensor, n: int, q: int, seed: Optional[int] = None, stream: Optional[int] = None,
+                       device=None) -> torch.Tensor:
+    """n x q x d scrambled-Sobol points inside `bounds` (2 x d); one (q*d)-dimensional engine as in BoTorch.  With a CUDA `device`
+    the points are generated there (`DeviceSobol`), bit-identical to the host path."""
     bounds = torch.as_tensor(bounds)
     d = bounds.shape[-1]
     lower, rng = bounds[0], bounds[1] - bounds[0]
+    if device is not None and torch.device(device).type == "cuda":
+        lo = lower.to(device, torch.float64).repeat(q).contiguous()
+        rg = rng.to(device, torch.float64).repeat(q).contiguous()
+        return _device_sobol_points(q * d, n, seed, stream, torch.device(device), lo, rg).reshape(n, q, d)
     u = _sobol_unit_points(q * d, n, seed, stream).reshape(n, q, d).to(bounds.device)
     return lower.to(torch.float64) + rng.to(torch.float64) * u
 

@@ -13,7 +13,8 @@
  *
  * Conventions
  *  - every pointer is a DEVICE pointer to FP64 (or as typed), owned by the caller; the library never allocates,
- *    frees or retains memory and has no global state besides one-time kernel attributes;
+ *    frees or retains memory and has no global state (kernel attributes are set per launch; timing events, when wanted,
+ *    live in a caller-owned hdbo_timeline);
  *  - all work is enqueued on `stream` (a cudaStream_t passed as void*), no implicit synchronisation;
  *  - return value: 0 ok; > 0 a cudaError_t from a launch; < 0 the (negated, 1-based) index of an invalid argument;
  *  - matrices are row-major.  Internal ("state") matrices are padded: n_pad = roundup(n,128), d_pad = roundup(d,16),
@@ -40,6 +41,25 @@ extern "C" {
 #define HDBO_ACQ_PI 4
 #define HDBO_ACQ_NONE (-1)
 
+/* Optional CALLER-OWNED timeline (bench.py's per-kernel roofline figures).  When hdbo_gp.timeline is non-NULL the entry points
+ * record events[used], events[used+1] (begin / end) on the caller's stream around each phase they enqueue, write the phase id of
+ * both slots to phase[] and advance `used`; they stop recording when the slots run out.  The caller creates the cudaEvent_t
+ * handles (timing enabled), resets `used`, and reads the elapsed times itself: the library keeps no profiling state. */
+#define HDBO_PHASE_CROSS 0      /* cross-kernel build K*(Z, X) (+ mean partials)                */
+#define HDBO_PHASE_VAR 1        /* variance contraction V = K* L^-T                              */
+#define HDBO_PHASE_PREP 2       /* candidate centring / scaling / digit slicing                  */
+#define HDBO_PHASE_FINALIZE 3   /* partial sums -> mean, variance, acquisition                   */
+#define HDBO_PHASE_FIT_BUILD 4  /* training-input scaling + K(X, X) + noise I                    */
+#define HDBO_PHASE_FIT_FACTOR 5 /* Cholesky factor + inverse                                     */
+#define HDBO_PHASE_FIT_SOLVE 6  /* w, alpha, logdet, quadratic form                              */
+#define HDBO_PHASE_MLL_GRAD 7   /* K^-1, G, lengthscale / outputscale / noise / mean gradients   */
+#define HDBO_PHASE_BWD 8        /* posterior backward (dZ)                                       */
+typedef struct hdbo_timeline {
+    void** events;          /* HOST array [capacity] of cudaEvent_t                                                    */
+    int32_t* phase;         /* HOST array [capacity] (may be NULL)                                                     */
+    int32_t capacity, used;
+} hdbo_timeline;
+
 /* One (batch of) exact GP(s).  hyp[b] = {outputscale, noise, constant mean, jitter}. */
 typedef struct hdbo_gp {
     int32_t n, d, n_pad, d_pad, kind, batch;
@@ -60,6 +80,7 @@ typedef struct hdbo_gp {
     double* alpha;          /* [batch][n_pad]        Khat^-1 (y - m)                                            */
     double* scal;           /* [batch][8]: logdet, quad, n*mll data term, sum(alpha), ...                       */
     int32_t* info;          /* [batch] 0 or 1-based index of the first non-positive pivot                       */
+    hdbo_timeline* timeline;/* HOST pointer to a caller-owned timeline, or NULL (the default: nothing is recorded)      */
 } hdbo_gp;
 
 /* library / build identification */
@@ -145,34 +166,32 @@ int hdbo_acq_elementwise(const double* mean, const double* var, int64_t m, int a
 int hdbo_qei(const double* mean, const double* Sigma, const double* base_samples, int64_t R, int q, int64_t S,
              double best_f, double jitter, double* value, double* gmean, double* gSigma, int32_t* info, void* stream);
 
+/* Replaces: torch.quasirandom.SobolEngine(dim, scramble=True, seed).draw(m) + `lower + range * u` inside
+ * botorch.utils.sampling.draw_sobol_samples, i.e. the raw-sample pool of gen_batch_initial_conditions (optimize_acqf),
+ * generated in HBM instead of on the host: points first .. first+m-1 of the sequence, bit-identical to torch's engine.
+ * state_t [30][dim] = the engine's (scrambled) direction numbers transposed, shift [dim] = its digital shift, both int32
+ * (torch keeps them as int64 < 2^30); lower / range [dim] or NULL (unit cube); out [m][ld]. */
+int hdbo_sobol_draw(const int32_t* state_t, const int32_t* shift, int dim, int64_t first, int64_t m, const double* lower,
+                    const double* range, double* out, int64_t ld, void* stream);
+
+/* Replaces: GPyTorchPosterior.rsample_from_base_samples on a joint q-point posterior (q <= 8): psd_safe_cholesky of the q x q
+ * covariance (+ jitter I) and  out[s][r][:] = mean[r][:] + L_r z[s][r][:]  (z_per_r != 0) or L_r z[s][:] (z shared by the R
+ * groups).  mean [R][q], Sigma [R][q][q], z [S][R][q] or [S][q], out [S][R][q]; info [R] (may be NULL): first non-positive pivot. */
+int hdbo_mvn_sample(const double* mean, const double* Sigma, const double* z, int64_t R, int q, int64_t S, int z_per_r,
+                    double jitter, double* out, int32_t* info, void* stream);
+
 /* argmax with first-index tie-break (torch.argmax semantics on a 1-d tensor).  work: >= 8192 bytes, zeroed once. */
 int hdbo_argmax(const double* v, int64_t m, void* work, double* out_val, int64_t* out_idx, void* stream);
 
-/* Generic FP64 C = alpha * A * B^T + beta * C on padded operands (rows multiples of 128, K multiple of 16);
- * exported for tests of the DMMA mainloop and for the pairwise-distance helper. */
+/* Generic FP64 C = alpha * A * B^T + beta * C on padded operands (rows multiples of 128, K multiple of 16), optional triangular
+ * k-range.  Replaces: `mean + base_samples @ L_Sigma^T` of MultivariateNormal.rsample in the Thompson-sampling path of TuRBO / BAxUS
+ * (hdbo_benchmark_b200/thompson.py; reference selection: load_solvers.py:224-246). */
 int hdbo_dgemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t m_pad,
                   int64_t n_pad, int64_t k_pad, double alpha, double beta, int krange, int lower_only, void* stream);
 
 /* Replaces: torch.cdist(x, x) in filter_close_points (training_gps.py:11-13): D [n][n] Euclidean distances.
  * Xs/xn/work as produced internally: caller passes scratch Xs [n_pad][d_pad], xn [n_pad], D_pad [n_pad][n_pad]. */
 int hdbo_cdist(const double* X, int64_t ldx, int n, int d, double* Xs, double* xn, double* D_pad, void* stream);
-
-/* Test hook: sqrt_out[i] = sqrt(clamp(x[i], 1e-30, 1e30)), exp_out[i] = exp(-|x[i]|) computed with the branch-free device
- * routines the kernel epilogues use (csrc/fast_math.cuh); either output may be NULL. */
-int hdbo_test_math(const double* x, int64_t n, double* sqrt_out, double* exp_out, void* stream);
-/* Same for the FP64-lean forms of the int8 cross kernel (cubic sqrt correction; table-based exp, |x| clamped to 700). */
-int hdbo_test_math_lean(const double* x, int64_t n, double* sqrt_out, double* exp_out, void* stream);
-
-/* Opt-in profiling for bench.py: while enabled, CUDA events are recorded on the caller's stream around the two GEMM
- * phases of the posterior (class 0 = cross-kernel build, class 1 = variance contraction).  collect() synchronises on
- * the recorded events, returns total milliseconds and launch counts per class (host arrays of 2) and resets.
- * This is the only mutable global state of the library and is off by default. */
-int hdbo_profile_enable(int on);
-int hdbo_profile_collect(double* ms_by_class, int64_t* launches_by_class);
-
-/* Launches a register-only DMMA.8x8x4 loop on `sms` CTAs x 512 threads (scratch: >= 8 bytes of device memory) and
- * writes the flops it performs to *flops_out (HOST pointer).  Timed by the caller: measured FP64 tensor peak. */
-int hdbo_fp64_peak_probe(double* scratch, int iters, int sms, double* flops_out, void* stream);
 
 /* Batched box-constrained L-BFGS on the device: R independent problems (the restarts of optimize_acqf), minimisation.
  * Replaces: scipy.optimize.minimize(method="L-BFGS-B") inside botorch.generation.gen_candidates_scipy, whose per-iteration
@@ -209,10 +228,6 @@ int hdbo_linear_f32(const float* X, int64_t ldx, int32_t b, int32_t K, const flo
 /* Replaces: np.argmax(logits.reshape(b, L, A), axis=-1) in VAESelfies._logits_to_string_array (vae_selfies.py:241-247):
  * tokens [b][L] (int32), first index on ties; logits [b][ld] finite FP32 with position p at columns p*A .. p*A+A-1. */
 int hdbo_argmax_tokens_f32(const float* logits, int64_t ld, int32_t b, int32_t L, int32_t A, int32_t* tokens, void* stream);
-
-/* Same for the int8 tensor pipe: `sms` CTAs issue resident-operand tcgen05.mma kind::i8 (M128 N256 K32) only; *ops_out (HOST) =
- * integer operations performed (2 per multiply-accumulate).  flag: device int32, set if the completion wait timed out. */
-int hdbo_i8_peak_probe(int32_t* flag, int iters, int sms, double* ops_out, void* stream);
 
 #ifdef __cplusplus
 }

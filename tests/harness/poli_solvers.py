@@ -1,4 +1,4 @@
-"""Stand-ins for the poli-baselines solver classes the reference selects
+"""TEST HARNESS (not product code).  Stand-ins for the poli-baselines solver classes the reference selects
 (/root/reference/src/hdbo_benchmark/utils/experiments/load_solvers.py:118-123 `vanilla_bo`, :124-145
 `vanilla_bo_with_lognormal_prior`, :159-182 `random_line_bo` / `coordinate_line_bo`).
 
@@ -16,10 +16,10 @@ from typing import Callable, Optional
 import numpy as np
 import torch
 
-from .acquisition import ExpectedImprovement, LogExpectedImprovement, UpperConfidenceBound
-from .fit import fit_gpytorch_mll
-from .models import ExactMarginalLogLikelihood, SingleTaskGP
-from .optim import optimize_acqf
+from hdbo_benchmark_b200.acquisition import ExpectedImprovement, LogExpectedImprovement, UpperConfidenceBound
+from hdbo_benchmark_b200.fit import fit_gpytorch_mll
+from hdbo_benchmark_b200.models import ExactMarginalLogLikelihood, SingleTaskGP
+from hdbo_benchmark_b200.optim import optimize_acqf
 
 
 class AbstractSolver:

@@ -78,3 +78,68 @@ def test_single_process_fallthrough():
     assert float(v) == 3.5 and int(i) == 14
     x = torch.arange(5, dtype=torch.float64)
     assert gather_values(x, 5) is x
+
+
+def _worker_axes(rank, world, port, out_q):
+    """SAAS sample shard (mixture moments / mixture LogEI by all-reduce) and restart shard r::P (best restart), world 2 on gloo."""
+    from hdbo_benchmark_b200.distributed import (best_restart, mixture_log_acq, mixture_moments, shard_bounds,
+                                                 strided_indices)
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(11)
+    S, m = 7, 50                                     # odd S: ragged shards
+    mean = torch.randn(S, m, generator=g, dtype=torch.float64)
+    var = torch.rand(S, m, generator=g, dtype=torch.float64) + 0.1
+    lacq = torch.randn(S, m, generator=g, dtype=torch.float64) * 30.0
+    lacq[:, 3] = float("-inf")                       # a candidate with zero improvement under every sample
+    s0, s1 = shard_bounds(S, rank, world)
+    e, v = mixture_moments(mean[s0:s1], var[s0:s1], S)
+    e_ref = mean.mean(0)
+    v_ref = (var + mean * mean).mean(0) - e_ref * e_ref
+    la = mixture_log_acq(lacq[s0:s1], S)
+    la_ref = torch.logsumexp(lacq, dim=0) - torch.log(torch.tensor(float(S), dtype=torch.float64))
+    ok = bool(torch.allclose(e, e_ref, rtol=1e-13, atol=1e-13)) and bool(torch.allclose(v, v_ref, rtol=1e-12, atol=1e-12))
+    fin = torch.isfinite(la_ref)
+    ok = ok and bool(torch.allclose(la[fin], la_ref[fin], rtol=1e-12, atol=1e-12)) and bool((la[~fin] == la_ref[~fin]).all())
+    # restarts r::P
+    R, q, d = 9, 2, 3
+    vals = torch.randn(R, generator=g, dtype=torch.float64)
+    vals[5] = vals[2] = vals.max() + 1.0             # tie: the smaller restart id (2, owned by rank 0) must win
+    Xs = torch.randn(R, q, d, generator=g, dtype=torch.float64)
+    ids = strided_indices(R, rank, world)
+    best, win, Xw = best_restart(vals[ids], Xs[ids], ids)
+    ok = ok and win == 2 and float(best) == float(vals.max()) and bool(torch.equal(Xw, Xs[2]))
+    ok = ok and sorted(torch.cat([strided_indices(R, r, world) for r in range(world)]).tolist()) == list(range(R))
+    out_q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sample_and_restart_shards_match_single_process():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_axes, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in results), results
+
+
+def test_mixture_helpers_single_process():
+    from hdbo_benchmark_b200.distributed import best_restart, mixture_log_acq, mixture_moments
+
+    mean = torch.tensor([[1.0, 2.0], [3.0, 2.0]], dtype=torch.float64)
+    var = torch.tensor([[0.5, 1.0], [0.5, 1.0]], dtype=torch.float64)
+    e, v = mixture_moments(mean, var, 2)
+    assert torch.allclose(e, torch.tensor([2.0, 2.0], dtype=torch.float64)) and torch.allclose(v, torch.tensor([1.5, 1.0], dtype=torch.float64))
+    la = mixture_log_acq(torch.log(torch.tensor([[0.2], [0.6]], dtype=torch.float64)), 2)
+    assert abs(float(la) - float(torch.log(torch.tensor(0.4)))) < 1e-7
+    val, win, X = best_restart(torch.tensor([0.1, 0.9, 0.3], dtype=torch.float64), torch.arange(6.0).reshape(3, 1, 2), torch.arange(3))
+    assert win == 1 and float(val) == 0.9 and X.tolist() == [[2.0, 3.0]]

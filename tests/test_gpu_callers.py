@@ -108,8 +108,9 @@ def test_eval_mode_mll_is_the_joint_predictive_log_density(cuda_device):
     assert abs(float(got) - float(want)) < REL * abs(float(want))
 
 
-def test_reference_trainer_mirror(cuda_device, tmp_path):
-    from hdbo_benchmark_b200.training_gps import filter_close_points, pairwise_distances, train_exact_gp_model
+def test_reference_trainer_protocol(cuda_device, tmp_path):
+    from hdbo_benchmark_b200.distances import filter_close_points, pairwise_distances
+    from harness.adam_trainer import fit_with_adam
 
     g = torch.Generator().manual_seed(0)
     x = torch.rand(60, 5, generator=g, dtype=torch.float64)
@@ -124,15 +125,15 @@ def test_reference_trainer_mirror(cuda_device, tmp_path):
     # Adam + early stopping loop of the reference on a small problem
     X, y, ls, os_, nz, mu = O.synthetic_problem(80, 5, "prior", 1e-2)
     model = _plain_model(X[:60], y[:60], torch.ones(5), 1.0, 0.05, 0.0)
-    model, lik, it, had_nans = train_exact_gp_model(model, model.likelihood, X[:60], y[:60], X[60:], y[60:], n_points=60,
-                                                    n_dimensions=5, patience=5, max_nr_iterations=25, verbose=False, models_dir=tmp_path)
-    assert not had_nans and it >= 5 and not model.training
-    assert list(tmp_path.glob("model_model_npoints_60_ndim_5.pt"))
+    ckpt = tmp_path / "model_model_npoints_60_ndim_5.pt"
+    it, diverged = fit_with_adam(model, (X[:60], y[:60]), (X[60:], y[60:]), patience=5, max_iterations=25, checkpoint=ckpt)
+    assert not diverged and it >= 5 and not model.training
+    assert ckpt.exists() and set(torch.load(ckpt)) == set(model.state_dict())
 
 
 def test_solver_step_contract_runs_end_to_end(cuda_device):
     from hdbo_benchmark_b200 import gp_modules as G
-    from hdbo_benchmark_b200.solvers import LineBO, VanillaBayesianOptimization
+    from harness.poli_solvers import LineBO, VanillaBayesianOptimization
 
     d = 4
     opt = np.full(d, 0.3)

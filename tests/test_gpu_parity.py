@@ -154,7 +154,7 @@ def test_branch_free_sqrt_exp_match_the_library(cuda_device):
     """csrc/fast_math.cuh (used by every distance -> kernel epilogue) against torch's float64 sqrt / exp."""
     from hdbo_benchmark_b200 import _lib
 
-    lib = _lib.load()
+    lib = _lib.load_dev()   # test hooks live in libhdbo_b200_dev.so, not in the product library
     g = torch.Generator().manual_seed(0)
     x = torch.cat([
         torch.rand(100000, generator=g, dtype=torch.float64) * 50.0,
@@ -176,7 +176,7 @@ def test_fp64_lean_sqrt_exp_of_the_int8_cross_kernel(cuda_device):
     """sqrt_pos_cubic / exp_neg_tab_inrange (csrc/fast_math.cuh; 5 and 10 FP64 instructions) against torch's float64 sqrt / exp."""
     from hdbo_benchmark_b200 import _lib
 
-    lib = _lib.load()
+    lib = _lib.load_dev()
     g = torch.Generator().manual_seed(1)
     x = torch.cat([
         torch.rand(200000, generator=g, dtype=torch.float64) * 60.0,

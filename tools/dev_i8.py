@@ -54,14 +54,12 @@ for mode in ("f64", "i8"):
     out = {"acq": torch.empty(1, m, dtype=torch.float64, device=dev)}
     for _ in range(2):
         gp.posterior_acq(Z, _lib.ACQ_LOGEI, 1.0, want_mean=False, want_var=False, out=out)
-    lib.hdbo_profile_enable(1)
+    gp.attach_timeline(4096)
     e[2].record()
     for _ in range(3):
         gp.posterior_acq(Z, _lib.ACQ_LOGEI, 1.0, want_mean=False, want_var=False, out=out)
     e[3].record(); torch.cuda.synchronize()
-    import ctypes as C
-    ms = (C.c_double * 2)(); cnt = (C.c_int64 * 2)()
-    lib.hdbo_profile_collect(ms, cnt); lib.hdbo_profile_enable(0)
+    tl = gp.collect_timeline()
     t = e[2].elapsed_time(e[3]) / 3
     print(json.dumps({"mode": mode, "fit_ms": e[0].elapsed_time(e[1]), "pool_ms": t, "evals_per_s": m / t * 1e3,
-                      "cross_ms": ms[0] / 3, "var_ms": ms[1] / 3, "launches": [cnt[0], cnt[1]], "flag": gp.i8_flag()}), flush=True)
+                      "phases_ms": {k: v[0] / 3 for k, v in tl.items()}, "flag": gp.i8_flag()}), flush=True)

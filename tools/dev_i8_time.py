@@ -15,12 +15,11 @@ gp.set_hyper(ls.to(dev), os_, nz, mu); gp.fit()
 out = {"acq": torch.empty(1, m, dtype=torch.float64, device=dev)}
 for _ in range(2):
     gp.posterior_acq(Z, _lib.ACQ_LOGEI, 1.0, want_mean=False, want_var=False, out=out)
-lib.hdbo_profile_enable(1)
+gp.attach_timeline(4096)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(3):
     gp.posterior_acq(Z, _lib.ACQ_LOGEI, 1.0, want_mean=False, want_var=False, out=out)
 e1.record(); torch.cuda.synchronize()
-ms = (C.c_double * 2)(); cnt = (C.c_int64 * 2)()
-lib.hdbo_profile_collect(ms, cnt); lib.hdbo_profile_enable(0)
-print(json.dumps({"pool_ms": e0.elapsed_time(e1) / 3, "cross_ms": ms[0] / 3, "var_ms": ms[1] / 3, "flag": gp.i8_flag()}))
+tl = gp.collect_timeline()
+print(json.dumps({"pool_ms": e0.elapsed_time(e1) / 3, "phases_ms": {k: v[0] / 3 for k, v in tl.items()}, "flag": gp.i8_flag()}))
