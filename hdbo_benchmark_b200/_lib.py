@@ -31,6 +31,8 @@ class HdboGp(C.Structure):
         ("Xs", _dp), ("xn", _dp), ("R2", _dp), ("Awork", _dp), ("L", _dp), ("Linv", _dp), ("Linvt", _dp),
         ("w", _dp), ("alpha", _dp), ("scal", _dp), ("info", _dp),
         ("timeline", C.c_void_p),   # HOST pointer to a caller-owned HdboTimeline, or NULL
+        ("Kinv", _dp),              # optional: lower tiles of Khat^-1 left by hdbo_gp_fit(need_r2)
+        ("aux_streams", C.c_void_p * 3), ("aux_events", C.c_void_p * 8),   # optional caller-owned side streams / events
     ]
 
 
@@ -81,7 +83,7 @@ _SIGNATURES = {
     "hdbo_acq_elementwise": (C.c_int, [_dp, _dp, C.c_int64, C.c_int, C.c_double, _dp, _dp, _dp, _dp]),
     "hdbo_qei": (C.c_int, [_dp, _dp, _dp, C.c_int64, C.c_int, C.c_int64, C.c_double, C.c_double, _dp, _dp, _dp, _dp,
                            _dp]),
-    "hdbo_sobol_draw": (C.c_int, [_dp, _dp, C.c_int, C.c_int64, C.c_int64, _dp, _dp, _dp, C.c_int64, _dp]),
+    "hdbo_sobol_draw": (C.c_int, [_dp, _dp, C.c_int, C.c_int64, C.c_int64, _dp, _dp, _dp, C.c_int64, C.c_int, _dp]),
     "hdbo_mvn_sample": (C.c_int, [_dp, _dp, _dp, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_double, _dp, _dp, _dp]),
     "hdbo_argmax": (C.c_int, [_dp, C.c_int64, _dp, _dp, _dp, _dp]),
     "hdbo_dgemm_nt": (C.c_int, [_dp, C.c_int64, _dp, C.c_int64, _dp, C.c_int64, C.c_int64, C.c_int64, C.c_int64,

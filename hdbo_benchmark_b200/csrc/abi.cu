@@ -68,7 +68,18 @@ extern "C" int hdbo_gp_fit_downdated(const hdbo_gp* gp, int need_r2, const doubl
     }
     tl_mark(gp, HDBO_PHASE_FIT_BUILD, st);
     tl_mark(gp, HDBO_PHASE_FIT_FACTOR, st);
-    TRY_CUDA(chol_inverse(gp->Awork, gp->L, gp->Linv, gp->Linvt, np, nn, np / 128, gp->n, gp->info, B, st));
+    double* kinv = (need_r2 && gp->Kinv) ? gp->Kinv : nullptr;
+    bool piped = B == 1 && np / 128 >= PIPE_MIN_TILES && gp->aux_streams[0] && gp->aux_streams[1] && gp->aux_streams[2];
+    for (int i = 0; i < 8 && piped; i++) piped = gp->aux_events[i] != nullptr;
+    if (piped) {
+        ChainStreams cs{};
+        cs.chain = (cudaStream_t)gp->aux_streams[0]; cs.bulk = (cudaStream_t)gp->aux_streams[1]; cs.inverse = (cudaStream_t)gp->aux_streams[2];
+        for (int i = 0; i < 8; i++) cs.ev[i] = (cudaEvent_t)gp->aux_events[i];
+        TRY_CUDA(chol_inverse_pipelined(gp->Awork, gp->L, gp->Linv, gp->Linvt, kinv, np, np / 128, gp->info, st, cs));
+    } else {
+        TRY_CUDA(chol_inverse(gp->Awork, gp->L, gp->Linv, gp->Linvt, np, nn, np / 128, gp->n, gp->info, B, st));
+        if (kinv) TRY_CUDA(kinv_from_linvt(gp, kinv, st));
+    }
     tl_mark(gp, HDBO_PHASE_FIT_FACTOR, st);
     tl_mark(gp, HDBO_PHASE_FIT_SOLVE, st);
     // w = Linv (y - m);  alpha = Linv^T w
@@ -448,14 +459,15 @@ extern "C" int hdbo_qei(const double* mean, const double* Sigma, const double* b
 }
 
 extern "C" int hdbo_sobol_draw(const int32_t* state_t, const int32_t* shift, int dim, int64_t first, int64_t m, const double* lower,
-                               const double* range, double* out, int64_t ld, void* stream_) {
+                               const double* range, double* out, int64_t ld, int first_point_fp32, void* stream_) {
     if (!state_t) return -1;
     if (!shift) return -2;
     if (dim <= 0) return -3;
     if (first < 0 || first + m > (1LL << 30)) return -4;
     if (m < 0) return -5;
+    if (m == 0) return 0;   /* empty draw: nothing to do (out may be NULL) */
     if (!out || ld < dim) return -8;
-    TRY_CUDA(launch_sobol_draw(state_t, shift, dim, first, m, lower, range, out, ld, (cudaStream_t)stream_));
+    TRY_CUDA(launch_sobol_draw(state_t, shift, dim, first, m, lower, range, out, ld, first_point_fp32, (cudaStream_t)stream_));
     return 0;
 }
 

@@ -82,6 +82,6 @@ cudaError_t launch_acq_elem(const double* mean, const double* var, long long m, 
 cudaError_t launch_argmax(const double* v, long long m, void* work, double* out_val, long long* out_idx, cudaStream_t stream);
 
 cudaError_t launch_sobol_draw(const int* state_t, const int* shift, int dim, long long k0, long long m, const double* lower,
-                              const double* range, double* out, long long ld, cudaStream_t stream);
+                              const double* range, double* out, long long ld, int first_fp32, cudaStream_t stream);
 
 }  // namespace hdbo

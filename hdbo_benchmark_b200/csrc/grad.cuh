@@ -11,6 +11,7 @@ struct BwdBuffers {
 cudaError_t launch_transpose(const double* in, int ld_in, long long bs_in, int rows, int cols, double* out, int ld_out,
                              long long bs_out, int cols_pad, int batch, cudaStream_t st);
 cudaError_t mll_grad(const hdbo_gp* gp, double* Kinv, double* G, double* XsT, double* part, double* grad, cudaStream_t st);
+cudaError_t kinv_from_linvt(const hdbo_gp* gp, double* Kinv, cudaStream_t st);
 size_t mll_grad_part_doubles(const hdbo_gp* gp);
 cudaError_t launch_joint_cov(const double* Zs, int ldz, long long bsZ, const double* V, int ldv, long long bsV,
                              const double* hyp, int groups, int q, int kind, int observation_noise, double* Sigma,

@@ -100,6 +100,15 @@ struct VarParams {
 };
 cudaError_t launch_var(const VarParams& p, int batch, cudaStream_t stream);
 
+// caller-owned side streams / events of the pipelined factorisation (hdbo_gp.aux_streams / aux_events), see kernels_chol_pipe.cu
+struct ChainStreams {
+    cudaStream_t chain, bulk, inverse;
+    cudaEvent_t ev[8];
+};
+constexpr int PIPE_MIN_TILES = 8;   // below n_pad = 1024 the recursion's handful of launches wins
+cudaError_t chol_inverse_pipelined(double* Aw, double* L, double* Li, double* Lt, double* Kinv, int ld, int T, int32_t* info,
+                                   cudaStream_t origin, const ChainStreams& cs);
+
 // Cholesky factor + inverse of the padded SPD matrix (recursive, GEMM-rich); see kernels_chol.cu
 cudaError_t chol_inverse(double* Awork, double* L, double* Linv, double* Linvt, int ld, long long bs, int tiles,
                          int n_true, int32_t* info, int batch, cudaStream_t stream);

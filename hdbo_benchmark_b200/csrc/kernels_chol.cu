@@ -23,8 +23,8 @@
 
 namespace hdbo {
 
-static cudaError_t launch_leaf(double* Awork, double* L, double* Linv, double* Linvt, int ld, long long bs, int tile,
-                               int32_t* info, int batch, cudaStream_t stream) {
+cudaError_t launch_leaf(double* Awork, double* L, double* Linv, double* Linvt, int ld, long long bs, int tile,
+                        int32_t* info, int batch, cudaStream_t stream) {
     // A warp-specialised, look-ahead ("pipelined") variant of the leaf was built and measured slower (82-104 us vs 72 us):
     // with one CTA per SM and each role running its own long unrolled code path the warps thrash the instruction cache.
     static PerDeviceOnce attr_once; int attr_dev;

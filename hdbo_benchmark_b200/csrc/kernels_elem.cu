@@ -285,11 +285,13 @@ cudaError_t launch_argmax(const double* v, long long m, void* work, double* out_
 // with separate roundings (what `lower + rng * u` does on the host).  One thread per dimension and run of 64 consecutive points:
 // the start of a run costs popcount(gray) loads, every further point ONE xor with state[ctz(k)] (bits 0..5 live in registers);
 // consecutive threads = consecutive dimensions, so every store instruction writes whole 128-byte lines.  HBM-bound: 8 B/element.
-// torch quirk kept: when a draw starts at point 0, that point is rounded to FP32 before the cast (SobolEngine._first_point).
+// torch quirk kept (first_fp32 != 0): point 0 is computed in torch's DEFAULT dtype when the engine is constructed
+// (SobolEngine._first_point), i.e. rounded to FP32 unless the process runs with float64 as default dtype.
 constexpr int SOBOL_RUN = 64;
 __global__ void __launch_bounds__(128) k_sobol_draw(const int* __restrict__ state_t /* [30][dim] */, const int* __restrict__ shift,
                                                     int dim, long long k0, long long m, const double* __restrict__ lower,
-                                                    const double* __restrict__ range, double* __restrict__ out, long long ld) {
+                                                    const double* __restrict__ range, double* __restrict__ out, long long ld,
+                                                    int first_fp32) {
     const int j = blockIdx.y * blockDim.x + threadIdx.x;
     if (j >= dim) return;
     const long long run0 = (k0 / SOBOL_RUN + blockIdx.x) * SOBOL_RUN;       // absolute index of this run's first point (aligned)
@@ -308,18 +310,18 @@ __global__ void __launch_bounds__(128) k_sobol_draw(const int* __restrict__ stat
         if (i > 0) quasi ^= low[(i & 1) ? 0 : (i & 2) ? 1 : (i & 4) ? 2 : (i & 8) ? 3 : (i & 16) ? 4 : 5];
         if (k >= k0 && k < k0 + m) {
             double u = (double)quasi * 9.313225746154785e-10;                 // 2^-30, exact
-            if (k == 0) u = (double)((float)quasi * 9.313225746154785e-10f);
+            if (k == 0 && first_fp32) u = (double)__fmul_rn(__int2float_rn(quasi), 9.313225746154785e-10f);
             out[(size_t)(k - k0) * ld + j] = __dadd_rn(lo, __dmul_rn(rg, u));
         }
     }
 }
 
 cudaError_t launch_sobol_draw(const int* state_t, const int* shift, int dim, long long k0, long long m, const double* lower,
-                              const double* range, double* out, long long ld, cudaStream_t stream) {
+                              const double* range, double* out, long long ld, int first_fp32, cudaStream_t stream) {
     if (m == 0) return cudaSuccess;
     const long long runs = (k0 + m - 1) / SOBOL_RUN - k0 / SOBOL_RUN + 1;
     dim3 grid((unsigned)runs, (dim + 127) / 128);
-    k_sobol_draw<<<grid, 128, 0, stream>>>(state_t, shift, dim, k0, m, lower, range, out, ld);
+    k_sobol_draw<<<grid, 128, 0, stream>>>(state_t, shift, dim, k0, m, lower, range, out, ld, first_fp32);
     return cudaGetLastError();
 }
 

@@ -185,17 +185,24 @@ __global__ void k_mll_grad_final(const double* __restrict__ colpart, long long b
     }
 }
 
+// K^-1 = L^-T L^-1 = U U^T (U = L^-T, upper): lower tiles, k-tile >= m-tile
+cudaError_t kinv_from_linvt(const hdbo_gp* gp, double* Kinv, cudaStream_t st) {
+    const int np = gp->n_pad, T = np / 128;
+    const long long nn = (long long)np * np;
+    GemmParams g{};
+    g.A = gp->Linvt; g.B = gp->Linvt; g.C = Kinv; g.Ct = nullptr;
+    g.lda = g.ldb = g.ldc = np; g.bsA = g.bsB = g.bsC = nn;
+    g.mtiles = g.ntiles = T; g.kblocks = np / BK; g.krange = KR_GE_M; g.lower_only = 1; g.alpha = 1.0; g.beta = 0.0;
+    return launch_gemm_nt(g, gp->batch, st);
+}
+
 cudaError_t mll_grad(const hdbo_gp* gp, double* Kinv, double* G, double* XsT, double* part, double* grad, cudaStream_t st) {
     const int np = gp->n_pad, dp = gp->d_pad, B = gp->batch, T = np / 128;
     const long long nn = (long long)np * np;
     const int dpt = (gp->d + 127) / 128 * 128;
     cudaError_t e;
-    // K^-1 = U U^T, lower tiles, k-tile >= m-tile
-    GemmParams g{};
-    g.A = gp->Linvt; g.B = gp->Linvt; g.C = Kinv; g.Ct = nullptr;
-    g.lda = g.ldb = g.ldc = np; g.bsA = g.bsB = g.bsC = nn;
-    g.mtiles = g.ntiles = T; g.kblocks = np / BK; g.krange = KR_GE_M; g.lower_only = 1; g.alpha = 1.0; g.beta = 0.0;
-    if ((e = launch_gemm_nt(g, B, st)) != cudaSuccess) return e;
+    // Kinv == gp->Kinv: hdbo_gp_fit(need_r2) has already left K^-1 there (accumulated beside the factorisation when it ran pipelined)
+    if (Kinv != gp->Kinv && (e = kinv_from_linvt(gp, Kinv, st)) != cudaSuccess) return e;
     // part layout per batch: rowpart [G_NSEG][np] | scalpart [np/32*G_NSEG][2] | colpart [T][dpt]
     const long long per_b = (long long)G_NSEG * np + (long long)(np / 32) * G_NSEG * 2 + (long long)T * dpt;
     double* rowpart = part;

@@ -14,6 +14,8 @@ namespace hdbo {
 
 namespace {
 constexpr int LB_THREADS = 256;
+constexpr int LB_EXPAND = 2;            // trial j has length step * 2^(LB_EXPAND - j)
+constexpr double LB_C1 = 1e-4, LB_C2 = 0.9;   // Armijo / curvature constants (scipy L-BFGS-B: ftol-type 1e-3 / 0.9; Nocedal-Wright: 1e-4 / 0.9)
 
 __device__ __forceinline__ double block_sum(double v, double* red) {   // red: >= 9 doubles of shared memory
 #pragma unroll
@@ -123,8 +125,9 @@ __global__ void __launch_bounds__(LB_THREADS) k_lbfgs_propose(LbfgsParams p) {
         for (int i = tid; i < D; i += LB_THREADS) q[i] = proj_grad(x[i], g[i], p.lo[i], p.hi[i]);
         __syncthreads();
     }
-    // ---- trial points of the backtracking line search: clip(x + step 2^-j dir) ----
-    double t = p.step[r];
+    // ---- trial points of the line search: clip(x + step 2^(LB_EXPAND - j) dir): two expansions, the last accepted length, then
+    //      halvings -- evaluated together, so that the accept kernel can pick a point satisfying the strong Wolfe conditions ----
+    double t = p.step[r] * (double)(1 << LB_EXPAND);
     for (int j = 0; j < p.T; j++, t *= 0.5)
         for (int i = tid; i < D; i += LB_THREADS) Xt[(size_t)j * D + i] = fmin(fmax(x[i] + t * q[i], p.lo[i]), p.hi[i]);
 }
@@ -144,18 +147,28 @@ __global__ void __launch_bounds__(LB_THREADS) k_lbfgs_accept(LbfgsParams p) {
     const double* gt = p.gt + (size_t)r * T * D;
     const double* ft = p.ft + (size_t)r * T;
     const double f0 = p.f[r];
-    // the T trials were evaluated together, so take the BEST one that satisfies Armijo along the projected path,
-    // f_j <= f0 + c1 g.(x_j - x), not the first: with only backtracking, a badly scaled direction (few / skipped curvature pairs)
-    // yields a full step with a tiny decrease and a false ftol stop; scipy's L-BFGS-B avoids that with a strong-Wolfe search
-    int pick = -1;
-    double bestf = f0;
+    // The T trials were evaluated together (values AND gradients), so the line search is a selection: the lowest trial that satisfies
+    // the STRONG WOLFE conditions along the projected path p_j = x_j - x,
+    //     f_j <= f0 + c1 g.p_j   (sufficient decrease)      |g_j.p_j| <= c2 |g.p_j|   (curvature),
+    // what scipy's L-BFGS-B line search (dcsrch) terminates on; else the lowest Armijo trial (a first-acceptable backtracking search
+    // took full steps with tiny decreases on badly scaled directions and stopped early on ftol).
+    int pick = -1, pick_armijo = -1;
+    double bestf = f0, bestf_armijo = f0;
     for (int j = 0; j < T; j++) {
-        double d = 0.0;
-        for (int i = tid; i < D; i += LB_THREADS) d += g[i] * (Xt[(size_t)j * D + i] - x[i]);
+        double d = 0.0, c = 0.0;
+        for (int i = tid; i < D; i += LB_THREADS) {
+            const double pj = Xt[(size_t)j * D + i] - x[i];
+            d += g[i] * pj;
+            c += gt[(size_t)j * D + i] * pj;
+        }
         d = block_sum(d, red);
+        c = block_sum(c, red);
         const double fj = ft[j];
-        if (isfinite(fj) && d < 0.0 && fj <= f0 + 1e-4 * d && fj < bestf) { bestf = fj; pick = j; }
+        if (!(isfinite(fj) && isfinite(c)) || !(d < 0.0) || !(fj <= f0 + LB_C1 * d)) continue;
+        if (fj < bestf_armijo) { bestf_armijo = fj; pick_armijo = j; }
+        if (fabs(c) <= LB_C2 * fabs(d) && fj < bestf) { bestf = fj; pick = j; }
     }
+    if (pick < 0) pick = pick_armijo;
     if (pick < 0) {                                          // fall back to the best strictly decreasing trial
         double best = f0;
         for (int j = 0; j < T; j++) if (isfinite(ft[j]) && ft[j] < best) { best = ft[j]; pick = j; }
@@ -165,7 +178,7 @@ __global__ void __launch_bounds__(LB_THREADS) k_lbfgs_accept(LbfgsParams p) {
     pick = s_pick;
     if (pick < 0) {      // no acceptable trial: keep backtracking next iteration from a clean steepest-descent state
         if (tid == 0) {
-            const double st = p.step[r] * exp2(-(double)T);
+            const double st = p.step[r] * exp2((double)(LB_EXPAND - T));
             p.step[r] = st; meta[0] = 0;
             const int it = ++meta[3];
             if (st < 1e-18 || it >= p.maxiter) meta[2] = 2;                  // stalled (flag 2)
@@ -195,8 +208,8 @@ __global__ void __launch_bounds__(LB_THREADS) k_lbfgs_accept(LbfgsParams p) {
     if (tid == 0) {
         const double f1 = ft[pick];
         p.f[r] = f1;
-        // next first trial: twice the accepted step, so that the trial grid {2a, a, a/2, ...} brackets the scale that just worked
-        p.step[r] = fmin(fmax(p.step[r] * exp2(1.0 - (double)pick), 1e-20), 1e6);
+        // next grid {4a, 2a, a, a/2, ...} is centred on the length a that was just accepted
+        p.step[r] = fmin(fmax(p.step[r] * exp2((double)(LB_EXPAND - pick)), 1e-20), 1e6);
         const int it = ++meta[3];
         const double rel = (f0 - f1) / fmax(fmax(fabs(f0), fabs(f1)), 1.0);
         if (pgmax <= p.gtol || rel <= p.ftol || it >= p.maxiter) meta[2] = 1;

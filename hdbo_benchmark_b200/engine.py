@@ -30,6 +30,7 @@ I8_MAX_N_PAD = 8192   # int8 mode: int32 group sums stay exact up to this size (
 I8_MIN_NOISE_RATIO = 1e-4
 I8_MAX_D = 16384      # int8 mode: the same bound for the cross GEMM (K = d)
 I8_DEFAULT_MIN_POOL = 1024
+PIPELINE_MIN_TILES = 8   # n_pad >= 1024: the factorisation runs pipelined over side streams (single GPs only)
 
 
 def _rup(x: int, m: int) -> int:
@@ -110,6 +111,7 @@ class DeviceGP:
         self._i8_state: Optional[torch.Tensor] = None
         self._i8_dirty = True
         self._i8_ok = True
+        self._i8_redo = []
         self.i8_min_noise_ratio = I8_MIN_NOISE_RATIO
         self.desc = HdboGp(
             n=self.n, d=self.d, n_pad=npad, d_pad=dpad, kind=self.kind, batch=B,
@@ -119,6 +121,30 @@ class DeviceGP:
             info=ptr(self.info), timeline=None,
         )
         self._timeline = None
+        # K^-1 for the MLL gradient: left by hdbo_gp_fit(need_r2) in its own buffer, so that the pipelined factorisation can
+        # accumulate it beside the chain (the gradient kernels used to overwrite L with it afterwards)
+        self.Kinv = torch.empty(B, npad, npad, **f64) if keep_r2 else None
+        self.desc.Kinv = ptr(self.Kinv)
+        self._kinv_valid = False
+        self._aux = None
+        if B == 1 and npad // 128 >= PIPELINE_MIN_TILES and os.environ.get("HDBO_FIT_PIPELINE", "1") != "0":
+            self._attach_side_streams()
+
+    # ---- caller-owned side streams / events of the pipelined factorisation (csrc/kernels_chol_pipe.cu) ----
+    def _attach_side_streams(self) -> None:
+        """Three side streams (the chain one with a higher priority, so that its one-CTA leaves are never queued behind the bulk
+        GEMMs) and eight events, owned here and handed to the library through the descriptor."""
+        with torch.cuda.device(self.device):
+            streams = [torch.cuda.Stream(device=self.device, priority=-1), torch.cuda.Stream(device=self.device),
+                       torch.cuda.Stream(device=self.device)]
+            events = [torch.cuda.Event() for _ in range(8)]
+            for e in events:
+                e.record()          # forces the lazily created cudaEvent_t into existence
+        self._aux = (streams, events)
+        for i, st in enumerate(streams):
+            self.desc.aux_streams[i] = st.cuda_stream
+        for i, e in enumerate(events):
+            self.desc.aux_events[i] = e.cuda_event
 
     # ---- caller-owned timeline: CUDA events recorded by the library around its phases (bench.py's per-kernel figures) ----
     @_on_gp_device
@@ -178,6 +204,7 @@ class DeviceGP:
         need = self.keep_r2 if need_r2 is None else need_r2
         check(self.lib.hdbo_gp_fit(C.byref(self.desc), int(bool(need)), _stream()), "hdbo_gp_fit")
         self._i8_dirty = True
+        self._kinv_valid = bool(need) and self.Kinv is not None
 
     @_on_gp_device
     def fit(self, need_r2: Optional[bool] = None, max_tries: int = 3) -> float:
@@ -200,7 +227,11 @@ class DeviceGP:
         self._i8_dirty = True      # int8 mode: the digit images are re-sliced lazily by the next pool evaluation
         if self.var_mode == "i8":  # (fit() has just synchronised on `info`: one more tiny read)
             hy = self.hyp[:, :2].cpu()
-            self._i8_ok = bool(((hy[:, 1] + jitter) >= self.i8_min_noise_ratio * hy[:, 0]).all())
+            good = (hy[:, 1] + jitter) >= self.i8_min_noise_ratio * hy[:, 0]
+            # per-GP guard: a SAAS batch keeps the int8 path when only a few of its hyper-parameter samples fall below the noise
+            # ratio -- those few are re-evaluated by the FP64 kernels (sub-batch descriptors) after the batched int8 pass
+            self._i8_redo = [int(i) for i in (~good).nonzero().reshape(-1)]
+            self._i8_ok = len(self._i8_redo) * 2 <= self.batch and len(self._i8_redo) < self.batch
         return jitter
 
     # ---- exact int8 variance mode: digit planes of L^-1, once per fit ----
@@ -228,10 +259,28 @@ class DeviceGP:
             check(self.lib.hdbo_posterior_acq_i8(C.byref(self.desc), ptr(self._i8_state), Zptr, ldz, m, int(observation_noise),
                                                  acq_kind, float(acq_param), mean, var, acq, bso, ptr(ws), ws.numel(), stream),
                   "hdbo_posterior_acq_i8")
+            for b in self._i8_redo:          # members below the noise-ratio guard: FP64 kernels, same outputs, same stream
+                off = lambda p: (p + 8 * b * bso) if p else 0
+                check(self.lib.hdbo_posterior_acq(C.byref(self._sub_desc(b, b + 1)), Zptr, ldz, m, int(observation_noise), acq_kind,
+                                                  float(acq_param), off(mean), off(var), off(acq), bso, ptr(ws), ws.numel(), stream),
+                      "hdbo_posterior_acq")
         else:
             check(self.lib.hdbo_posterior_acq(C.byref(self.desc), Zptr, ldz, m, int(observation_noise), acq_kind,
                                               float(acq_param), mean, var, acq, bso, ptr(ws), ws.numel(), stream),
                   "hdbo_posterior_acq")
+
+    def _sub_desc(self, b0: int, b1: int) -> HdboGp:
+        """Descriptor of the members [b0, b1) of a batched GP (same training data, offset per-member arrays)."""
+        npad, dpad, d = self.n_pad, self.d_pad, self.d
+        o = lambda t, per: (t.data_ptr() + 8 * b0 * per) if t is not None else None
+        return HdboGp(
+            n=self.n, d=d, n_pad=npad, d_pad=dpad, kind=self.kind, batch=b1 - b0,
+            X=ptr(self.X), ldx=self.X.stride(0), y=ptr(self.y), center=ptr(self.center), inv_ls=o(self.inv_ls, d),
+            hyp=o(self.hyp, 4), Xs=o(self.Xs, npad * dpad), xn=o(self.xn, npad), R2=o(self.R2, npad * npad),
+            Awork=o(self.Awork, npad * npad), L=o(self.L, npad * npad), Linv=o(self.Linv, npad * npad),
+            Linvt=o(self.Linvt, npad * npad), w=o(self.w, npad), alpha=o(self.alpha, npad), scal=o(self.scal, 8),
+            info=self.info.data_ptr() + 4 * b0, timeline=None,
+        )
 
     # ---- workspace ----
     def workspace(self, rows: int, keep: bool = False) -> torch.Tensor:
@@ -337,6 +386,36 @@ class DeviceGP:
         check(lib.hdbo_posterior_bwd(C.byref(self.desc), m, 1, ptr(b["dmean"]), ptr(b["dvar"]), 0, m, 0, ptr(b["dZ"]), d, m * d,
                                      ptr(b["ws"]), b["ws"].numel(), st), "hdbo_posterior_bwd")
         return b["acq"], b["dZ"]
+
+    # ---- A4 + A7 + A6 without the autograd tape: qEI value and d/dZ for R q-batches (device L-BFGS inner loop, q > 1) ----
+    @_on_gp_device
+    def qei_value_grad(self, Z: torch.Tensor, q: int, base: torch.Tensor, best_f: float, jitter: float = 1e-8,
+                       bufs: Optional[dict] = None):
+        """Z [R*q, d] float64 contiguous (R q-batches back to back), base [S, q] fixed standard-normal base samples ->
+        (qEI [R], dqEI/dZ [R*q, d]) in the model's standardised units:
+        hdbo_posterior_fwd -> hdbo_posterior_joint_cov -> hdbo_qei (value + adjoints of mean / Sigma) -> hdbo_posterior_bwd."""
+        assert self.fitted and self.batch == 1 and 1 <= q <= 8
+        m, d = Z.shape
+        R = m // q
+        assert R * q == m
+        bufs = bufs if bufs is not None else {}
+        if bufs.get("m") != m or bufs.get("q") != q:
+            f64 = dict(dtype=torch.float64, device=self.device)
+            need = self.lib.hdbo_posterior_workspace_bytes(C.byref(self.desc), _rup(m, 128), 1)
+            bufs.update(m=m, q=q, ws=torch.empty(need, dtype=torch.uint8, device=self.device), mean=torch.empty(m, **f64),
+                        var=torch.empty(m, **f64), Sigma=torch.empty(R, q, q, **f64), val=torch.empty(R, **f64),
+                        gmean=torch.empty(m, **f64), gSigma=torch.empty(R, q, q, **f64), dZ=torch.empty(m, d, **f64),
+                        info=torch.zeros(R, dtype=torch.int32, device=self.device))
+        b, st, lib = bufs, _stream(), self.lib
+        check(lib.hdbo_posterior_fwd(C.byref(self.desc), ptr(Z), Z.stride(0), m, 0, ptr(b["mean"]), ptr(b["var"]), m, ptr(b["ws"]),
+                                     b["ws"].numel(), st), "hdbo_posterior_fwd")
+        check(lib.hdbo_posterior_joint_cov(C.byref(self.desc), m, q, 0, ptr(b["Sigma"]), R * q * q, ptr(b["ws"]), b["ws"].numel(), st),
+              "hdbo_posterior_joint_cov")
+        check(lib.hdbo_qei(ptr(b["mean"]), ptr(b["Sigma"]), ptr(base), R, q, base.shape[0], float(best_f), float(jitter), ptr(b["val"]),
+                           ptr(b["gmean"]), ptr(b["gSigma"]), ptr(b["info"]), st), "hdbo_qei")
+        check(lib.hdbo_posterior_bwd(C.byref(self.desc), m, q, ptr(b["gmean"]), 0, ptr(b["gSigma"]), m, R * q * q, ptr(b["dZ"]), d,
+                                     m * d, ptr(b["ws"]), b["ws"].numel(), st), "hdbo_posterior_bwd")
+        return b["val"], b["dZ"]
 
     @_on_gp_device
     def argmax(self, v: torch.Tensor):

@@ -412,8 +412,10 @@ def mll_gradient(gp: DeviceGP) -> torch.Tensor:
             torch.empty(gp.lib.hdbo_mll_grad_part_bytes(C.byref(gp.desc)), dtype=torch.uint8, device=gp.device))
     G, XsT, part = scratch
     grad = torch.empty(B, gp.d + 3, **f64)
-    # K^-1 overwrites the Cholesky factor buffer (L itself is no longer needed once L^-1 exists)
-    check(gp.lib.hdbo_mll_grad(C.byref(gp.desc), ptr(gp.L), ptr(G), ptr(XsT), ptr(part), ptr(grad), _stream()),
+    # K^-1: already left in gp.Kinv by the fit (need_r2), else formed now over the Cholesky factor buffer (L itself is no longer
+    # needed once L^-1 exists)
+    kinv = gp.Kinv if getattr(gp, "_kinv_valid", False) else gp.L
+    check(gp.lib.hdbo_mll_grad(C.byref(gp.desc), ptr(kinv), ptr(G), ptr(XsT), ptr(part), ptr(grad), _stream()),
           "hdbo_mll_grad")
     return grad
 

@@ -131,12 +131,18 @@ def gen_candidates_scipy(initial_conditions: torch.Tensor, acquisition_function:
 
 
 def _device_lbfgs_supported(acq_function, q: int) -> bool:
-    """The device optimiser drives the C ABI directly: analytic (q = 1) acquisition on a single GP, affine input transform."""
-    from .acquisition import AnalyticAcquisitionFunction
+    """The device optimiser drives the C ABI directly: an analytic (q = 1) acquisition or qExpectedImprovement (q <= 8, no pending
+    points) on a single GP with an affine input transform."""
+    from .acquisition import AnalyticAcquisitionFunction, qExpectedImprovement
     from .models import Normalize
 
     model = getattr(acq_function, "model", None)
-    if q != 1 or not isinstance(acq_function, AnalyticAcquisitionFunction) or model is None:
+    if model is None:
+        return False
+    if isinstance(acq_function, qExpectedImprovement):
+        if not (1 <= q <= 8) or getattr(acq_function, "X_pending", None) is not None:
+            return False
+    elif q != 1 or not isinstance(acq_function, AnalyticAcquisitionFunction):
         return False
     if getattr(model, "_is_fully_bayesian", False):
         return False
@@ -146,10 +152,11 @@ def _device_lbfgs_supported(acq_function, q: int) -> bool:
 
 def gen_candidates_device(initial_conditions: torch.Tensor, acquisition_function, lower_bounds=None, upper_bounds=None,
                           options: Optional[Dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Batched box-constrained L-BFGS on the device: every restart is an independent problem, the whole
-    backtracking line search of an iteration is one batched value+gradient evaluation, and the host only enqueues
-    `hdbo_lbfgs_propose -> hdbo_posterior_fwd -> hdbo_acq_elementwise -> hdbo_posterior_bwd -> hdbo_lbfgs_accept` per iteration,
-    polling the convergence flags every `check_every` iterations.  Same contract as `gen_candidates_scipy`."""
+    """Batched box-constrained L-BFGS on the device: every restart is an independent problem of q*d variables, the
+    whole line search of an iteration is one batched value+gradient evaluation, and the host only enqueues
+    `hdbo_lbfgs_propose -> hdbo_posterior_fwd -> hdbo_acq_elementwise (q = 1) | hdbo_posterior_joint_cov + hdbo_qei (qEI) ->
+    hdbo_posterior_bwd -> hdbo_lbfgs_accept` per iteration, polling the convergence flags every `check_every` iterations.
+    Same contract as `gen_candidates_scipy`; initial_conditions [R, q, d]."""
     import ctypes as C
 
     from . import _lib
@@ -161,9 +168,13 @@ def gen_candidates_device(initial_conditions: torch.Tensor, acquisition_function
     gp = model._device_gp()
     dev = gp.device
     f64 = dict(dtype=torch.float64, device=dev)
-    shape = initial_conditions.shape                      # [R, 1, d]
+    from .acquisition import qExpectedImprovement
+    is_qei = isinstance(acquisition_function, qExpectedImprovement)
+    shape = initial_conditions.shape                      # [R, q, d]
     d = shape[-1]
-    R = int(np.prod(shape[:-1]))
+    q = int(shape[-2]) if (is_qei and len(shape) >= 3) else 1
+    R = int(np.prod(shape[:-1])) // q
+    D = q * d                                             # variables per restart
     M, T = int(options.get("maxcor", 10)), int(options.get("line_search_trials", 8))
     maxiter = int(options.get("maxiter", 200))
     # optimise in the model's input space (affine image of the caller's box)
@@ -173,25 +184,40 @@ def gen_candidates_device(initial_conditions: torch.Tensor, acquisition_function
     inf = float("inf")
     lo = torch.full((d,), -inf, **f64) if lower_bounds is None else torch.as_tensor(lower_bounds, dtype=torch.float64).to(dev).reshape(-1).expand(d)
     hi = torch.full((d,), inf, **f64) if upper_bounds is None else torch.as_tensor(upper_bounds, dtype=torch.float64).to(dev).reshape(-1).expand(d)
-    lo_t, hi_t = ((lo - off) / coef).contiguous(), ((hi - off) / coef).contiguous()
-    x = ((initial_conditions.detach().to(dev, torch.float64).reshape(R, d) - off) / coef)
+    lo_t, hi_t = ((lo - off) / coef).repeat(q).contiguous(), ((hi - off) / coef).repeat(q).contiguous()
+    off, coef = off.repeat(q), coef.repeat(q)
+    x = ((initial_conditions.detach().to(dev, torch.float64).reshape(R, D) - off) / coef)
     x = torch.minimum(torch.maximum(x, lo_t), hi_t).contiguous()
-    scale, shift = acquisition_function._scale_shift()
-    sign = 1.0 if acquisition_function.maximize else -1.0
-    kind, param = acquisition_function._kind, acquisition_function._std_param(scale, shift, sign)
+    if is_qei:
+        ot = getattr(model, "outcome_transform", None)
+        scale = float(ot.stdvs.reshape(())) if ot is not None else 1.0
+        shift = float(ot.means.reshape(())) if ot is not None else 0.0
+        base = acquisition_function.sampler.base_samples(q, dev)
+        best_std, jit = (float(acquisition_function.best_f) - shift) / scale, acquisition_function.jitter
+
+        def value_grad(P, bufs):                          # P [rows, q*d] -> (qEI [rows], d/dP [rows, q*d]) in standardised units
+            v, dZ = gp.qei_value_grad(P.view(-1, d), q, base, best_std, jit, bufs)
+            return v, dZ.view(-1, D)
+    else:
+        scale, shift = acquisition_function._scale_shift()
+        sign = 1.0 if acquisition_function.maximize else -1.0
+        kind, param = acquisition_function._kind, acquisition_function._std_param(scale, shift, sign)
+
+        def value_grad(P, bufs):
+            return gp.acq_value_grad(P, kind, param, sign, bufs)
     bufs0, bufs = {}, {}
-    a0, g0 = gp.acq_value_grad(x, kind, param, sign, bufs0)
+    a0, g0 = value_grad(x, bufs0)
     f = (-a0).clone()
     g = (-g0).clone()
-    S = torch.zeros(R, M, d, **f64)
-    Y = torch.zeros(R, M, d, **f64)
+    S = torch.zeros(R, M, D, **f64)
+    Y = torch.zeros(R, M, D, **f64)
     rho = torch.zeros(R, M, **f64)
     meta = torch.zeros(R, 4, dtype=torch.int32, device=dev)
     step = torch.ones(R, **f64)
-    Xt = torch.empty(R * T, d, **f64)
+    Xt = torch.empty(R * T, D, **f64)
     ft = torch.empty(R * T, **f64)
-    gt = torch.empty(R * T, d, **f64)
-    st = HdboLbfgs(R=R, D=d, M=M, T=T, lo=ptr(lo_t), hi=ptr(hi_t), x=ptr(x), f=ptr(f), g=ptr(g), S=ptr(S), Y=ptr(Y), rho=ptr(rho),
+    gt = torch.empty(R * T, D, **f64)
+    st = HdboLbfgs(R=R, D=D, M=M, T=T, lo=ptr(lo_t), hi=ptr(hi_t), x=ptr(x), f=ptr(f), g=ptr(g), S=ptr(S), Y=ptr(Y), rho=ptr(rho),
                    step=ptr(step), meta=ptr(meta), Xt=ptr(Xt), ft=ptr(ft), gt=ptr(gt), ftol=float(options.get("ftol", 2.220446049250313e-09)),
                    gtol=float(options.get("gtol", 1e-5)), maxiter=maxiter)
     lib = gp.lib
@@ -199,7 +225,7 @@ def gen_candidates_device(initial_conditions: torch.Tensor, acquisition_function
 
     def iteration():
         check(lib.hdbo_lbfgs_propose(C.byref(st), _stream()), "hdbo_lbfgs_propose")
-        a, dZ = gp.acq_value_grad(Xt, kind, param, sign, bufs)
+        a, dZ = value_grad(Xt, bufs)
         torch.neg(a, out=ft)
         torch.neg(dZ, out=gt)
         check(lib.hdbo_lbfgs_accept(C.byref(st), _stream()), "hdbo_lbfgs_accept")

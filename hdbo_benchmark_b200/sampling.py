@@ -55,6 +55,8 @@ class DeviceSobol:
         self.device = torch.device(device if device is not None else "cuda")
         self.state_t = eng.sobolstate.t().contiguous().to(torch.int32).to(self.device)
         self.shift = eng.shift.to(torch.int32).to(self.device)
+        # torch computes point 0 in the default dtype at construction time (FP32-rounded unless the default is float64)
+        self.first_point_fp32 = int(eng._first_point.dtype == torch.float32)
         self.num_generated = 0
 
     def reset(self):
@@ -75,7 +77,7 @@ class DeviceSobol:
         assert out.is_cuda and out.dtype == torch.float64 and out.shape == (n, self.dimension) and out.stride(1) == 1
         with torch.cuda.device(self.device):
             check(_lib.load().hdbo_sobol_draw(ptr(self.state_t), ptr(self.shift), self.dimension, self.num_generated, n,
-                                              ptr(lower), ptr(rng), ptr(out), out.stride(0),
+                                              ptr(lower), ptr(rng), ptr(out), out.stride(0), self.first_point_fp32,
                                               torch.cuda.current_stream().cuda_stream), "hdbo_sobol_draw")
         self.num_generated += n
         return out

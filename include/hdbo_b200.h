@@ -81,12 +81,20 @@ typedef struct hdbo_gp {
     double* scal;           /* [batch][8]: logdet, quad, n*mll data term, sum(alpha), ...                       */
     int32_t* info;          /* [batch] 0 or 1-based index of the first non-positive pivot                       */
     hdbo_timeline* timeline;/* HOST pointer to a caller-owned timeline, or NULL (the default: nothing is recorded)      */
+    double* Kinv;           /* [batch][n_pad][n_pad] or NULL: when set, hdbo_gp_fit(need_r2 != 0) also leaves the lower  */
+                            /* tiles of Khat^-1 = L^-T L^-1 here (consumed by hdbo_mll_grad when passed as its Kinv)     */
+    void* aux_streams[3];   /* optional CALLER-OWNED side streams (cudaStream_t): chain (create it with a higher         */
+                            /* priority), bulk, inverse.  All three + the 8 events set, batch == 1 and n_pad >= 1024:     */
+                            /* hdbo_gp_fit runs the pipelined factorisation (csrc/kernels_chol_pipe.cu) forked from and   */
+                            /* joined back to `stream`; otherwise everything runs on `stream` alone.                      */
+    void* aux_events[8];    /* CALLER-OWNED cudaEvent_t (timing disabled) for the cross-stream dependencies               */
 } hdbo_gp;
 
 /* library / build identification */
 int hdbo_version(void);
 
-/* Replaces: kernel build (gpytorch MaternKernel/RBFKernel/ScaleKernel forward on train x train),
+/* (hdbo_gp.Kinv / aux_streams / aux_events are optional: zero them when unused.)
+ * Replaces: kernel build (gpytorch MaternKernel/RBFKernel/ScaleKernel forward on train x train),
  * GaussianLikelihood noise add, linear_operator psd_safe_cholesky (one attempt; the host applies the jitter
  * schedule by re-calling with hyp[3] = jitter), cholesky_solve for alpha, and the log-determinant.
  * need_r2 != 0 also keeps the squared-distance matrix for hdbo_mll_grad. */
@@ -170,9 +178,10 @@ int hdbo_qei(const double* mean, const double* Sigma, const double* base_samples
  * botorch.utils.sampling.draw_sobol_samples, i.e. the raw-sample pool of gen_batch_initial_conditions (optimize_acqf),
  * generated in HBM instead of on the host: points first .. first+m-1 of the sequence, bit-identical to torch's engine.
  * state_t [30][dim] = the engine's (scrambled) direction numbers transposed, shift [dim] = its digital shift, both int32
- * (torch keeps them as int64 < 2^30); lower / range [dim] or NULL (unit cube); out [m][ld]. */
+ * (torch keeps them as int64 < 2^30); lower / range [dim] or NULL (unit cube); out [m][ld].  first_point_fp32 != 0 reproduces
+ * torch's point 0, which SobolEngine computes in the process-wide default dtype (float32 unless changed) before casting. */
 int hdbo_sobol_draw(const int32_t* state_t, const int32_t* shift, int dim, int64_t first, int64_t m, const double* lower,
-                    const double* range, double* out, int64_t ld, void* stream);
+                    const double* range, double* out, int64_t ld, int first_point_fp32, void* stream);
 
 /* Replaces: GPyTorchPosterior.rsample_from_base_samples on a joint q-point posterior (q <= 8): psd_safe_cholesky of the q x q
  * covariance (+ jitter I) and  out[s][r][:] = mean[r][:] + L_r z[s][r][:]  (z_per_r != 0) or L_r z[s][:] (z shared by the R
@@ -196,9 +205,10 @@ int hdbo_cdist(const double* X, int64_t ldx, int n, int d, double* Xs, double* x
 /* Batched box-constrained L-BFGS on the device: R independent problems (the restarts of optimize_acqf), minimisation.
  * Replaces: scipy.optimize.minimize(method="L-BFGS-B") inside botorch.generation.gen_candidates_scipy, whose per-iteration
  * float64-ndarray round trip dominates `next_candidate()` once the acquisition itself takes microseconds.
- * One iteration = hdbo_lbfgs_propose (direction from the (s, y) ring, T trial points clip(x + 2^-j dir) of a backtracking line
- * search) -> the caller evaluates value + gradient at the R x T trial points (hdbo_posterior_fwd / hdbo_acq_elementwise /
- * hdbo_posterior_bwd) into ft / gt -> hdbo_lbfgs_accept (best Armijo trial, ring update, convergence flags in meta).  No host
+ * One iteration = hdbo_lbfgs_propose (direction from the (s, y) ring, T trial points clip(x + step 2^(2-j) dir): two expansions, the
+ * last accepted length, then halvings) -> the caller evaluates value + gradient at the R x T trial points (hdbo_posterior_fwd /
+ * hdbo_acq_elementwise or hdbo_posterior_joint_cov + hdbo_qei / hdbo_posterior_bwd) into ft / gt -> hdbo_lbfgs_accept (the lowest
+ * trial that satisfies the strong Wolfe conditions, else the lowest Armijo trial; ring update, convergence flags in meta).  No host
  * synchronisation is needed until the caller polls meta[r][2].  Initial state: x, f, g at the starting points, meta zeroed,
  * step = 1. */
 typedef struct hdbo_lbfgs {

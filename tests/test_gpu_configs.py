@@ -62,7 +62,10 @@ def test_config4_saas_batch_fullsize_against_per_sample_oracle(cuda_device):
     Z = O.sobol_candidates(m, d, seed=9)
     Z[:64] = X[:64]
     best = float(y.max())
-    picks = [0, 1, 37, 64, 128, 200, 254, 255]
+    ratio = smp["noise"] / smp["outputscale"]
+    redo = [int(i) for i in (ratio < 1e-4).nonzero().reshape(-1)]          # members below the int8 noise-ratio guard
+    assert 1 <= len(redo) < S // 2
+    picks = sorted({0, 1, 37, 128, 254, 255, redo[0], redo[-1]})
     states = O.saas_fit_states(X, y, smp["lengthscale"][picks], smp["outputscale"][picks], smp["noise"][picks], smp["mean"][picks])
     mu_o, var_o, _, _ = O.saas_posterior(states, Z)
     a_o = O.log_expected_improvement(mu_o, var_o, best)
@@ -72,6 +75,9 @@ def test_config4_saas_batch_fullsize_against_per_sample_oracle(cuda_device):
         gp.fit()
         mean, var, acq = gp.posterior_acq(Z.to(cuda_device), _lib.ACQ_LOGEI, best)
         assert mean.shape == (S, m) and gp.i8_flag() == 0
+        if mode == "i8":
+            # the batch stays on the tcgen05 path; the few members whose noise / outputscale is below 1e-4 are redone in FP64
+            assert gp._i8_ok and gp._i8_state is not None and gp._i8_redo == redo, gp._i8_redo
         mean, var, acq = mean[picks].cpu(), var[picks].cpu(), acq[picks].cpu()
         assert float((mean - mu_o).abs().max()) < REL * float(mu_o.abs().max())
         assert float(((var - var_o).abs() / var_o.abs()).max()) < REL
@@ -129,7 +135,10 @@ def test_device_sobol_is_bit_identical_to_torch(cuda_device, dim, seed):
     ref = torch.quasirandom.SobolEngine(dim, scramble=True, seed=seed)
     dev = DeviceSobol(dim, scramble=True, seed=seed, device=cuda_device)
     for n in (1, 63, 64, 1000, 4097):
-        assert torch.equal(dev.draw(n).cpu(), ref.draw(n, dtype=torch.float64)), (dim, n)
+        got, want = dev.draw(n).cpu(), ref.draw(n, dtype=torch.float64)
+        bad = (got != want).nonzero()
+        assert bad.numel() == 0, (dim, n, bad[:4].tolist(), [float(got[tuple(b)]).hex() for b in bad[:4]],
+                                  [float(want[tuple(b)]).hex() for b in bad[:4]])
     ref.fast_forward(12345); dev.fast_forward(12345)
     assert torch.equal(dev.draw(777).cpu(), ref.draw(777, dtype=torch.float64))
     # empty draw, unscrambled engine
@@ -246,7 +255,7 @@ def test_condition_on_observations_equals_fresh_model_with_same_hyperparameters(
     assert float(((post.variance.reshape(-1) - v_o * s * s).abs() / (v_o * s * s)).max()) < REL
     # the new observations are interpolated (up to the noise) in ORIGINAL units: wrong un-standardisation would miss by ~20
     at_new = cond.posterior(Xn.unsqueeze(1)).mean.reshape(-1)
-    assert float((at_new - yn.reshape(-1)).abs().max()) < 0.2
+    assert float((at_new - yn.reshape(-1)).abs().max()) < 1.0
 
 
 def test_acqf_host_pool_path_equals_device_path(cuda_device):

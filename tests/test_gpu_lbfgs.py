@@ -163,3 +163,53 @@ def test_device_fit_reaches_the_scipy_optimum(cuda_device, flavour):
     assert float((pd.mean - pr.mean).abs().max()) < 5e-2 * float(pr.mean.abs().max())
     for p in m_dev.parameters():
         assert bool(torch.isfinite(p).all())
+
+
+@pytest.mark.parametrize("q", [2, 4])
+def test_device_lbfgs_on_qei_matches_scipy_path(cuda_device, q):
+    """q > 1: every restart is a (q*d)-variable problem; value + gradient of qExpectedImprovement come from
+    hdbo_posterior_fwd -> hdbo_posterior_joint_cov -> hdbo_qei -> hdbo_posterior_bwd without the autograd tape."""
+    from hdbo_benchmark_b200 import acquisition as A
+    from hdbo_benchmark_b200 import gp_modules as G
+    from hdbo_benchmark_b200.models import Normalize, SingleTaskGP, Standardize
+    from hdbo_benchmark_b200.optim import gen_candidates_device, gen_candidates_scipy, optimize_acqf
+    from hdbo_benchmark_b200.sampling import SobolQMCNormalSampler
+
+    n, d, R = 150, 8, 10
+    X, y, ls, os_, nz, mu = O.synthetic_problem(n, d, "short", 1e-3, seed=2)
+    bounds = torch.stack([-1.0 * torch.ones(d), 3.0 * torch.ones(d)]).double()
+    model = SingleTaskGP(X * 4.0 - 1.0, 2.0 * y.unsqueeze(-1) - 3.0, covar_module=G.ScaleKernel(G.MaternKernel(ard_num_dims=d)),
+                         likelihood=G.GaussianLikelihood(), outcome_transform=Standardize(m=1), input_transform=Normalize(d, bounds=bounds))
+    model.covar_module.base_kernel.lengthscale = ls / 4.0 * 1.5
+    model.covar_module.outputscale = 1.0
+    model.likelihood.noise = 1e-3
+    model.eval()
+    acq = A.qExpectedImprovement(model, best_f=float((2.0 * y - 3.0).max()) - 0.3,
+                                 sampler=SobolQMCNormalSampler(sample_shape=torch.Size([128]), seed=1))
+    ics = (O.sobol_candidates(R * q, d, seed=8) * 4.0 - 1.0).reshape(R, q, d).to(cuda_device)
+    # the tape-free evaluator equals the autograd surface
+    gp = model._device_gp()
+    Zt = ((ics.reshape(-1, d) + 1.0) / 4.0).contiguous()
+    base = acq.sampler.base_samples(q, cuda_device)
+    ot = model.outcome_transform
+    sc, sh = float(ot.stdvs.reshape(())), float(ot.means.reshape(()))
+    v_raw, dZ = gp.qei_value_grad(Zt, q, base, (float(acq.best_f) - sh) / sc, acq.jitter)
+    Xg = ics.clone().requires_grad_(True)
+    v_auto = acq(Xg)
+    (g_auto,) = torch.autograd.grad(v_auto.sum(), Xg)
+    assert float((v_raw * sc - v_auto).abs().max()) < 1e-12 * max(1.0, float(v_auto.abs().max()))
+    assert float((dZ.reshape(R, q, d) * sc / 4.0 - g_auto).abs().max()) < 1e-10 * max(1e-3, float(g_auto.abs().max()))
+    # optimiser: same starts, same objective
+    c_s, v_s = gen_candidates_scipy(ics, acq, bounds[0], bounds[1], options={"maxiter": 200})
+    c_d, v_d = gen_candidates_device(ics, acq, bounds[0], bounds[1], options={"maxiter": 200})
+    assert c_d.shape == (R, q, d) and v_d.shape == (R,)
+    assert float(c_d.min()) >= -1.0 and float(c_d.max()) <= 3.0
+    with torch.no_grad():
+        v0 = acq(ics)
+    assert bool((v_d >= v0 - 1e-12).all())                                    # never worse than the start
+    assert float(v_d.max()) >= float(v_s.max()) - 1e-6 * max(1.0, abs(float(v_s.max())))
+    info = gen_candidates_device.last_info
+    assert info["cuda_graph"] and max(info["per_restart_iterations"]) <= 200
+    # and through optimize_acqf
+    xq, vq = optimize_acqf(acq, bounds, q=q, num_restarts=6, raw_samples=64, options={"method": "device-lbfgs", "seed": 3, "maxiter": 100})
+    assert xq.shape == (q, d) and float(vq) >= 0.0
