@@ -32,7 +32,7 @@ class HdboGp(C.Structure):
         ("w", _dp), ("alpha", _dp), ("scal", _dp), ("info", _dp),
         ("timeline", C.c_void_p),   # HOST pointer to a caller-owned HdboTimeline, or NULL
         ("Kinv", _dp),              # optional: lower tiles of Khat^-1 left by hdbo_gp_fit(need_r2)
-        ("aux_streams", C.c_void_p * 3), ("aux_events", C.c_void_p * 8),   # optional caller-owned side streams / events
+        ("aux_streams", C.c_void_p * 4), ("aux_events", C.c_void_p * 12),   # optional caller-owned side streams / events
     ]
 
 

@@ -51,7 +51,13 @@ extern "C" int hdbo_gp_fit_downdated(const hdbo_gp* gp, int need_r2, const doubl
     const int np = gp->n_pad, dp = gp->d_pad, B = gp->batch;
     const long long nn = (long long)np * np;
     TRY_CUDA(cudaMemsetAsync(gp->info, 0, sizeof(int32_t) * B, st));
+    bool piped = B == 1 && np / 128 >= PIPE_MIN_TILES;
+    for (int i = 0; i < 4 && piped; i++) piped = gp->aux_streams[i] != nullptr;
+    for (int i = 0; i < 12 && piped; i++) piped = gp->aux_events[i] != nullptr;
     tl_mark(gp, HDBO_PHASE_FIT_BUILD, st);
+    // pipelined factorisation: the unused UPPER tiles of Awork hold the running rows of L^-1 and must start at zero (the build
+    // below rewrites the lower tiles)
+    if (piped) TRY_CUDA(cudaMemsetAsync(gp->Awork, 0, sizeof(double) * (size_t)nn, st));
     TRY_CUDA(launch_scale_inputs(gp->X, (int)gp->ldx, 0, gp->n, gp->d, gp->center, gp->inv_ls, gp->d, gp->Xs, dp, np,
                                  (long long)np * dp, gp->xn, np, B, st));
     SymBuildParams sb{};
@@ -69,12 +75,11 @@ extern "C" int hdbo_gp_fit_downdated(const hdbo_gp* gp, int need_r2, const doubl
     tl_mark(gp, HDBO_PHASE_FIT_BUILD, st);
     tl_mark(gp, HDBO_PHASE_FIT_FACTOR, st);
     double* kinv = (need_r2 && gp->Kinv) ? gp->Kinv : nullptr;
-    bool piped = B == 1 && np / 128 >= PIPE_MIN_TILES && gp->aux_streams[0] && gp->aux_streams[1] && gp->aux_streams[2];
-    for (int i = 0; i < 8 && piped; i++) piped = gp->aux_events[i] != nullptr;
     if (piped) {
         ChainStreams cs{};
-        cs.chain = (cudaStream_t)gp->aux_streams[0]; cs.bulk = (cudaStream_t)gp->aux_streams[1]; cs.inverse = (cudaStream_t)gp->aux_streams[2];
-        for (int i = 0; i < 8; i++) cs.ev[i] = (cudaEvent_t)gp->aux_events[i];
+        cs.chain = (cudaStream_t)gp->aux_streams[0]; cs.bulk = (cudaStream_t)gp->aux_streams[1];
+        cs.inverse = (cudaStream_t)gp->aux_streams[2]; cs.kinv = (cudaStream_t)gp->aux_streams[3];
+        for (int i = 0; i < 12; i++) cs.ev[i] = (cudaEvent_t)gp->aux_events[i];
         TRY_CUDA(chol_inverse_pipelined(gp->Awork, gp->L, gp->Linv, gp->Linvt, kinv, np, np / 128, gp->info, st, cs));
     } else {
         TRY_CUDA(chol_inverse(gp->Awork, gp->L, gp->Linv, gp->Linvt, np, nn, np / 128, gp->n, gp->info, B, st));

@@ -47,6 +47,7 @@ struct GemmParams {
     int krange;                                               // KRange
     int lower_only;                                           // only tiles with m-tile >= n-tile (grid.x enumerates them)
     double alpha, beta;
+    int tile_hint;                                            // 0: choose the CTA tile by the launch's tile count; 32 / 64 / 128: force it
 };
 
 // kernel value k(r^2) and derivative dk/dr^2 for unit outputscale.  kind: 0 Matern-5/2, 1 RBF.
@@ -102,8 +103,8 @@ cudaError_t launch_var(const VarParams& p, int batch, cudaStream_t stream);
 
 // caller-owned side streams / events of the pipelined factorisation (hdbo_gp.aux_streams / aux_events), see kernels_chol_pipe.cu
 struct ChainStreams {
-    cudaStream_t chain, bulk, inverse;
-    cudaEvent_t ev[8];
+    cudaStream_t chain, bulk, inverse, kinv;
+    cudaEvent_t ev[12];
 };
 constexpr int PIPE_MIN_TILES = 8;   // below n_pad = 1024 the recursion's handful of launches wins
 cudaError_t chol_inverse_pipelined(double* Aw, double* L, double* Li, double* Lt, double* Kinv, int ld, int T, int32_t* info,

@@ -53,23 +53,38 @@ __global__ void __launch_bounds__(G::THREADS) k_gemm_nt(GemmParams p) {
     const int b = blockIdx.z;
     int kb0, kb1;
     krange_blocks(p.krange, bm, bn, p.kblocks, G::KB_PER_TM, G::KB_PER_TN, kb0, kb1);
-    typename G::Frag acc; acc.zero();
-    G::mainloop(p.A + b * p.bsA + (size_t)bm * G::TM * p.lda, p.lda, p.B + b * p.bsB + (size_t)bn * G::TN * p.ldb, p.ldb,
-                kb0, kb1, smem, acc);
     double* C = p.C + b * p.bsC;
     double* Ct = p.Ct ? p.Ct + b * p.bsCt : nullptr;
+    typename G::Frag acc;
+    // beta != 0 (the rank-128 updates of the factorisation: K = 128, so a tile is 8 k-blocks long and the C round trip is a visible
+    // part of it): C is read INTO the accumulators before the mainloop -- the loads overlap the pipeline fill instead of following the
+    // last DMMA -- as (beta / alpha) C, so that the result is alpha (A B^T + (beta / alpha) C); exact for the +-1 factors used here
+    if (p.beta != 0.0) {
+        const double f = p.beta / p.alpha;
+#pragma unroll
+        for (int mt = 0; mt < G::MT; mt++) {
+            const int i = bm * G::TM + G::frag_row(mt);
+#pragma unroll
+            for (int nt = 0; nt < G::NT; nt++) {
+                const double2 c = *reinterpret_cast<const double2*>(C + (size_t)i * p.ldc + bn * G::TN + G::frag_col(nt));
+                acc.v[mt][nt][0] = f * c.x; acc.v[mt][nt][1] = f * c.y;
+            }
+        }
+    } else {
+        acc.zero();
+    }
+    G::mainloop(p.A + b * p.bsA + (size_t)bm * G::TM * p.lda, p.lda, p.B + b * p.bsB + (size_t)bn * G::TN * p.ldb, p.ldb,
+                kb0, kb1, smem, acc);
 #pragma unroll
     for (int mt = 0; mt < G::MT; mt++) {
         const int i = bm * G::TM + G::frag_row(mt);
 #pragma unroll
         for (int nt = 0; nt < G::NT; nt++) {
             const int j = bn * G::TN + G::frag_col(nt);
-            double2* dst = reinterpret_cast<double2*>(C + (size_t)i * p.ldc + j);
             double2 o;
             o.x = p.alpha * acc.v[mt][nt][0];
             o.y = p.alpha * acc.v[mt][nt][1];
-            if (p.beta != 0.0) { double2 c = *dst; o.x += p.beta * c.x; o.y += p.beta * c.y; }
-            *dst = o;
+            *reinterpret_cast<double2*>(C + (size_t)i * p.ldc + j) = o;
             if (Ct) { Ct[(size_t)j * p.ldct + i] = o.x; Ct[(size_t)(j + 1) * p.ldct + i] = o.y; }
         }
     }
@@ -100,6 +115,9 @@ cudaError_t launch_gemm_nt(const GemmParams& p, int batch, cudaStream_t stream) 
     const long long t128 = (p.lower_only ? (long long)p.mtiles * (p.mtiles + 1) / 2 : (long long)p.mtiles * p.ntiles) * batch;
     static const long long t128_min = [] { const char* e = getenv("HDBO_GEMM_T128_MIN"); return e ? atoll(e) : 600LL; }();
     static const long long t64_min = [] { const char* e = getenv("HDBO_GEMM_T64_MIN"); return e ? atoll(e) : 60LL; }();
+    if (p.tile_hint == 128) return launch_gemm_cfg<G128>(p, batch, stream);
+    if (p.tile_hint == 64) return launch_gemm_cfg<G64>(p, batch, stream);
+    if (p.tile_hint == 32) return launch_gemm_cfg<G32>(p, batch, stream);
     if (t128 >= t128_min) return launch_gemm_cfg<G128>(p, batch, stream);
     if (t128 >= t64_min) return launch_gemm_cfg<G64>(p, batch, stream);
     return launch_gemm_cfg<G32>(p, batch, stream);

@@ -132,12 +132,12 @@ class DeviceGP:
 
     # ---- caller-owned side streams / events of the pipelined factorisation (csrc/kernels_chol_pipe.cu) ----
     def _attach_side_streams(self) -> None:
-        """Three side streams (the chain one with a higher priority, so that its one-CTA leaves are never queued behind the bulk
-        GEMMs) and eight events, owned here and handed to the library through the descriptor."""
+        """Four side streams with descending priorities -- chain (its one-CTA leaves must never queue behind the bulk GEMMs), bulk (the
+        chain waits for it every step), inverse, K^-1 (no deadlines: they fill what is left) -- and twelve events, owned here and
+        handed to the library through the descriptor."""
         with torch.cuda.device(self.device):
-            streams = [torch.cuda.Stream(device=self.device, priority=-1), torch.cuda.Stream(device=self.device),
-                       torch.cuda.Stream(device=self.device)]
-            events = [torch.cuda.Event() for _ in range(8)]
+            streams = [torch.cuda.Stream(device=self.device, priority=p) for p in (-3, -2, -1, 0)]
+            events = [torch.cuda.Event() for _ in range(12)]
             for e in events:
                 e.record()          # forces the lazily created cudaEvent_t into existence
         self._aux = (streams, events)
