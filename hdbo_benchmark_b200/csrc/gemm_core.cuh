@@ -65,11 +65,21 @@ struct GemmT {
                 for (int j = 0; j < NT; j++) { v[i][j][0] = 0.0; v[i][j][1] = 0.0; }
         }
     };
+    // thread index inside the GEMM's own group of THREADS threads: a CTA may hold several independent groups (warp groups of the
+    // multi-pipeline side kernel, kernels_gemm.cu); THREADS is a power of two, so this is the identity for single-group CTAs
+    static_assert((THREADS & (THREADS - 1)) == 0, "THREADS must be a power of two");
+    static __device__ __forceinline__ int group_tid() { return threadIdx.x & (THREADS - 1); }
     static __device__ __forceinline__ int frag_row(int mt) {
-        return ((threadIdx.x >> 5) / WN) * (TM / WM) + mt * 8 + ((threadIdx.x & 31) >> 2);
+        return ((group_tid() >> 5) / WN) * (TM / WM) + mt * 8 + ((threadIdx.x & 31) >> 2);
     }
     static __device__ __forceinline__ int frag_col(int nt) {
-        return ((threadIdx.x >> 5) % WN) * (TN / WN) + nt * 8 + ((threadIdx.x & 3) << 1);
+        return ((group_tid() >> 5) % WN) * (TN / WN) + nt * 8 + ((threadIdx.x & 3) << 1);
+    }
+    // barrier over the group: BAR = 0 -> the whole CTA (__syncthreads), BAR > 0 -> named barrier BAR over THREADS threads
+    template <int BAR>
+    static __device__ __forceinline__ void group_sync() {
+        if (BAR == 0) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(THREADS) : "memory");
     }
 
     template <int ROWS>
@@ -82,9 +92,10 @@ struct GemmT {
     }
 
     // gA / gB point at the first row of the operand slabs (column 0).  k-blocks [kb_begin, kb_end).
+    template <int BAR = 0>
     static __device__ __forceinline__ void mainloop(const double* __restrict__ gA, int lda, const double* __restrict__ gB,
                                                     int ldb, int kb_begin, int kb_end, double* smem, Frag& acc) {
-        const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+        const int tid = group_tid(), lane = tid & 31, warp = tid >> 5;
         const int wm = warp / WN, wn = warp % WN;
         double* sA = smem;
         double* sB = smem + STAGES * A_ELEMS;
@@ -106,7 +117,7 @@ struct GemmT {
         static_assert(TM * CH % THREADS == 0 && TN * CH % THREADS == 0, "slab chunks must divide evenly over the threads");
         for (int it = 0; it < nkb; it++) {
             cp_async_wait<STAGES - 2>();
-            __syncthreads();
+            group_sync<BAR>();
             // The cp.async for stage it+STAGES-1 are NOT issued here in one burst: measured (tools/dmma_order.cu), a burst of
             // 8 LDGSTS per thread right after the barrier costs 10 % of DMMA throughput (32.4 vs 36.0 TFLOP/s) because all
             // warps queue on the LSU while the tensor pipe drains.  They are spread over the k4 steps, behind the LDS.
@@ -147,7 +158,7 @@ struct GemmT {
             slot = (slot + 1 == STAGES) ? 0 : slot + 1;
         }
         cp_async_wait<0>();
-        __syncthreads();
+        group_sync<BAR>();
     }
 };
 

@@ -101,6 +101,17 @@ struct VarParams {
 };
 cudaError_t launch_var(const VarParams& p, int batch, cudaStream_t stream);
 
+// the rank-256 updates one pair of columns of the pipelined factorisation makes available, as a single persistent launch
+// (k_side_updates, kernels_gemm.cu)
+struct SideParams {
+    double *Aw, *L, *Lt, *Kinv;
+    int ld, T;
+    int k0, kblocks;             // first column tile of the pair, contraction length in 16-blocks (16: a pair, 8: a single column)
+    int c0, r0, jmax;            // first tile column of the bulk region; first tile row / last tile column (j) of the inverse region
+    int n_bulk, n_inv, n_kinv;   // job counts of the three regions (n_kinv: lower tiles a >= b of a (jmax+1)^2 block)
+};
+cudaError_t launch_side_updates(const SideParams& p, int max_ctas, cudaStream_t stream);
+
 // caller-owned side streams / events of the pipelined factorisation (hdbo_gp.aux_streams / aux_events), see kernels_chol_pipe.cu
 struct ChainStreams {
     cudaStream_t chain, bulk, inverse, kinv;

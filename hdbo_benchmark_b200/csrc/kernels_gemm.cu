@@ -124,6 +124,68 @@ cudaError_t launch_gemm_nt(const GemmParams& p, int batch, cudaStream_t stream) 
 }
 
 // --------------------------------------------------------------------------------------------------------------
+// All rank-256 updates that one PAIR of columns (k0, k0+1) of the pipelined factorisation (kernels_chol_pipe.cu) makes available, as
+// ONE persistent launch (kblocks = 8: a single trailing column, K = 128):
+//   bulk     A(i, j)    -= L(i, k0..) L(j, k0..)^T          c0 <= j <= i < T        (trailing update of the factorisation)
+//   inverse  W^T(j, i)  -= L^-T(j, k0..) L(i, k0..)^T       j <= jmax, r0 <= i < T  (running rows of L^-1, transposed, upper tiles of Awork)
+//   K^-1     Kinv(a, b) += L^-T(a, k0..) L^-T(b, k0..)^T    b <= a <= jmax          (MLL gradient only)
+// The three loads add up to ~T^2/2 tile updates per pair.  What was measured on the way here (profiles/r02_fit_trace_*.jsonl,
+// r02_pipe_prof_*.jsonl): as separate launches on separate streams they fought the chain's one-CTA leaf for SMs (a leaf needs a whole
+// SM's shared memory: 10-40 us of queueing per step); as K = 128 updates they are L2 / HBM-bound, not DMMA-bound -- 8 flop per byte of
+// tile traffic, 24 us per 4.2 MFLOP tile = 65 % of the SM's DMMA rate, and three independent 64x64 pipelines per SM did not change
+// that -- hence K = 256 (pairs of columns: 16 flop per byte).  The grid is capped below the SM count: one 122 KB CTA per SM, so the
+// remaining SMs stay free for the chain; every CTA walks a strided list of jobs, C is read into the accumulators before each mainloop.
+__global__ void __launch_bounds__(NTHREADS, 1) k_side_updates(SideParams p) {
+    extern __shared__ __align__(16) double smem[];
+    const int total = p.n_bulk + p.n_inv + p.n_kinv;
+    const size_t ld = (size_t)p.ld;
+    auto tile = [&](double* base, int r, int c) { return base + (size_t)r * 128 * ld + (size_t)c * 128; };
+    for (int job = blockIdx.x; job < total; job += gridDim.x) {
+        const double *A, *B; double* C; double sign;
+        if (job < p.n_bulk) {
+            int bi, bj; lower_tile_decode(job, bi, bj);
+            const int i = p.c0 + bi, j = p.c0 + bj;
+            A = tile(p.L, i, p.k0); B = tile(p.L, j, p.k0); C = tile(p.Aw, i, j); sign = -1.0;
+        } else if (job < p.n_bulk + p.n_inv) {
+            const int q = job - p.n_bulk;                          // (j, i): j fastest so that neighbouring CTAs share B = L(i, k0..)
+            const int j = q % (p.jmax + 1), i = p.r0 + q / (p.jmax + 1);
+            A = tile(p.Lt, j, p.k0); B = tile(p.L, i, p.k0); C = tile(p.Aw, j, i); sign = -1.0;
+        } else {
+            int a, b; lower_tile_decode(job - p.n_bulk - p.n_inv, a, b);
+            A = tile(p.Lt, a, p.k0); B = tile(p.Lt, b, p.k0); C = tile(p.Kinv, a, b); sign = 1.0;
+        }
+        Frag acc;
+#pragma unroll
+        for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+                const double2 c = *reinterpret_cast<const double2*>(C + (size_t)frag_row(mt) * ld + frag_col(nt));
+                acc.v[mt][nt][0] = sign * c.x; acc.v[mt][nt][1] = sign * c.y;
+            }
+        gemm_nt_mainloop(A, p.ld, B, p.ld, 0, p.kblocks, smem, acc);
+#pragma unroll
+        for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++)
+                *reinterpret_cast<double2*>(C + (size_t)frag_row(mt) * ld + frag_col(nt)) =
+                    make_double2(sign * acc.v[mt][nt][0], sign * acc.v[mt][nt][1]);
+    }
+}
+
+cudaError_t launch_side_updates(const SideParams& p, int max_ctas, cudaStream_t stream) {
+    const int total = p.n_bulk + p.n_inv + p.n_kinv;
+    if (total <= 0) return cudaSuccess;
+    static PerDeviceOnce attr_once; int attr_dev;
+    if (attr_once.pending(attr_dev)) {
+        cudaError_t e = cudaFuncSetAttribute(k_side_updates, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_once.mark(attr_dev);
+    }
+    k_side_updates<<<total < max_ctas ? total : max_ctas, NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------------------------------
 // K*(Z, X) tile: r2 = |z|^2 + |x|^2 - 2 z.x (clamped at 0), k(r2) * outputscale, masked beyond n; plus the partial
 // dot with alpha over this tile's 128 columns (posterior mean), written to meanpart[bn][row].
 template <int KIND>
@@ -192,8 +254,10 @@ cudaError_t launch_cross(const CrossParams& p, int batch, cudaStream_t stream) {
 
 // --------------------------------------------------------------------------------------------------------------
 // Train covariance, lower tiles only: Khat = outputscale*k(r2) + (noise + jitter) on the diagonal; rows/cols >= n are
-// the identity so that the padded matrix stays SPD and its factor / inverse are block-diagonal with I.  R2 gets the
-// full symmetric squared-distance matrix (diagonal exactly 0, padding 0) when requested (needed by the MLL gradient).
+// the identity so that the padded matrix stays SPD and its factor / inverse are block-diagonal with I.  When the MLL gradient is
+// wanted, the `R2` state buffer gets dk/dr^2 (unit outputscale; padding 0) on the SAME lower tiles -- the only other function of the
+// distances the gradient needs, already at hand here (the first version stored r^2, mirrored with strided 8-byte stores, and
+// the gradient kernel evaluated exp / sqrt a second time for all n^2 entries).
 // Templated on the tile configuration: few-tile problems (the small n of a BO loop: 6 tiles of 128x128 at n_pad = 384) run on
 // 32x32 / 64x64 CTA tiles so that the FP64 kernel epilogue spreads over the SMs (p.tiles counts tiles of G::TM).
 template <class G>
@@ -226,13 +290,10 @@ __global__ void __launch_bounds__(G::THREADS) k_sym_build(SymBuildParams p) {
                 kernel_eval(p.kind, r2, k, dk);
                 const bool valid = (i < p.n) && (j < p.n);
                 kv[e] = valid ? os * k + ((i == j) ? (noise + jitter) : 0.0) : ((i == j) ? 1.0 : 0.0);
-                rv[e] = valid ? r2 : 0.0;
+                rv[e] = valid ? dk : 0.0;
             }
             *reinterpret_cast<double2*>(Kh + (size_t)i * p.ldk + j0) = make_double2(kv[0], kv[1]);
-            if (R2) {
-                *reinterpret_cast<double2*>(R2 + (size_t)i * p.ldk + j0) = make_double2(rv[0], rv[1]);
-                if (bm != bn) { R2[(size_t)j0 * p.ldk + i] = rv[0]; R2[(size_t)(j0 + 1) * p.ldk + i] = rv[1]; }
-            }
+            if (R2) *reinterpret_cast<double2*>(R2 + (size_t)i * p.ldk + j0) = make_double2(rv[0], rv[1]);
         }
     }
 }

@@ -44,29 +44,31 @@ cudaError_t launch_transpose(const double* in, int ld_in, long long bs_in, int r
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// G[i][j] = (alpha_i alpha_j - Kinv_ij) * (-2 os dk/dr2(R2_ij)) for i,j < n, else 0.  Kinv holds lower tiles only; the
-// upper half is read transposed through shared memory.  Grid: (n_pad/32 row stripes, NSEG column segments, batch).
-// Per (stripe, segment): partial row sums of G, partial sum(W o K), partial tr(W).
+// G[i][j] = (alpha_i alpha_j - Kinv_ij) * (-2 os DK_ij) for i,j < n, else 0.  Kinv and DK (= dk/dr^2 for unit outputscale, left by the
+// kernel build) hold lower tiles only; the upper half is read transposed through shared memory.  HBM-bound: no kernel evaluation here
+// (the first version re-derived k and dk from the squared distances: 16.7 M FP64 exp / sqrt at n = 4096).
+// Grid: (n_pad/32 row stripes, NSEG column segments, batch).  Per (stripe, segment): partial row sums of G and partial tr(W);
+// sum(W o K), the other trace the gradient needs, follows from  sum(W o K) = r^T alpha - n - noise tr(W)  (Khat alpha = r).
 constexpr int G_NSEG = 4;
-__global__ void __launch_bounds__(256) k_mll_G(const double* __restrict__ Kinv, const double* __restrict__ R2, int ld,
+__global__ void __launch_bounds__(256) k_mll_G(const double* __restrict__ Kinv, const double* __restrict__ DK, int ld,
                                                long long bsM, const double* __restrict__ alpha, long long bsv,
-                                               const double* __restrict__ hyp, int n, int n_pad, int kind,
+                                               const double* __restrict__ hyp, int n, int n_pad,
                                                double* __restrict__ G, double* __restrict__ rowpart /*[B][NSEG][n_pad]*/,
                                                double* __restrict__ scalpart /*[B][stripes*NSEG][2]*/) {
-    __shared__ double t[32][33];
-    __shared__ double red[32];
+    __shared__ double t[32][33], td[32][33];
+    __shared__ double red[8];
     const int b = blockIdx.z, stripe = blockIdx.x, seg = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double os = hyp[b * 4 + 0];
+    const double m2os = -2.0 * hyp[b * 4 + 0];
     const double* Ki = Kinv + b * bsM;
-    const double* R = R2 + b * bsM;
+    const double* Dk = DK + b * bsM;
     const double* al = alpha + b * bsv;
     double* Gg = G + b * bsM;
     const int ntile = n_pad / 32;
     const int per = (ntile + G_NSEG - 1) / G_NSEG;
     const int t0 = seg * per, t1 = min(ntile, t0 + per);
     double rs[4] = {0, 0, 0, 0};
-    double swk = 0.0, trw = 0.0;
+    double trw = 0.0;
     double ai[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) ai[r] = al[stripe * 32 + warp * 4 + r];
@@ -75,7 +77,11 @@ __global__ void __launch_bounds__(256) k_mll_G(const double* __restrict__ Kinv, 
         if (upper) {
             __syncthreads();
 #pragma unroll
-            for (int r = 0; r < 4; r++) t[warp * 4 + r][lane] = Ki[(size_t)(tj * 32 + warp * 4 + r) * ld + stripe * 32 + lane];
+            for (int r = 0; r < 4; r++) {
+                const size_t o = (size_t)(tj * 32 + warp * 4 + r) * ld + stripe * 32 + lane;
+                t[warp * 4 + r][lane] = Ki[o];
+                td[warp * 4 + r][lane] = Dk[o];
+            }
             __syncthreads();
         }
         const int j = tj * 32 + lane;
@@ -83,17 +89,14 @@ __global__ void __launch_bounds__(256) k_mll_G(const double* __restrict__ Kinv, 
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             const int i = stripe * 32 + warp * 4 + r;
-            double kin;
-            if (upper) kin = t[lane][warp * 4 + r];
-            else if (tj < stripe || lane <= warp * 4 + r) kin = Ki[(size_t)i * ld + j];
-            else kin = Ki[(size_t)j * ld + i];   // upper part of a diagonal 32x32 tile (stored tile is a full lower-tile member)
+            double kin, dk;
+            if (upper) { kin = t[lane][warp * 4 + r]; dk = td[lane][warp * 4 + r]; }
+            else if (tj < stripe || lane <= warp * 4 + r) { kin = Ki[(size_t)i * ld + j]; dk = Dk[(size_t)i * ld + j]; }
+            else { kin = Ki[(size_t)j * ld + i]; dk = Dk[(size_t)j * ld + i]; }   // upper part of a diagonal 32x32 tile (stored tiles are full)
             double g = 0.0;
             if (i < n && j < n) {
                 const double W = ai[r] * aj - kin;
-                double k, dk;
-                kernel_eval(kind, R[(size_t)i * ld + j], k, dk);
-                g = W * (-2.0 * os * dk);
-                swk = fma(W, os * k, swk);
+                g = W * (m2os * dk);
                 if (i == j) trw += W;
             }
             Gg[(size_t)i * ld + j] = g;
@@ -105,15 +108,15 @@ __global__ void __launch_bounds__(256) k_mll_G(const double* __restrict__ Kinv, 
         double s = warp_sum_g(rs[r]);
         if (lane == 0) rowpart[((size_t)b * G_NSEG + seg) * n_pad + stripe * 32 + warp * 4 + r] = s;
     }
-    swk = warp_sum_g(swk); trw = warp_sum_g(trw);
+    trw = warp_sum_g(trw);
     __syncthreads();
-    if (lane == 0) { red[warp] = swk; red[8 + warp] = trw; }
+    if (lane == 0) red[warp] = trw;
     __syncthreads();
     if (threadIdx.x == 0) {
-        double a = 0, c = 0;
-        for (int w = 0; w < 8; w++) { a += red[w]; c += red[8 + w]; }
+        double c = 0;
+        for (int w = 0; w < 8; w++) c += red[w];
         size_t o = ((size_t)b * gridDim.x * G_NSEG + (size_t)stripe * G_NSEG + seg) * 2;
-        scalpart[o] = a; scalpart[o + 1] = c;
+        scalpart[o] = 0.0; scalpart[o + 1] = c;
     }
 }
 
@@ -159,7 +162,7 @@ constexpr int GXA_MAX_SPLITS = 4;
 
 __global__ void k_mll_grad_final(const double* __restrict__ colpart, long long bscol, int mtiles, int dpt,
                                  const double* __restrict__ scalpart, int nscal, const double* __restrict__ inv_ls,
-                                 const double* __restrict__ hyp, const double* __restrict__ scal, int d,
+                                 const double* __restrict__ hyp, const double* __restrict__ scal, int d, int n_true,
                                  double* __restrict__ grad) {
     const int b = blockIdx.x;
     for (int k = threadIdx.x; k < d; k += blockDim.x) {
@@ -179,6 +182,9 @@ __global__ void k_mll_grad_final(const double* __restrict__ colpart, long long b
     if (threadIdx.x == 0) {
         a = 0.0; c = 0.0;
         for (int w = 0; w < (int)(blockDim.x >> 5); w++) { a += red[0][w]; c += red[1][w]; }
+        // sum(W o K) over the n x n block:  alpha^T K alpha - tr(Khat^-1 K)  with  K = Khat - s I  (s = noise + jitter), Khat alpha = r
+        //   = r^T alpha - s alpha^T alpha - n + s tr(Khat^-1) = quad - n - s tr(W)
+        a = scal[b * 8 + 1] - (double)n_true - (hyp[b * 4 + 1] + hyp[b * 4 + 3]) * c;
         grad[(size_t)b * (d + 3) + d] = 0.5 * a / hyp[b * 4 + 0];
         grad[(size_t)b * (d + 3) + d + 1] = 0.5 * c;
         grad[(size_t)b * (d + 3) + d + 2] = scal[b * 8 + 3];
@@ -210,7 +216,7 @@ cudaError_t mll_grad(const hdbo_gp* gp, double* Kinv, double* G, double* XsT, do
     double* colpart = scalpart + (long long)B * (np / 32) * G_NSEG * 2;
     (void)per_b;
     dim3 gg(np / 32, G_NSEG, B);
-    k_mll_G<<<gg, 256, 0, st>>>(Kinv, gp->R2, np, nn, gp->alpha, np, gp->hyp, gp->n, np, gp->kind, G, rowpart, scalpart);
+    k_mll_G<<<gg, 256, 0, st>>>(Kinv, gp->R2, np, nn, gp->alpha, np, gp->hyp, gp->n, np, G, rowpart, scalpart);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if ((e = launch_transpose(gp->Xs, dp, (long long)np * dp, np, dp, XsT, np, (long long)dpt * np, dpt, B, st)) != cudaSuccess)
         return e;
@@ -237,7 +243,7 @@ cudaError_t mll_grad(const hdbo_gp* gp, double* Kinv, double* G, double* XsT, do
     k_gxa<<<dim3(T, (dpt / 128) * splits, B), NTHREADS, GEMM_SMEM_BYTES, st>>>(x);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     k_mll_grad_final<<<B, 256, 0, st>>>(colpart, (long long)T * GXA_MAX_SPLITS * dpt, T * splits, dpt, scalpart, (np / 32) * G_NSEG, gp->inv_ls, gp->hyp,
-                                        gp->scal, gp->d, grad);
+                                        gp->scal, gp->d, gp->n, grad);
     return cudaGetLastError();
 }
 

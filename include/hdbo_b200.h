@@ -71,7 +71,8 @@ typedef struct hdbo_gp {
     const double* hyp;      /* [batch][4]                                                                       */
     double* Xs;             /* [batch][n_pad][d_pad] centred, scaled inputs                                     */
     double* xn;             /* [batch][n_pad]        squared norms of the rows of Xs                            */
-    double* R2;             /* [batch][n_pad][n_pad] scaled squared distances (may be NULL when no MLL gradient)*/
+    double* R2;             /* [batch][n_pad][n_pad] MLL-gradient state (may be NULL when no gradient is wanted): the    */
+                            /* kernel build leaves dk/dr^2 (unit outputscale) on the lower tiles (historical field name) */
     double* Awork;          /* [batch][n_pad][n_pad] K + noise I, destroyed by the factorisation                */
     double* L;              /* [batch][n_pad][n_pad] Cholesky factor (lower)                                    */
     double* Linv;           /* [batch][n_pad][n_pad] L^-1 (lower)                                               */
