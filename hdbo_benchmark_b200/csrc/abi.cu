@@ -55,15 +55,18 @@ extern "C" int hdbo_gp_fit_downdated(const hdbo_gp* gp, int need_r2, const doubl
     for (int i = 0; i < 4 && piped; i++) piped = gp->aux_streams[i] != nullptr;
     for (int i = 0; i < 12 && piped; i++) piped = gp->aux_events[i] != nullptr;
     tl_mark(gp, HDBO_PHASE_FIT_BUILD, st);
-    // pipelined factorisation: the unused UPPER tiles of Awork hold the running rows of L^-1 and must start at zero (the build
-    // below rewrites the lower tiles)
-    if (piped) TRY_CUDA(cudaMemsetAsync(gp->Awork, 0, sizeof(double) * (size_t)nn, st));
+    // (pipelined factorisation: the unused UPPER tiles of Awork hold the running rows of L^-1; their first update starts from zero
+    // accumulators, so nothing is cleared here)
     TRY_CUDA(launch_scale_inputs(gp->X, (int)gp->ldx, 0, gp->n, gp->d, gp->center, gp->inv_ls, gp->d, gp->Xs, dp, np,
                                  (long long)np * dp, gp->xn, np, B, st));
     SymBuildParams sb{};
     sb.Xs = gp->Xs; sb.xn = gp->xn; sb.hyp = gp->hyp; sb.Khat = gp->Awork; sb.R2 = need_r2 ? gp->R2 : nullptr;
     sb.ldx = dp; sb.ldk = np; sb.bsX = (long long)np * dp; sb.bsxn = np; sb.bsK = nn;
     sb.n = gp->n; sb.tiles = np / 128; sb.kblocks = dp / BK; sb.kind = gp->kind;
+    // pipelined factorisation: only the first four tile columns are built here; the rest of the build runs on the side stream beside
+    // the first pair's chain (kernels_chol_pipe.cu)
+    const bool split_build = piped && !V;
+    if (split_build) { sb.colmajor = 1; sb.t0 = 0; sb.t1 = pipe_build_head_tiles(np / 128); }
     TRY_CUDA(launch_sym_build(sb, B, st));
     if (V) {   // Khat -= V V^T on the lower tiles (joint predictive covariance K(Z,Z) + noise I - V V^T)
         GemmParams g{};
@@ -78,9 +81,12 @@ extern "C" int hdbo_gp_fit_downdated(const hdbo_gp* gp, int need_r2, const doubl
     if (piped) {
         ChainStreams cs{};
         cs.chain = (cudaStream_t)gp->aux_streams[0]; cs.bulk = (cudaStream_t)gp->aux_streams[1];
-        cs.inverse = (cudaStream_t)gp->aux_streams[2]; cs.kinv = (cudaStream_t)gp->aux_streams[3];
+        cs.inverse = (cudaStream_t)gp->aux_streams[2]; cs.panel = (cudaStream_t)gp->aux_streams[3];
         for (int i = 0; i < 12; i++) cs.ev[i] = (cudaEvent_t)gp->aux_events[i];
-        TRY_CUDA(chol_inverse_pipelined(gp->Awork, gp->L, gp->Linv, gp->Linvt, kinv, np, np / 128, gp->info, st, cs));
+        SymBuildParams rest = sb;
+        rest.t0 = sb.t1; rest.t1 = 0;
+        TRY_CUDA(chol_inverse_pipelined(gp->Awork, gp->L, gp->Linv, gp->Linvt, kinv, np, np / 128, gp->info, st, cs,
+                                        split_build ? &rest : nullptr));
     } else {
         TRY_CUDA(chol_inverse(gp->Awork, gp->L, gp->Linv, gp->Linvt, np, nn, np / 128, gp->n, gp->info, B, st));
         if (kinv) TRY_CUDA(kinv_from_linvt(gp, kinv, st));

@@ -163,6 +163,9 @@ struct GemmT {
 };
 
 using G128 = GemmT<128, 128, 2, 4>;
+// same warp grid / fragment layout as G128, 32-wide k-blocks (3 x 72 KB ring = 221 KB): half the barriers; measured best of the
+// variants in tools/var_bench.cu (35.0 vs 34.5 TFLOP/s for BK = 16 inside k_var)
+using G128W = GemmT<128, 128, 2, 4, 32, 3>;
 using G64 = GemmT<64, 64, 2, 2>;
 using G32 = GemmT<32, 32, 2, 2>;
 

@@ -90,6 +90,9 @@ struct SymBuildParams {
     int ldx, ldk;
     long long bsX, bsxn, bsK;
     int n, tiles, kblocks, kind;
+    int colmajor;                // enumerate the lower tiles column by column (column 0 first) instead of row by row
+    int t0, t1;                  // tile range [t0, t1) of that enumeration (t1 = 0: all)
+    int max_ctas;                // > 0: at most this many CTAs, each walking a strided list of tiles (128x128 tiles only)
 };
 cudaError_t launch_sym_build(const SymBuildParams& p, int batch, cudaStream_t stream);
 
@@ -107,19 +110,38 @@ struct SideParams {
     double *Aw, *L, *Lt, *Kinv;
     int ld, T;
     int k0, kblocks;             // first column tile of the pair, contraction length in 16-blocks (16: a pair, 8: a single column)
-    int c0, r0, jmax;            // first tile column of the bulk region; first tile row / last tile column (j) of the inverse region
-    int n_bulk, n_inv, n_kinv;   // job counts of the three regions (n_kinv: lower tiles a >= b of a (jmax+1)^2 block)
+    int n0, nn;                  // first tile column / row of the NEXT pair and its width (0, 1 or 2)
+    int f;                       // first "far" tile column / row (= n0 + 2)
+    int jmax;                    // last tile column of this pair (= n0 - 1): rows j <= jmax of L^-T exist
+    double* Li;                  // L^-1 (region s writes its rows)
+    int e_k0, e_jmax, e_kblocks; // the PREVIOUS pair's K^-1 region (deferred by one pair: filler without consumers before the end)
+    int e2_k0, e2_kblocks;       // source columns of region e2 (the last pair but one merges its own and the previous pair's: K = 512)
+    int w;                       // columns in this pair (1 or 2)
+    // job counts of the regions, in list order.  Launch A (one round of the grid) holds only jobs whose operands exist as soon as the
+    // pair's panel does -- a, s, c, e_prev, starting with the "head" (a, s and the first mb + 1 jobs of c: the next pair's columns,
+    // this pair's rows of L^-1, the diagonal block of the pair after next); launch B = the rest, which reads those rows of L^-1:
+    //   a  bulk, next pair's columns, far rows      A(i, j)    i >= f, n0 <= j < n0 + nn
+    //   s  rows k0 .. k0+w-1 of L^-1                Linv(k0+r, j) = Linv(k0+r, k0..k0+r) W(k0..k0+r, j), j < k0  (+ L^-T(j, k0+r))
+    //   c  bulk, lower triangle from f (column-major: (f, f), (f+1, f), ... so the next-but-one pair's diagonal block comes early)
+    //   e  K^-1 of the previous pair                Kinv(a, b) b <= a <= e_jmax
+    //   b  inverse, next pair's rows                W^T(j, i)  j <= jmax, n0 <= i < n0 + nn
+    //   d  inverse, far rows                        W^T(j, i)  j <= jmax, i >= f
+    //   e2 K^-1 of this pair (last two pairs only; the last but one folds the previous pair's columns in: the zero lower tiles of
+    //      L^-T make that exact)                    Kinv(a, b) b <= a <= jmax
+    int n_a, n_s, n_c, n_e, n_b, n_d, n_e2;
+    int job0, job1;              // this launch walks jobs [job0, job1) of the pair's list
 };
 cudaError_t launch_side_updates(const SideParams& p, int max_ctas, cudaStream_t stream);
 
 // caller-owned side streams / events of the pipelined factorisation (hdbo_gp.aux_streams / aux_events), see kernels_chol_pipe.cu
 struct ChainStreams {
-    cudaStream_t chain, bulk, inverse, kinv;
+    cudaStream_t chain, bulk, inverse, panel;
     cudaEvent_t ev[12];
 };
 constexpr int PIPE_MIN_TILES = 8;   // below n_pad = 1024 the recursion's handful of launches wins
 cudaError_t chol_inverse_pipelined(double* Aw, double* L, double* Li, double* Lt, double* Kinv, int ld, int T, int32_t* info,
-                                   cudaStream_t origin, const ChainStreams& cs);
+                                   cudaStream_t origin, const ChainStreams& cs, const SymBuildParams* build_rest);
+int pipe_build_head_tiles(int T);   // lower tiles (column-major) the caller must build before chol_inverse_pipelined: columns 0..3
 
 // Cholesky factor + inverse of the padded SPD matrix (recursive, GEMM-rich); see kernels_chol.cu
 cudaError_t chol_inverse(double* Awork, double* L, double* Linv, double* Linvt, int ld, long long bs, int tiles,

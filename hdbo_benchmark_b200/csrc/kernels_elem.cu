@@ -61,22 +61,41 @@ cudaError_t launch_scale_inputs(const double* X, int ldx, long long bsX, int nro
 // ------------------------------------------------------------------------------------------------------------
 // out[i] = sum_{j in range(i)} M[i][j] v[j]; lower: j <= i, upper: j >= i.  One warp per row.
 // rhs mode: v[j] = y[j] - mean (j < n) when y != nullptr, else v = vin.
-__global__ void k_tri_matvec(const double* __restrict__ M, int ld, long long bsM, int n_pad, int upper,
+// HBM-bound (n_pad^2 * 4 B per call): 16-byte loads, four independent row segments in flight per lane (the first version -- one 8-byte
+// load per lane per iteration -- reached 0.22 of the copy bandwidth), long rows first (upper: row 0 first; lower: last row first).
+__global__ void __launch_bounds__(256) k_tri_matvec(const double* __restrict__ M, int ld, long long bsM, int n_pad, int upper,
                              const double* __restrict__ vin, long long bsv, const double* __restrict__ y, int n,
                              const double* __restrict__ hyp, double* __restrict__ out, long long bso) {
     const int b = blockIdx.y;
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= n_pad) return;
+    if (!upper) row = n_pad - 1 - row;
     const double* m = M + b * bsM + (size_t)row * ld;
     const double mean = y ? hyp[b * 4 + 2] : 0.0;
+    const double* vv = vin ? vin + b * bsv : nullptr;
     const int j0 = upper ? row : 0, j1 = upper ? n_pad : row + 1;
-    double s = 0.0;
-    for (int j = j0 + lane; j < j1; j += 32) {
-        double v = y ? ((j < n) ? y[j] - mean : 0.0) : vin[b * bsv + j];
-        s = fma(m[j], v, s);
+    auto vec = [&](int j) -> double { return y ? ((j < n) ? __ldg(y + j) - mean : 0.0) : __ldg(vv + j); };
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const int ja = j0 & ~1;                       // 16-byte aligned start (ld, n_pad are even)
+    const int jb = j1 & ~1;                       // end of the full pairs
+    int j = ja + 2 * lane;
+    for (; j + 192 < jb; j += 256) {
+        const double2 a0 = *reinterpret_cast<const double2*>(m + j);
+        const double2 a1 = *reinterpret_cast<const double2*>(m + j + 64);
+        const double2 a2 = *reinterpret_cast<const double2*>(m + j + 128);
+        const double2 a3 = *reinterpret_cast<const double2*>(m + j + 192);
+        s0 = fma((j >= j0) ? a0.x : 0.0, (j >= j0) ? vec(j) : 0.0, s0); s0 = fma(a0.y, vec(j + 1), s0);
+        s1 = fma(a1.x, vec(j + 64), s1); s1 = fma(a1.y, vec(j + 65), s1);
+        s2 = fma(a2.x, vec(j + 128), s2); s2 = fma(a2.y, vec(j + 129), s2);
+        s3 = fma(a3.x, vec(j + 192), s3); s3 = fma(a3.y, vec(j + 193), s3);
     }
-    s = warp_sum(s);
+    for (; j < jb; j += 64) {
+        const double2 a0 = *reinterpret_cast<const double2*>(m + j);
+        s0 = fma((j >= j0) ? a0.x : 0.0, (j >= j0) ? vec(j) : 0.0, s0); s0 = fma(a0.y, vec(j + 1), s0);
+    }
+    if (lane == 0 && jb < j1) s1 = fma(m[jb], vec(jb), s1);      // odd tail (lower rows of even index)
+    double s = warp_sum((s0 + s1) + (s2 + s3));
     if (lane == 0) out[b * bso + row] = s;
 }
 

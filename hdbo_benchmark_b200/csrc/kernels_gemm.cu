@@ -125,63 +125,92 @@ cudaError_t launch_gemm_nt(const GemmParams& p, int batch, cudaStream_t stream) 
 
 // --------------------------------------------------------------------------------------------------------------
 // All rank-256 updates that one PAIR of columns (k0, k0+1) of the pipelined factorisation (kernels_chol_pipe.cu) makes available, as
-// ONE persistent launch (kblocks = 8: a single trailing column, K = 128):
-//   bulk     A(i, j)    -= L(i, k0..) L(j, k0..)^T          c0 <= j <= i < T        (trailing update of the factorisation)
-//   inverse  W^T(j, i)  -= L^-T(j, k0..) L(i, k0..)^T       j <= jmax, r0 <= i < T  (running rows of L^-1, transposed, upper tiles of Awork)
+// persistent launches over one job list (kblocks = 8: a single trailing column, K = 128):
+//   bulk     A(i, j)    -= L(i, k0..) L(j, k0..)^T          n0 <= j <= i < T, except the next pair's diagonal block (the chain's)
+//   inverse  W^T(j, i)  -= L^-T(j, k0..) L(i, k0..)^T       j <= jmax, n0 <= i < T  (running rows of L^-1, transposed, upper tiles of Awork)
 //   K^-1     Kinv(a, b) += L^-T(a, k0..) L^-T(b, k0..)^T    b <= a <= jmax          (MLL gradient only)
-// The three loads add up to ~T^2/2 tile updates per pair.  What was measured on the way here (profiles/r02_fit_trace_*.jsonl,
+// The three loads add up to T^2/2 + T/2 - 3 tile updates per pair.  What was measured on the way here (profiles/r02_fit_trace_*.jsonl,
 // r02_pipe_prof_*.jsonl): as separate launches on separate streams they fought the chain's one-CTA leaf for SMs (a leaf needs a whole
 // SM's shared memory: 10-40 us of queueing per step); as K = 128 updates they are L2 / HBM-bound, not DMMA-bound -- 8 flop per byte of
 // tile traffic, 24 us per 4.2 MFLOP tile = 65 % of the SM's DMMA rate, and three independent 64x64 pipelines per SM did not change
 // that -- hence K = 256 (pairs of columns: 16 flop per byte).  The grid is capped below the SM count: one 122 KB CTA per SM, so the
 // remaining SMs stay free for the chain; every CTA walks a strided list of jobs, C is read into the accumulators before each mainloop.
+// Job order: the jobs on the NEXT pair's tile columns / rows and on the diagonal block of the pair after it -- the "head" -- come
+// first, so that the launcher can cut the list after one round of the grid (launch A = jobs [0, cut), launch B = the rest) and record an
+// event between the two: the next pair's panel and the chain's diagonal-block update wait for the head only, not for the whole list.
 __global__ void __launch_bounds__(NTHREADS, 1) k_side_updates(SideParams p) {
     extern __shared__ __align__(16) double smem[];
-    const int total = p.n_bulk + p.n_inv + p.n_kinv;
     const size_t ld = (size_t)p.ld;
     auto tile = [&](double* base, int r, int c) { return base + (size_t)r * 128 * ld + (size_t)c * 128; };
-    for (int job = blockIdx.x; job < total; job += gridDim.x) {
+    const int mb = p.T - p.f;                                    // far tile columns (lower triangle of mb x mb tiles from f)
+    const int e_a = p.n_a, e_s = e_a + p.n_s, e_c = e_s + p.n_c, e_e = e_c + p.n_e, e_b = e_e + p.n_b, e_d = e_b + p.n_d;
+    for (int job = p.job0 + blockIdx.x; job < p.job1; job += gridDim.x) {
         const double *A, *B; double* C; double sign;
-        if (job < p.n_bulk) {
-            int bi, bj; lower_tile_decode(job, bi, bj);
-            const int i = p.c0 + bi, j = p.c0 + bj;
+        double* Ct = nullptr;                                      // region s: C = A B^T (no accumulation) + transposed copy
+        bool first = false;                                        // first update of this tile ever: nothing to read (no memset needed)
+        int kb = p.kblocks;
+        if (job < e_a) {
+            const int j = p.n0 + job % p.nn, i = p.f + job / p.nn;
             A = tile(p.L, i, p.k0); B = tile(p.L, j, p.k0); C = tile(p.Aw, i, j); sign = -1.0;
-        } else if (job < p.n_bulk + p.n_inv) {
-            const int q = job - p.n_bulk;                          // (j, i): j fastest so that neighbouring CTAs share B = L(i, k0..)
-            const int j = q % (p.jmax + 1), i = p.r0 + q / (p.jmax + 1);
-            A = tile(p.Lt, j, p.k0); B = tile(p.L, i, p.k0); C = tile(p.Aw, j, i); sign = -1.0;
+        } else if (job < e_s) {
+            const int q = job - e_a, r = q % p.w, j = q / p.w;
+            A = tile(p.Li, p.k0 + r, p.k0); B = tile(p.Aw, j, p.k0); C = tile(p.Li, p.k0 + r, j); Ct = tile(p.Lt, j, p.k0 + r);
+            sign = 1.0; kb = (r + 1) * KB_PER_TILE;
+        } else if (job < e_c) {
+            // column-major over the lower triangle (column f first): the row-major decode of the reversed index, mirrored
+            int bi, bj; lower_tile_decode(p.n_c - 1 - (job - e_s), bi, bj);
+            const int i = p.f + (mb - 1 - bj), j = p.f + (mb - 1 - bi);
+            A = tile(p.L, i, p.k0); B = tile(p.L, j, p.k0); C = tile(p.Aw, i, j); sign = -1.0;
+        } else if (job < e_e) {
+            int a, b; lower_tile_decode(job - e_c, a, b);
+            A = tile(p.Lt, a, p.e_k0); B = tile(p.Lt, b, p.e_k0); C = tile(p.Kinv, a, b); sign = 1.0; kb = p.e_kblocks;
+            first = a >= p.e_k0;
+        } else if (job < e_b) {
+            // (j, i): j fastest so that neighbouring CTAs share B = L(i, k0..)
+            const int q = job - e_e, j = q % (p.jmax + 1), i = p.n0 + q / (p.jmax + 1);
+            A = tile(p.Lt, j, p.k0); B = tile(p.L, i, p.k0); C = tile(p.Aw, j, i); sign = -1.0; first = j >= p.k0;
+        } else if (job < e_d) {
+            const int q = job - e_b, j = q % (p.jmax + 1), i = p.f + q / (p.jmax + 1);
+            A = tile(p.Lt, j, p.k0); B = tile(p.L, i, p.k0); C = tile(p.Aw, j, i); sign = -1.0; first = j >= p.k0;
         } else {
-            int a, b; lower_tile_decode(job - p.n_bulk - p.n_inv, a, b);
-            A = tile(p.Lt, a, p.k0); B = tile(p.Lt, b, p.k0); C = tile(p.Kinv, a, b); sign = 1.0;
+            int a, b; lower_tile_decode(job - e_d, a, b);
+            A = tile(p.Lt, a, p.e2_k0); B = tile(p.Lt, b, p.e2_k0); C = tile(p.Kinv, a, b); sign = 1.0; kb = p.e2_kblocks;
+            first = a >= p.e2_k0;
         }
         Frag acc;
+        if (Ct || first) acc.zero();
+        else {
+#pragma unroll
+            for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) {
+                    const double2 c = *reinterpret_cast<const double2*>(C + (size_t)frag_row(mt) * ld + frag_col(nt));
+                    acc.v[mt][nt][0] = sign * c.x; acc.v[mt][nt][1] = sign * c.y;
+                }
+        }
+        gemm_nt_mainloop(A, p.ld, B, p.ld, 0, kb, smem, acc);
 #pragma unroll
         for (int mt = 0; mt < 8; mt++)
 #pragma unroll
             for (int nt = 0; nt < 4; nt++) {
-                const double2 c = *reinterpret_cast<const double2*>(C + (size_t)frag_row(mt) * ld + frag_col(nt));
-                acc.v[mt][nt][0] = sign * c.x; acc.v[mt][nt][1] = sign * c.y;
+                const double2 o = make_double2(sign * acc.v[mt][nt][0], sign * acc.v[mt][nt][1]);
+                *reinterpret_cast<double2*>(C + (size_t)frag_row(mt) * ld + frag_col(nt)) = o;
+                if (Ct) { Ct[(size_t)frag_col(nt) * ld + frag_row(mt)] = o.x; Ct[(size_t)(frag_col(nt) + 1) * ld + frag_row(mt)] = o.y; }
             }
-        gemm_nt_mainloop(A, p.ld, B, p.ld, 0, p.kblocks, smem, acc);
-#pragma unroll
-        for (int mt = 0; mt < 8; mt++)
-#pragma unroll
-            for (int nt = 0; nt < 4; nt++)
-                *reinterpret_cast<double2*>(C + (size_t)frag_row(mt) * ld + frag_col(nt)) =
-                    make_double2(sign * acc.v[mt][nt][0], sign * acc.v[mt][nt][1]);
     }
 }
 
+// jobs [p.job0, p.job1) of the pair's list on at most max_ctas CTAs
 cudaError_t launch_side_updates(const SideParams& p, int max_ctas, cudaStream_t stream) {
-    const int total = p.n_bulk + p.n_inv + p.n_kinv;
-    if (total <= 0) return cudaSuccess;
+    const int count = p.job1 - p.job0;
+    if (count <= 0) return cudaSuccess;
     static PerDeviceOnce attr_once; int attr_dev;
     if (attr_once.pending(attr_dev)) {
         cudaError_t e = cudaFuncSetAttribute(k_side_updates, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_once.mark(attr_dev);
     }
-    k_side_updates<<<total < max_ctas ? total : max_ctas, NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
+    k_side_updates<<<count < max_ctas ? count : max_ctas, NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -263,9 +292,12 @@ cudaError_t launch_cross(const CrossParams& p, int batch, cudaStream_t stream) {
 template <class G>
 __global__ void __launch_bounds__(G::THREADS) k_sym_build(SymBuildParams p) {
     extern __shared__ __align__(16) double smem[];
-    int bm, bn;
-    lower_tile_decode(blockIdx.x, bm, bn);
     const int b = blockIdx.z;
+    const int t_all = p.tiles * (p.tiles + 1) / 2, t_end = p.t1 > 0 ? p.t1 : t_all;
+    for (int t = p.t0 + blockIdx.x; t < t_end; t += gridDim.x) {
+    int bm, bn;
+    if (p.colmajor) { int bi, bj; lower_tile_decode(t_all - 1 - t, bi, bj); bm = p.tiles - 1 - bj; bn = p.tiles - 1 - bi; }
+    else lower_tile_decode(t, bm, bn);
     typename G::Frag acc; acc.zero();
     const double* Xs = p.Xs + b * p.bsX;
     G::mainloop(Xs + (size_t)bm * G::TM * p.ldx, p.ldx, Xs + (size_t)bn * G::TN * p.ldx, p.ldx, 0, p.kblocks, smem, acc);
@@ -296,6 +328,7 @@ __global__ void __launch_bounds__(G::THREADS) k_sym_build(SymBuildParams p) {
             if (R2) *reinterpret_cast<double2*>(R2 + (size_t)i * p.ldk + j0) = make_double2(rv[0], rv[1]);
         }
     }
+    }
 }
 
 template <class G>
@@ -307,14 +340,17 @@ static cudaError_t launch_sym_build_cfg(SymBuildParams p, int batch, cudaStream_
         attr_once.mark(attr_dev);
     }
     p.tiles *= 128 / G::TM;
-    dim3 grid(p.tiles * (p.tiles + 1) / 2, 1, batch);
+    int count = (p.t1 > 0 ? p.t1 : p.tiles * (p.tiles + 1) / 2) - p.t0;
+    if (count <= 0) return cudaSuccess;
+    if (p.max_ctas > 0 && count > p.max_ctas) count = p.max_ctas;
+    dim3 grid(count, 1, batch);
     k_sym_build<G><<<grid, G::THREADS, G::SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_sym_build(const SymBuildParams& p, int batch, cudaStream_t stream) {
     const long long t128 = (long long)p.tiles * (p.tiles + 1) / 2 * batch;
-    if (t128 >= 148) return launch_sym_build_cfg<G128>(p, batch, stream);
+    if (t128 >= 148 || p.t1 > 0 || p.t0 > 0) return launch_sym_build_cfg<G128>(p, batch, stream);   // (tile ranges count 128-tiles)
     if (t128 >= 37) return launch_sym_build_cfg<G64>(p, batch, stream);
     return launch_sym_build_cfg<G32>(p, batch, stream);
 }
@@ -325,7 +361,7 @@ cudaError_t launch_sym_build(const SymBuildParams& p, int batch, cudaStream_t st
 // squares over this tile's 128 columns -> varpart[bn][row]; V itself is stored only for the gradient path.
 // Mainloop configuration: same 2x4 warp grid / fragment layout as G128, but 32-wide k-blocks (3 x 72 KB ring = 221 KB):
 // half the barriers; measured best of the variants in tools/var_bench.cu (35.0 vs 34.5 TFLOP/s for BK = 16).
-using GVAR = GemmT<128, 128, 2, 4, 32, 3>;
+using GVAR = G128W;
 __global__ void __launch_bounds__(NTHREADS, 1) k_var(VarParams p) {
     extern __shared__ __align__(16) double smem[];
     const int bm = blockIdx.x, bn = p.ntiles - 1 - blockIdx.y, b = blockIdx.z;

@@ -132,11 +132,12 @@ class DeviceGP:
 
     # ---- caller-owned side streams / events of the pipelined factorisation (csrc/kernels_chol_pipe.cu) ----
     def _attach_side_streams(self) -> None:
-        """Four side streams with descending priorities -- chain (its one-CTA leaves must never queue behind the bulk GEMMs), bulk (the
-        chain waits for it every step), inverse, K^-1 (no deadlines: they fill what is left) -- and twelve events, owned here and
-        handed to the library through the descriptor."""
+        """Four side streams -- chain (highest priority: its one-CTA leaves and single-tile updates must never queue), side (the
+        persistent rank-256 updates, lowest priority), near (rows of L^-1 next to the chain) and panel (the rest of each panel and
+        the next pair's column updates, second priority: the chain waits for it once per column) -- and twelve events, owned here
+        and handed to the library through the descriptor."""
         with torch.cuda.device(self.device):
-            streams = [torch.cuda.Stream(device=self.device, priority=p) for p in (-3, -2, -1, 0)]
+            streams = [torch.cuda.Stream(device=self.device, priority=p) for p in (-3, 0, -1, -2)]   # chain, side, near, panel
             events = [torch.cuda.Event() for _ in range(12)]
             for e in events:
                 e.record()          # forces the lazily created cudaEvent_t into existence

@@ -84,8 +84,8 @@ typedef struct hdbo_gp {
     hdbo_timeline* timeline;/* HOST pointer to a caller-owned timeline, or NULL (the default: nothing is recorded)      */
     double* Kinv;           /* [batch][n_pad][n_pad] or NULL: when set, hdbo_gp_fit(need_r2 != 0) also leaves the lower  */
                             /* tiles of Khat^-1 = L^-T L^-1 here (consumed by hdbo_mll_grad when passed as its Kinv)     */
-    void* aux_streams[4];   /* optional CALLER-OWNED side streams (cudaStream_t): chain (create it with a higher         */
-                            /* priority), bulk, inverse, K^-1.  All four + the 12 events set, batch == 1, n_pad >= 1024:  */
+    void* aux_streams[4];   /* optional CALLER-OWNED side streams (cudaStream_t): chain (create it with the highest      */
+                            /* priority), side (lowest), near, panel.  All four + the 12 events set, batch == 1, n_pad >= 1024: */
                             /* hdbo_gp_fit runs the pipelined factorisation (csrc/kernels_chol_pipe.cu) forked from and   */
                             /* joined back to `stream`; otherwise everything runs on `stream` alone.                      */
     void* aux_events[12];   /* CALLER-OWNED cudaEvent_t (timing disabled) for the cross-stream dependencies               */
