@@ -105,6 +105,7 @@ extern "C" int hdbo_gp_fit_downdated(const hdbo_gp* gp, int need_r2, const doubl
 namespace {
 struct PostWs {
     double *Zs, *zn, *Kstar, *meanpart, *varpart, *DK, *V, *T, *XsT;
+    double* P2;       // [rows][n_pad / 2]: second parts of the split-K triangular products of the few-candidate gradient path
     double* zscale;   // int8 mode: power-of-two row scales of the candidate digit images
     int8_t* Zdig;     // int8 mode: candidate digit images
     size_t bytes;
@@ -126,6 +127,7 @@ PostWs carve(const hdbo_gp* gp, int64_t rows, int keep, void* base) {
         w.V = take(B * rows * np);
         w.T = take(B * rows * np);
         w.XsT = take(B * (size_t)rup(gp->d, 128) * np);
+        w.P2 = take(rows * np / 2);
     }
     w.bytes = off * sizeof(double);
     return w;
@@ -201,9 +203,15 @@ cudaError_t posterior_chunk(const hdbo_gp* gp, const PostWs& w, int64_t rows_all
         g.A = w.Kstar; g.B = gp->Linv; g.C = w.V; g.Ct = nullptr;
         g.lda = g.ldb = g.ldc = np; g.bsA = (long long)rows_alloc * np; g.bsB = (long long)np * np; g.bsC = (long long)rows_alloc * np;
         g.mtiles = mt; g.ntiles = nt; g.kblocks = np / BK; g.krange = KR_LE_N; g.lower_only = 0; g.alpha = 1.0; g.beta = 0.0;
+        // single GP: the long half of the columns is cut at K/2 (second parts -> P2, added back by the row reduction): the launch
+        // was as long as its longest k-range (402 us for 512 candidates at n = 4096 with the DMMA pipe 93 % busy WHILE ACTIVE)
+        const bool split = B == 1 && nt % 2 == 0 && nt >= 4;
+        const double* add = nullptr;
+        if (split) { g.krange = KR_LE_N_SPLIT; g.C2 = w.P2 - np / 2; g.ldc2 = np / 2; add = w.P2 - np / 2; }
         tl_mark(gp, HDBO_PHASE_VAR, st);
         e = launch_gemm_nt(g, B, st);
-        if (e == cudaSuccess) e = launch_row_sumsq(w.V, np, (long long)rows_alloc * np, rp, np, w.varpart, 2LL * nt * rows_alloc, B, st);
+        if (e == cudaSuccess)
+            e = launch_row_sumsq(w.V, np, (long long)rows_alloc * np, rp, np, add, np / 2, np / 2, w.varpart, 2LL * nt * rows_alloc, B, st);
         tl_mark(gp, HDBO_PHASE_VAR, st);
         *var_tiles = 1;
         return e;
@@ -448,7 +456,7 @@ extern "C" int hdbo_posterior_bwd(const hdbo_gp* gp, int64_t m, int q, const dou
     const int64_t rows = rup(m, 128);
     if (!workspace || carve(gp, rows, 1, nullptr).bytes > workspace_bytes) return -12;
     PostWs w = carve(gp, rows, 1, workspace);
-    BwdBuffers b{w.Zs, w.Kstar, w.DK, w.V, w.T, w.XsT, w.meanpart};
+    BwdBuffers b{w.Zs, w.Kstar, w.DK, w.V, w.T, w.XsT, w.meanpart, w.P2};
     tl_mark(gp, HDBO_PHASE_BWD, (cudaStream_t)stream_);
     TRY_CUDA(posterior_bwd(gp, b, rows, m, q, gmean, gvar, gSigma, bsg, bsS, dZ, (int)lddz, bsdz, (cudaStream_t)stream_));
     tl_mark(gp, HDBO_PHASE_BWD, (cudaStream_t)stream_);

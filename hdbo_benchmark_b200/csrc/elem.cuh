@@ -71,8 +71,8 @@ cudaError_t launch_tri_matvec(const double* M, int ld, long long bsM, int n_pad,
                               int batch, cudaStream_t stream);
 cudaError_t launch_fit_scalars(const double* L, int ld, long long bsL, const double* w, const double* alpha,
                                long long bsv, int n, int n_pad, double* scal, int batch, cudaStream_t stream);
-cudaError_t launch_row_sumsq(const double* V, int ldv, long long bsV, int rows, int cols, double* out, long long bso, int batch,
-                             cudaStream_t stream);
+cudaError_t launch_row_sumsq(double* V, int ldv, long long bsV, int rows, int cols, const double* add, int ldadd, int add_from,
+                             double* out, long long bso, int batch, cudaStream_t stream);
 cudaError_t launch_finalize_acq(const double* meanpart, const double* varpart, long long bsp, int ntiles, int ntiles_var, int rows_pad,
                                 int m, const double* hyp, int observation_noise, int acq_kind, double acq_param,
                                 double* mean_out, double* var_out, double* acq_out, long long bso, int batch,

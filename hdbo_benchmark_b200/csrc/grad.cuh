@@ -5,7 +5,7 @@
 namespace hdbo {
 
 struct BwdBuffers {
-    double *Zs, *Kstar, *DK, *V, *T, *XsT, *csum;
+    double *Zs, *Kstar, *DK, *V, *T, *XsT, *csum, *P2;
 };
 
 cudaError_t launch_transpose(const double* in, int ld_in, long long bs_in, int rows, int cols, double* out, int ld_out,

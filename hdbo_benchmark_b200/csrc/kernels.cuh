@@ -37,6 +37,10 @@ enum KRange : int {
     KR_GE_N = 3,   // k-tile >= n-tile   (B upper triangular)
     KR_GE_M = 4,   // k-tile >= m-tile   (A upper triangular)
     KR_GE_MN = 5,  // k-tile >= max(m,n) (both upper)
+    // the two triangular ranges with the long half of the columns cut in two at K/2 (C2 / ldc2 receive the second parts; beta = 0,
+    // batch 1, even ntiles): 1.5 ntiles virtual columns of at most K/2 each, so that a launch with few row tiles is not as long as
+    // its single longest k-range (the consumer adds C2 onto C)
+    KR_LE_N_SPLIT = 6, KR_GE_N_SPLIT = 7,
 };
 
 struct GemmParams {
@@ -48,6 +52,7 @@ struct GemmParams {
     int lower_only;                                           // only tiles with m-tile >= n-tile (grid.x enumerates them)
     double alpha, beta;
     int tile_hint;                                            // 0: choose the CTA tile by the launch's tile count; 32 / 64 / 128: force it
+    double* C2; int ldc2;                                     // KR_*_SPLIT: second-part output, addressed like C (same row / column indices)
 };
 
 // kernel value k(r^2) and derivative dk/dr^2 for unit outputscale.  kind: 0 Matern-5/2, 1 RBF.

@@ -76,7 +76,7 @@ cudaError_t chol_inverse_pipelined(double* Aw, double* L, double* Li, double* Lt
     auto at = [&](double* base, int r, int c) { return base + (size_t)r * 128 * ld + (size_t)c * 128; };
     const long long bs = (long long)ld * ld;
     const int skip = pipe_skip_mask();
-    static const int side_ctas = env_int("HDBO_PIPE_SIDE_CTAS", 136);
+    static const int side_ctas = env_int("HDBO_PIPE_SIDE_CTAS", 140);
     static const int rest_tile = env_int("HDBO_PIPE_REST_TILE", 32);       // CTA tile of the panel-rest / row-pair GEMMs
     int sms = 148;
     { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }

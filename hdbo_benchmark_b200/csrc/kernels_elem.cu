@@ -140,10 +140,10 @@ cudaError_t launch_fit_scalars(const double* L, int ld, long long bsL, const dou
 // ------------------------------------------------------------------------------------------------------------
 // Per candidate: mean = m0 + sum_t meanpart[t][i]; var = outputscale - sum_t varpart[t][i] (+ noise);
 // acquisition value (A5) and, if requested, d acq / d mean and d acq / d var.
-// HBM-bound (16 B x ntiles per candidate): 64 candidates x 4 tile slices per CTA so that a 18 944-candidate chunk fills the SMs
-// (296 CTAs) and every thread keeps 4 independent loads in flight; the 4 slice sums are combined through shared memory in a fixed
-// order (deterministic, independent of the chunking).
-constexpr int FIN_CAND = 64, FIN_SLICES = 4;
+// HBM-bound (8 B x (ntiles + ntiles_var) per candidate): 32 candidates x 8 tile slices per CTA so that a 18 944-candidate chunk is 592
+// CTAs = 4 per SM and every thread issues its 4 + 8 loads at once (64 x 4: 296 CTAs, 0.11 of the copy bandwidth in a 21 us launch);
+// the slice sums are combined through shared memory in a fixed order (deterministic, independent of the chunking).
+constexpr int FIN_CAND = 32, FIN_SLICES = 8;
 __global__ void __launch_bounds__(FIN_CAND * FIN_SLICES)
 k_finalize_acq(const double* __restrict__ meanpart, const double* __restrict__ varpart, long long bsp,
                int ntiles, int ntiles_var, int rows_pad, int m, const double* __restrict__ hyp, int observation_noise,
@@ -170,8 +170,9 @@ k_finalize_acq(const double* __restrict__ meanpart, const double* __restrict__ v
     red[1][sl][c] = live ? slice_sum(varpart, ntiles_var) : 0.0;
     __syncthreads();
     if (sl != 0 || !live) return;
-    const double sm = (red[0][0][c] + red[0][1][c]) + (red[0][2][c] + red[0][3][c]);
-    const double sv = (red[1][0][c] + red[1][1][c]) + (red[1][2][c] + red[1][3][c]);
+    static_assert(FIN_SLICES == 8, "fixed-order combine below is written for 8 slices");
+    const double sm = ((red[0][0][c] + red[0][1][c]) + (red[0][2][c] + red[0][3][c])) + ((red[0][4][c] + red[0][5][c]) + (red[0][6][c] + red[0][7][c]));
+    const double sv = ((red[1][0][c] + red[1][1][c]) + (red[1][2][c] + red[1][3][c])) + ((red[1][4][c] + red[1][5][c]) + (red[1][6][c] + red[1][7][c]));
     const double os = hyp[b * 4 + 0], noise = hyp[b * 4 + 1], m0 = hyp[b * 4 + 2];
     const double mean = m0 + sm;
     double var = os - sv;
@@ -195,24 +196,32 @@ cudaError_t launch_finalize_acq(const double* meanpart, const double* varpart, l
     return cudaGetLastError();
 }
 
-// row sums of squares of V [rows][cols] (one warp per row) -> out[b*bso + row]   (small-m variance path)
-__global__ void k_row_sumsq(const double* __restrict__ V, int ldv, long long bsV, int rows, int cols, double* __restrict__ out,
-                            long long bso) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31, b = blockIdx.y;
-    if (row >= rows) return;
-    const double2* src = reinterpret_cast<const double2*>(V + b * bsV + (size_t)row * ldv);
+// row sums of squares of V [rows][cols] (one CTA per row, 16-byte accesses) -> out[b*bso + row]   (small-m variance path).
+// add != nullptr: columns >= add_from of V first receive the second parts of a split-K product (add[row][col], leading dimension ldadd)
+// and are written back, so that V is whole for the gradient path.
+__global__ void __launch_bounds__(256) k_row_sumsq(double* __restrict__ V, int ldv, long long bsV, int rows, int cols,
+                                                   const double* __restrict__ add, int ldadd, int add_from, double* __restrict__ out, long long bso) {
+    __shared__ double red[8];
+    const int row = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.y;
+    double2* src = reinterpret_cast<double2*>(V + b * bsV + (size_t)row * ldv);
+    const double2* ad = add ? reinterpret_cast<const double2*>(add + (size_t)row * ldadd) : nullptr;
     double s = 0.0;
-    for (int j = lane; j < cols / 2; j += 32) { const double2 v = src[j]; s = fma(v.x, v.x, s); s = fma(v.y, v.y, s); }
+    for (int j = threadIdx.x; j < cols / 2; j += 256) {
+        double2 v = src[j];
+        if (ad && 2 * j >= add_from) { const double2 a = ad[j]; v.x += a.x; v.y += a.y; src[j] = v; }
+        s = fma(v.x, v.x, s); s = fma(v.y, v.y, s);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) out[b * bso + row] = s;
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) out[b * bso + row] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
 }
 
-cudaError_t launch_row_sumsq(const double* V, int ldv, long long bsV, int rows, int cols, double* out, long long bso, int batch,
-                             cudaStream_t stream) {
+cudaError_t launch_row_sumsq(double* V, int ldv, long long bsV, int rows, int cols, const double* add, int ldadd, int add_from,
+                             double* out, long long bso, int batch, cudaStream_t stream) {
     if (rows == 0) return cudaSuccess;
-    dim3 grid((rows + 7) / 8, batch);
-    k_row_sumsq<<<grid, 256, 0, stream>>>(V, ldv, bsV, rows, cols, out, bso);
+    k_row_sumsq<<<dim3(rows, batch), 256, 0, stream>>>(V, ldv, bsV, rows, cols, add, ldadd, add_from, out, bso);
     return cudaGetLastError();
 }
 

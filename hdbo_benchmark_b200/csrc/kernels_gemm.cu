@@ -52,8 +52,27 @@ __global__ void __launch_bounds__(G::THREADS) k_gemm_nt(GemmParams p) {
     }
     const int b = blockIdx.z;
     int kb0, kb1;
-    krange_blocks(p.krange, bm, bn, p.kblocks, G::KB_PER_TM, G::KB_PER_TN, kb0, kb1);
-    double* C = p.C + b * p.bsC;
+    int part = -1;                                              // KR_*_SPLIT: 0 / 1 = first / second part of a split column, -1 = whole
+    if (!p.lower_only && (p.krange == KR_LE_N_SPLIT || p.krange == KR_GE_N_SPLIT)) {
+        // virtual columns in order of decreasing k-range: the H first parts (H tiles each), then alternately the second part of a
+        // split column and the unsplit column of the same length
+        const int id = blockIdx.y * gridDim.x + blockIdx.x, v = id / p.mtiles, N = p.ntiles, H = N / 2;
+        bm = id % p.mtiles;
+        const bool le = p.krange == KR_LE_N_SPLIT;
+        if (v < H) { bn = le ? N - 1 - v : v; part = 0; }
+        else {
+            const int u = v - H, k = H - u / 2;                 // k tiles of contraction left
+            if ((u & 1) == 0) { bn = le ? k + H - 1 : H - k; part = 1; }
+            else bn = le ? k - 1 : N - k;
+        }
+        const int kh = H * G::KB_PER_TN;
+        if (le) { kb0 = part == 1 ? kh : 0; kb1 = part == 0 ? kh : (bn + 1) * G::KB_PER_TN; }
+        else { kb0 = part == 0 ? kh : bn * G::KB_PER_TN; kb1 = part == 1 ? kh : p.kblocks; }
+    } else {
+        krange_blocks(p.krange, bm, bn, p.kblocks, G::KB_PER_TM, G::KB_PER_TN, kb0, kb1);
+    }
+    double* C = (part == 1 ? p.C2 : p.C) + b * p.bsC;
+    const int ldc = part == 1 ? p.ldc2 : p.ldc;
     double* Ct = p.Ct ? p.Ct + b * p.bsCt : nullptr;
     typename G::Frag acc;
     // beta != 0 (the rank-128 updates of the factorisation: K = 128, so a tile is 8 k-blocks long and the C round trip is a visible
@@ -66,7 +85,7 @@ __global__ void __launch_bounds__(G::THREADS) k_gemm_nt(GemmParams p) {
             const int i = bm * G::TM + G::frag_row(mt);
 #pragma unroll
             for (int nt = 0; nt < G::NT; nt++) {
-                const double2 c = *reinterpret_cast<const double2*>(C + (size_t)i * p.ldc + bn * G::TN + G::frag_col(nt));
+                const double2 c = *reinterpret_cast<const double2*>(C + (size_t)i * ldc + bn * G::TN + G::frag_col(nt));
                 acc.v[mt][nt][0] = f * c.x; acc.v[mt][nt][1] = f * c.y;
             }
         }
@@ -84,7 +103,7 @@ __global__ void __launch_bounds__(G::THREADS) k_gemm_nt(GemmParams p) {
             double2 o;
             o.x = p.alpha * acc.v[mt][nt][0];
             o.y = p.alpha * acc.v[mt][nt][1];
-            *reinterpret_cast<double2*>(C + (size_t)i * p.ldc + j) = o;
+            *reinterpret_cast<double2*>(C + (size_t)i * ldc + j) = o;
             if (Ct) { Ct[(size_t)j * p.ldct + i] = o.x; Ct[(size_t)(j + 1) * p.ldct + i] = o.y; }
         }
     }
@@ -102,6 +121,7 @@ static cudaError_t launch_gemm_cfg(GemmParams p, int batch, cudaStream_t stream)
     p.ntiles *= 128 / G::TN;
     dim3 grid;
     if (p.lower_only) grid = dim3(p.mtiles * (p.mtiles + 1) / 2, 1, batch);
+    else if (p.krange == KR_LE_N_SPLIT || p.krange == KR_GE_N_SPLIT) grid = dim3(p.mtiles, p.ntiles + p.ntiles / 2, batch);
     else grid = dim3(p.mtiles, p.ntiles, batch);
     if (grid.x == 0 || grid.y == 0) return cudaSuccess;
     k_gemm_nt<G><<<grid, G::THREADS, G::SMEM_BYTES, stream>>>(p);

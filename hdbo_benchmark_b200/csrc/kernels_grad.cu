@@ -276,25 +276,38 @@ __global__ void k_make_dV(const double* __restrict__ V, int ld, long long bsV, c
     }
 }
 
-// C[c][j] = (gmean_c alpha_j + Bm[c][j]) * DK[c][j] in place over Bm; csum[c] = sum_j C[c][j].  One warp per row.
-__global__ void k_make_C(double* __restrict__ Bm, const double* __restrict__ DK, int ld, long long bsM,
+// C[c][j] = (gmean_c alpha_j + Bm[c][j]) * DK[c][j] in place over Bm; csum[c] = sum_j C[c][j].  One CTA per row, 16-byte accesses
+// (the first version -- one warp per row, 8-byte accesses -- left 512-point calls on 64 CTAs: 64 us for 50 MB of traffic).
+// add != nullptr: columns < add_cols of Bm first receive the second parts of a split-K product (add[row][col], leading dimension ldadd).
+__global__ void __launch_bounds__(256) k_make_C(double* __restrict__ Bm, const double* __restrict__ DK, int ld, long long bsM,
                          const double* __restrict__ gmean, long long bsg, const double* __restrict__ alpha, long long bsa,
-                         int m, int rows_pad, double* __restrict__ csum, long long bsc) {
-    const int b = blockIdx.y;
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (c >= rows_pad) return;
-    double* row = Bm + b * bsM + (size_t)c * ld;
-    const double* dk = DK + b * bsM + (size_t)c * ld;
-    const double gm = (c < m && gmean) ? gmean[b * bsg + c] : 0.0;
+                         int m, int rows_pad, double* __restrict__ csum, long long bsc,
+                         const double* __restrict__ add, int ldadd, int add_cols) {
+    __shared__ double red[8];
+    const int b = blockIdx.y, c = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double2* row = reinterpret_cast<double2*>(Bm + b * bsM + (size_t)c * ld);
+    const double2* dk = reinterpret_cast<const double2*>(DK + b * bsM + (size_t)c * ld);
+    const double2* al = reinterpret_cast<const double2*>(alpha + b * bsa);
+    const double2* ad = add ? reinterpret_cast<const double2*>(add + (size_t)c * ldadd) : nullptr;
+    const bool live = c < m;
+    const double gm = (live && gmean) ? gmean[b * bsg + c] : 0.0;
     double s = 0.0;
-    for (int j = lane; j < ld; j += 32) {
-        double v = (c < m) ? (gm * alpha[b * bsa + j] + row[j]) * dk[j] : 0.0;
+    for (int j = threadIdx.x; j < ld / 2; j += 256) {
+        double2 v = make_double2(0.0, 0.0);
+        if (live) {
+            double2 r = row[j];
+            const double2 k = dk[j], a = al[j];
+            if (ad && 2 * j < add_cols) { const double2 x = ad[j]; r.x += x.x; r.y += x.y; }
+            v.x = (gm * a.x + r.x) * k.x; v.y = (gm * a.y + r.y) * k.y;
+        }
         row[j] = v;
-        s += v;
+        s += v.x + v.y;
     }
     s = warp_sum_g(s);
-    if (lane == 0) csum[b * bsc + c] = s;
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) csum[b * bsc + c] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
 }
 
 // dZ[c][k] = 2 inv_ls[k] (Zs[c][k] csum[c] - (C Xs)[c][k])
@@ -327,15 +340,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dz(DzParams p) {
 }
 
 // the same epilogue on a product P = C Xs that the generic GEMM already formed (few-candidate path of posterior_bwd)
-__global__ void k_dz_finish(const double* __restrict__ P, int ldp, long long bsP, const double* __restrict__ Zs, int ldz, long long bsZ,
+// (P may arrive as `nsplit` split-K partial products `split_stride` doubles apart: summed here in a fixed order)
+__global__ void k_dz_finish(const double* __restrict__ P, int ldp, long long bsP, int nsplit, long long split_stride,
+                            const double* __restrict__ Zs, int ldz, long long bsZ,
                             const double* __restrict__ csum, long long bscs, const double* __restrict__ inv_ls, int m, int d,
                             double* __restrict__ dZ, int lddz, long long bsdz) {
     const int b = blockIdx.y;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)m * d) return;
     const int c = (int)(idx / d), k = (int)(idx - (long long)c * d);
+    const double* pp = P + b * bsP + (size_t)c * ldp + k;
+    double pv = pp[0];
+    for (int sidx = 1; sidx < nsplit; sidx++) pv += pp[sidx * split_stride];
     dZ[b * bsdz + (size_t)c * lddz + k] =
-        2.0 * inv_ls[(size_t)b * d + k] * (Zs[b * bsZ + (size_t)c * ldz + k] * csum[b * bscs + c] - P[b * bsP + (size_t)c * ldp + k]);
+        2.0 * inv_ls[(size_t)b * d + k] * (Zs[b * bsZ + (size_t)c * ldz + k] * csum[b * bscs + c] - pv);
 }
 
 // joint covariance of each q-group: Sigma[a][b] = os k(r2(z_a,z_b)) - V_a.V_b (+ noise on the diagonal).  One block per group.
@@ -422,6 +440,7 @@ cudaError_t posterior_bwd(const hdbo_gp* gp, const BwdBuffers& w, int64_t rows_a
     const long long bsM = (long long)rows_alloc * np;
     cudaError_t e;
     const bool have_v = (gvar != nullptr) || (gSigma != nullptr);
+    const double* add = nullptr;
     // (1) dV into T, (2) Bm = dV * Linv into Kstar
     if (have_v) {
         k_make_dV<<<dim3(rp, B), 256, 0, st>>>(w.V, np, bsM, gvar, gSigma, bsg, bsS, (int)m, q, rp, w.T);
@@ -430,12 +449,16 @@ cudaError_t posterior_bwd(const hdbo_gp* gp, const BwdBuffers& w, int64_t rows_a
         g.A = w.T; g.B = gp->Linvt; g.C = w.Kstar; g.Ct = nullptr;
         g.lda = np; g.ldb = np; g.ldc = np; g.bsA = bsM; g.bsB = (long long)np * np; g.bsC = bsM;
         g.mtiles = mt; g.ntiles = np / 128; g.kblocks = np / BK; g.krange = KR_GE_N; g.lower_only = 0; g.alpha = 1.0; g.beta = 0.0;
+        // few candidates, single GP: the long half of the columns is cut at K/2 (second parts -> P2, added back by k_make_C)
+        if (B == 1 && (long long)mt * (np / 128) < 148 && (np / 128) % 2 == 0 && np / 128 >= 4 && w.P2) {
+            g.krange = KR_GE_N_SPLIT; g.C2 = w.P2; g.ldc2 = np / 2; add = w.P2;
+        }
         if ((e = launch_gemm_nt(g, B, st)) != cudaSuccess) return e;
     } else {
         if ((e = cudaMemsetAsync(w.Kstar, 0, sizeof(double) * (size_t)B * bsM, st)) != cudaSuccess) return e;
     }
     // (3) C and its row sums
-    k_make_C<<<dim3((rp + 7) / 8, B), 256, 0, st>>>(w.Kstar, w.DK, np, bsM, gmean, bsg, gp->alpha, np, (int)m, rp, w.csum, rows_alloc);
+    k_make_C<<<dim3(rp, B), 256, 0, st>>>(w.Kstar, w.DK, np, bsM, gmean, bsg, gp->alpha, np, (int)m, rp, w.csum, rows_alloc, add, np / 2, np / 2);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     // (4) dZ = 2/l o (z csum - C Xs)
     if ((e = launch_transpose(gp->Xs, dp, (long long)np * dp, np, dp, w.XsT, np, (long long)dpt * np, dpt, B, st)) != cudaSuccess) return e;
@@ -446,10 +469,19 @@ cudaError_t posterior_bwd(const hdbo_gp* gp, const BwdBuffers& w, int64_t rows_a
         g.A = w.Kstar; g.B = w.XsT; g.C = w.T; g.Ct = nullptr;
         g.lda = np; g.ldb = np; g.ldc = dpt; g.bsA = bsM; g.bsB = (long long)dpt * np; g.bsC = bsM;
         g.mtiles = mt; g.ntiles = dpt / 128; g.kblocks = np / BK; g.krange = KR_FULL; g.lower_only = 0; g.alpha = 1.0; g.beta = 0.0;
-        if ((e = launch_gemm_nt(g, B, st)) != cudaSuccess) return e;
+        // single GP: split K over the batch axis of the generic GEMM (the contraction index is contiguous, so a batch stride of
+        // K / S doubles selects the s-th K window) -- 128 CTAs walking k = 4096 each measured 102 us, latency-bound per CTA
+        int S = 1;
+        const long long split_stride = (long long)mt * 128 * dpt;
+        if (B == 1) {
+            const long long ctas32 = (long long)mt * 4 * (dpt / 32);
+            while (S < 8 && ctas32 * S < 444 && (long long)(2 * S) * dpt <= np && (np / BK) % (2 * S) == 0 && (np / BK) / (2 * S) >= 16) S *= 2;
+            if (S > 1) { g.bsA = np / S; g.bsB = np / S; g.bsC = split_stride; g.kblocks = np / BK / S; }
+        }
+        if ((e = launch_gemm_nt(g, S > 1 ? S : B, st)) != cudaSuccess) return e;
         const long long tot = (long long)m * gp->d;
-        k_dz_finish<<<dim3((unsigned)((tot + 255) / 256), B), 256, 0, st>>>(w.T, dpt, bsM, w.Zs, dp, (long long)rows_alloc * dp, w.csum,
-                                                                             rows_alloc, gp->inv_ls, (int)m, gp->d, dZ, lddz, bsdz);
+        k_dz_finish<<<dim3((unsigned)((tot + 255) / 256), B), 256, 0, st>>>(w.T, dpt, bsM, S, split_stride, w.Zs, dp, (long long)rows_alloc * dp,
+                                                                             w.csum, rows_alloc, gp->inv_ls, (int)m, gp->d, dZ, lddz, bsdz);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (gSigma && q > 1) {
             k_dz_pairs<<<dim3((unsigned)(m / q), B), 256, 0, st>>>(w.Zs, dp, (long long)rows_alloc * dp, gSigma, bsS, gp->hyp, gp->inv_ls, q,
