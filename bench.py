@@ -93,7 +93,7 @@ def cpu_model_name():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms under the load of the timed region."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -106,7 +106,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -431,15 +431,22 @@ def main():
         assert mode_check["max_rel_var_diff"] < 1e-6 and mode_check["same_argmax"] and mode_check["timeout_flag"] == 0, mode_check
 
     # ---- headline: W warm-up steps, K timed steps, CUDA events + barrier on both sides, max over ranks ----
+    # clocks / throttle reasons are sampled from the warm-up on (the same load as the timed steps): at N = 8 the timed region of a
+    # strong-scaled run is 0.1 s, shorter than nvidia-smi's start-up + one 100 ms sampling period
+    clocks = ClockSampler(local)
+    clocks.start()
     for _ in range(args.warmup):
         step_resident()
     gp.attach_timeline(args.steps * chunks * 8 + 64)
-    clocks = ClockSampler(local)
-    clocks.start()
     ms_total, (best_v, best_i) = timed(step_resident, args.steps)
-    clk = clocks.stop()
     tl = gp.collect_timeline()
     gp.detach_timeline()
+    t_more = time.perf_counter()
+    while len(clocks.lines) < 4 and time.perf_counter() - t_more < 3.0:      # untimed: keep the load up until the sampler has data
+        step_resident()
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    clk["window"] = "warm-up + timed steps (+ untimed identical steps until >= 4 samples)"
     value = args.steps * pool_total / (ms_total / 1e3)
     if args.var_mode == "i8":
         assert int(best_i) == int(bi_f64), "int8 and FP64 modes disagree on the arg-max of the full pool"

@@ -342,8 +342,11 @@ class DeviceGP:
         for ev in free:
             ev.record(main)
         step = self._slabs[0].shape[0]
-        for i, off in enumerate(range(0, m, step)):
-            mc = min(step, m - off)
+        # the first slab's copy is the only one nothing overlaps: keep it short (37 row tiles; the persistent kernels fill the SMs
+        # from the column tiles) -- at N = 8 a strong-scaled rank has 3.5 slabs per step and a full first slab cost 10 % of it
+        first = min(step, 37 * 128)
+        pieces = [(0, min(first, m))] + [(off, min(step, m - off)) for off in range(first, m, step)]
+        for i, (off, mc) in enumerate(pieces):
             slab = self._slabs[i % 2]
             with torch.cuda.stream(self._copy_stream):
                 self._copy_stream.wait_event(free[i % 2])
