@@ -133,7 +133,7 @@ __global__ void k_fit_scalars(const double* __restrict__ L, int ld, long long bs
 
 cudaError_t launch_fit_scalars(const double* L, int ld, long long bsL, const double* w, const double* alpha,
                                long long bsv, int n, int n_pad, double* scal, int batch, cudaStream_t stream) {
-    k_fit_scalars<<<batch, 512, 0, stream>>>(L, ld, bsL, w, alpha, bsv, n, n_pad, scal);
+    k_fit_scalars<<<batch, 1024, 0, stream>>>(L, ld, bsL, w, alpha, bsv, n, n_pad, scal);
     return cudaGetLastError();
 }
 

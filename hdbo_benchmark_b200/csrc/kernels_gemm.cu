@@ -309,7 +309,9 @@ cudaError_t launch_cross(const CrossParams& p, int batch, cudaStream_t stream) {
 // the gradient kernel evaluated exp / sqrt a second time for all n^2 entries).
 // Templated on the tile configuration: few-tile problems (the small n of a BO loop: 6 tiles of 128x128 at n_pad = 384) run on
 // 32x32 / 64x64 CTA tiles so that the FP64 kernel epilogue spreads over the SMs (p.tiles counts tiles of G::TM).
-template <class G>
+// (KIND is a template parameter: with a run-time kind both kernel functions were inlined behind selects for each of the 64 elements
+// of a thread -- 15.6 k SASS instructions, 55 % of the tile time in an instruction-cache-bound epilogue, ncu r02_ncu_fit2)
+template <class G, int KIND>
 __global__ void __launch_bounds__(G::THREADS) k_sym_build(SymBuildParams p) {
     extern __shared__ __align__(16) double smem[];
     const int b = blockIdx.z;
@@ -325,6 +327,29 @@ __global__ void __launch_bounds__(G::THREADS) k_sym_build(SymBuildParams p) {
     const double* xn = p.xn + b * p.bsxn;
     double* Kh = p.Khat + b * p.bsK;
     double* R2 = p.R2 ? p.R2 + b * p.bsK : nullptr;
+    // interior tiles (off the diagonal, inside the n x n block: all but ~2 T of the T^2 / 2) take a path without the per-element
+    // diagonal / padding selects
+    const bool interior = bm != bn && (bm + 1) * G::TM <= p.n;
+    double xnj[G::NT][2];
+#pragma unroll
+    for (int nt = 0; nt < G::NT; nt++) { xnj[nt][0] = xn[bn * G::TN + G::frag_col(nt)]; xnj[nt][1] = xn[bn * G::TN + G::frag_col(nt) + 1]; }
+    if (interior) {
+#pragma unroll
+        for (int mt = 0; mt < G::MT; mt++) {
+            const int i = bm * G::TM + G::frag_row(mt);
+            const double xi = xn[i];
+            double* krow = Kh + (size_t)i * p.ldk + bn * G::TN;
+            double* rrow = R2 ? R2 + (size_t)i * p.ldk + bn * G::TN : nullptr;
+#pragma unroll
+            for (int nt = 0; nt < G::NT; nt++) {
+                double k0, d0, k1, d1;
+                kernel_eval(KIND, fmax((xi + xnj[nt][0]) - 2.0 * acc.v[mt][nt][0], 0.0), k0, d0);
+                kernel_eval(KIND, fmax((xi + xnj[nt][1]) - 2.0 * acc.v[mt][nt][1], 0.0), k1, d1);
+                *reinterpret_cast<double2*>(krow + G::frag_col(nt)) = make_double2(os * k0, os * k1);
+                if (rrow) *reinterpret_cast<double2*>(rrow + G::frag_col(nt)) = make_double2(d0, d1);
+            }
+        }
+    } else {
 #pragma unroll
     for (int mt = 0; mt < G::MT; mt++) {
         const int i = bm * G::TM + G::frag_row(mt);
@@ -336,10 +361,10 @@ __global__ void __launch_bounds__(G::THREADS) k_sym_build(SymBuildParams p) {
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 const int j = j0 + e;
-                double r2 = fmax((xi + xn[j]) - 2.0 * acc.v[mt][nt][e], 0.0);
+                double r2 = fmax((xi + xnj[nt][e]) - 2.0 * acc.v[mt][nt][e], 0.0);
                 if (i == j) r2 = 0.0;
                 double k, dk;
-                kernel_eval(p.kind, r2, k, dk);
+                kernel_eval(KIND, r2, k, dk);
                 const bool valid = (i < p.n) && (j < p.n);
                 kv[e] = valid ? os * k + ((i == j) ? (noise + jitter) : 0.0) : ((i == j) ? 1.0 : 0.0);
                 rv[e] = valid ? dk : 0.0;
@@ -349,13 +374,14 @@ __global__ void __launch_bounds__(G::THREADS) k_sym_build(SymBuildParams p) {
         }
     }
     }
+    }
 }
 
-template <class G>
-static cudaError_t launch_sym_build_cfg(SymBuildParams p, int batch, cudaStream_t stream) {
+template <class G, int KIND>
+static cudaError_t launch_sym_build_kind(SymBuildParams p, int batch, cudaStream_t stream) {
     static PerDeviceOnce attr_once; int attr_dev;
     if (attr_once.pending(attr_dev)) {
-        cudaError_t e = cudaFuncSetAttribute(k_sym_build<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_sym_build<G, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_once.mark(attr_dev);
     }
@@ -364,8 +390,12 @@ static cudaError_t launch_sym_build_cfg(SymBuildParams p, int batch, cudaStream_
     if (count <= 0) return cudaSuccess;
     if (p.max_ctas > 0 && count > p.max_ctas) count = p.max_ctas;
     dim3 grid(count, 1, batch);
-    k_sym_build<G><<<grid, G::THREADS, G::SMEM_BYTES, stream>>>(p);
+    k_sym_build<G, KIND><<<grid, G::THREADS, G::SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
+}
+template <class G>
+static cudaError_t launch_sym_build_cfg(SymBuildParams p, int batch, cudaStream_t stream) {
+    return p.kind == 0 ? launch_sym_build_kind<G, 0>(p, batch, stream) : launch_sym_build_kind<G, 1>(p, batch, stream);
 }
 
 cudaError_t launch_sym_build(const SymBuildParams& p, int batch, cudaStream_t stream) {
