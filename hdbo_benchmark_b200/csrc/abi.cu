@@ -51,7 +51,8 @@ extern "C" int hdbo_gp_fit_downdated(const hdbo_gp* gp, int need_r2, const doubl
     const int np = gp->n_pad, dp = gp->d_pad, B = gp->batch;
     const long long nn = (long long)np * np;
     TRY_CUDA(cudaMemsetAsync(gp->info, 0, sizeof(int32_t) * B, st));
-    bool piped = B == 1 && np / 128 >= PIPE_MIN_TILES;
+    static const int pipe_min_tiles = [] { const char* e = getenv("HDBO_PIPE_MIN_TILES"); return e ? atoi(e) : PIPE_MIN_TILES; }();   // (developer knob)
+    bool piped = B == 1 && np / 128 >= pipe_min_tiles;
     for (int i = 0; i < 4 && piped; i++) piped = gp->aux_streams[i] != nullptr;
     for (int i = 0; i < 12 && piped; i++) piped = gp->aux_events[i] != nullptr;
     tl_mark(gp, HDBO_PHASE_FIT_BUILD, st);
