@@ -247,12 +247,17 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # a default run takes well under a minute of GPU time: anything still alive after 7 minutes is stuck (a collective waiting for a
+    # rank that left) -- leave loudly instead of holding N GPUs until somebody's limit kills the job
+    watchdog = threading.Timer(420.0, lambda: (sys.stderr.write("bench.py: watchdog expired after 420 s, aborting\n"), sys.stderr.flush(), os._exit(3)))
+    watchdog.daemon = True
+    watchdog.start()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
         # a rank that dies must not leave the others spinning in a collective until the box is reclaimed
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=600))
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     _lib.load()
     devlib = _lib.load_dev()      # tensor-pipe ceiling probes (roofline denominators): developer library, not the product one
     peaks = _measured_peaks()
@@ -441,9 +446,14 @@ def main():
     ms_total, (best_v, best_i) = timed(step_resident, args.steps)
     tl = gp.collect_timeline()
     gp.detach_timeline()
+    # untimed: keep the same load up until the sampler has data.  Every rank decides for ITSELF how long that takes, so these steps
+    # must not contain a collective (the first version called step_resident() here: ranks left the loop at different times and the
+    # arg-max all-gather of the slower ones hung an 8-GPU run)
     t_more = time.perf_counter()
-    while len(clocks.lines) < 4 and time.perf_counter() - t_more < 3.0:      # untimed: keep the load up until the sampler has data
-        step_resident()
+    while len(clocks.lines) < 4 and time.perf_counter() - t_more < 3.0:
+        with torch.no_grad():
+            gp.argmax(acqf(Xq_dev))
+        torch.cuda.synchronize()
     torch.cuda.synchronize()
     clk = clocks.stop()
     clk["window"] = "warm-up + timed steps (+ untimed identical steps until >= 4 samples)"
