@@ -46,12 +46,6 @@ cudaError_t launch_leaf(double* Awork, double* L, double* Linv, double* Linvt, i
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 static int pipe_skip_mask() { static const int m = env_int("HDBO_PIPE_SKIP", 0); return m; }
 
-// CTA tile for a launch of `tiles128` 128x128 output tiles: enough CTAs to cover the 148 SMs, else the largest tile
-static int pipe_tile(long long tiles128) {
-    static const int t128 = env_int("HDBO_PIPE_T128", 100), t64 = env_int("HDBO_PIPE_T64", 24);
-    return tiles128 >= t128 ? 128 : (tiles128 >= t64 ? 64 : 32);
-}
-
 #define PIPE_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return _e; } while (0)
 
 // The caller builds only the first four tile columns of Khat (column-major tile order: what the first pair's chain, panel and the second
@@ -73,6 +67,7 @@ cudaError_t chol_inverse_pipelined(double* Aw, double* L, double* Li, double* Lt
     cudaEvent_t eChain = cs.ev[6];                     // L(n0..n1, c1) exists, next diagonal block updated          chain -> side, panel
     cudaEvent_t ePanel = cs.ev[7];                     // rest of the pair's panel (rows >= f) done                  panel -> side
     cudaEvent_t eHead = cs.ev[9];                      // launch A of side(p) (with the head) done                   side -> panel (-> chain)
+    // (ev[8] and ev[10] are spare: earlier schedules needed separate row / side-done events)
     auto at = [&](double* base, int r, int c) { return base + (size_t)r * 128 * ld + (size_t)c * 128; };
     const long long bs = (long long)ld * ld;
     const int skip = pipe_skip_mask();
