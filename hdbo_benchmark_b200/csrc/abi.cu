@@ -208,7 +208,7 @@ cudaError_t posterior_chunk(const hdbo_gp* gp, const PostWs& w, int64_t rows_all
         // was as long as its longest k-range (402 us for 512 candidates at n = 4096 with the DMMA pipe 93 % busy WHILE ACTIVE)
         const bool split = B == 1 && nt % 2 == 0 && nt >= 4;
         const double* add = nullptr;
-        if (split) { g.krange = KR_LE_N_SPLIT; g.C2 = w.P2 - np / 2; g.ldc2 = np / 2; add = w.P2 - np / 2; }
+        if (split) { g.krange = KR_LE_N_SPLIT; g.C2 = w.P2; g.ldc2 = np / 2; g.c2_col0 = np / 2; add = w.P2; }
         tl_mark(gp, HDBO_PHASE_VAR, st);
         e = launch_gemm_nt(g, B, st);
         if (e == cudaSuccess)

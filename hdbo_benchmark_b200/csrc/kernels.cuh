@@ -52,7 +52,7 @@ struct GemmParams {
     int lower_only;                                           // only tiles with m-tile >= n-tile (grid.x enumerates them)
     double alpha, beta;
     int tile_hint;                                            // 0: choose the CTA tile by the launch's tile count; 32 / 64 / 128: force it
-    double* C2; int ldc2;                                     // KR_*_SPLIT: second-part output, addressed like C (same row / column indices)
+    double* C2; int ldc2, c2_col0;                            // KR_*_SPLIT: second-part output: element (i, j) of C lives at C2[i * ldc2 + j - c2_col0]
 };
 
 // kernel value k(r^2) and derivative dk/dr^2 for unit outputscale.  kind: 0 Matern-5/2, 1 RBF.

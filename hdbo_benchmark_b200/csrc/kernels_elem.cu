@@ -197,7 +197,8 @@ cudaError_t launch_finalize_acq(const double* meanpart, const double* varpart, l
 }
 
 // row sums of squares of V [rows][cols] (one CTA per row, 16-byte accesses) -> out[b*bso + row]   (small-m variance path).
-// add != nullptr: columns >= add_from of V first receive the second parts of a split-K product (add[row][col], leading dimension ldadd)
+// add != nullptr: columns >= add_from of V first receive the second parts of a split-K product (add[row][col - add_from], leading
+// dimension ldadd)
 // and are written back, so that V is whole for the gradient path.
 __global__ void __launch_bounds__(256) k_row_sumsq(double* __restrict__ V, int ldv, long long bsV, int rows, int cols,
                                                    const double* __restrict__ add, int ldadd, int add_from, double* __restrict__ out, long long bso) {
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(256) k_row_sumsq(double* __restrict__ V, int l
     double s = 0.0;
     for (int j = threadIdx.x; j < cols / 2; j += 256) {
         double2 v = src[j];
-        if (ad && 2 * j >= add_from) { const double2 a = ad[j]; v.x += a.x; v.y += a.y; src[j] = v; }
+        if (ad && 2 * j >= add_from) { const double2 a = ad[j - add_from / 2]; v.x += a.x; v.y += a.y; src[j] = v; }
         s = fma(v.x, v.x, s); s = fma(v.y, v.y, s);
     }
 #pragma unroll

@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(G::THREADS) k_gemm_nt(GemmParams p) {
     }
     double* C = (part == 1 ? p.C2 : p.C) + b * p.bsC;
     const int ldc = part == 1 ? p.ldc2 : p.ldc;
+    const int col0 = part == 1 ? p.c2_col0 : 0;                 // column origin of the output buffer
     double* Ct = p.Ct ? p.Ct + b * p.bsCt : nullptr;
     typename G::Frag acc;
     // beta != 0 (the rank-128 updates of the factorisation: K = 128, so a tile is 8 k-blocks long and the C round trip is a visible
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(G::THREADS) k_gemm_nt(GemmParams p) {
             const int i = bm * G::TM + G::frag_row(mt);
 #pragma unroll
             for (int nt = 0; nt < G::NT; nt++) {
-                const double2 c = *reinterpret_cast<const double2*>(C + (size_t)i * ldc + bn * G::TN + G::frag_col(nt));
+                const double2 c = *reinterpret_cast<const double2*>(C + (size_t)i * ldc + (bn * G::TN + G::frag_col(nt) - col0));
                 acc.v[mt][nt][0] = f * c.x; acc.v[mt][nt][1] = f * c.y;
             }
         }
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(G::THREADS) k_gemm_nt(GemmParams p) {
             double2 o;
             o.x = p.alpha * acc.v[mt][nt][0];
             o.y = p.alpha * acc.v[mt][nt][1];
-            *reinterpret_cast<double2*>(C + (size_t)i * ldc + j) = o;
+            *reinterpret_cast<double2*>(C + (size_t)i * ldc + (j - col0)) = o;
             if (Ct) { Ct[(size_t)j * p.ldct + i] = o.x; Ct[(size_t)(j + 1) * p.ldct + i] = o.y; }
         }
     }

@@ -451,7 +451,7 @@ cudaError_t posterior_bwd(const hdbo_gp* gp, const BwdBuffers& w, int64_t rows_a
         g.mtiles = mt; g.ntiles = np / 128; g.kblocks = np / BK; g.krange = KR_GE_N; g.lower_only = 0; g.alpha = 1.0; g.beta = 0.0;
         // few candidates, single GP: the long half of the columns is cut at K/2 (second parts -> P2, added back by k_make_C)
         if (B == 1 && (long long)mt * (np / 128) < 148 && (np / 128) % 2 == 0 && np / 128 >= 4 && w.P2) {
-            g.krange = KR_GE_N_SPLIT; g.C2 = w.P2; g.ldc2 = np / 2; add = w.P2;
+            g.krange = KR_GE_N_SPLIT; g.C2 = w.P2; g.ldc2 = np / 2; g.c2_col0 = 0; add = w.P2;
         }
         if ((e = launch_gemm_nt(g, B, st)) != cudaSuccess) return e;
     } else {
