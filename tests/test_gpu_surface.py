@@ -290,3 +290,31 @@ def test_fast_mll_closure_matches_generic_closure(cuda_device, flavour):
     assert abs(vals[0] - vals[1]) < 1e-5 * max(1.0, abs(vals[1])), vals
     for (na, pa), (nb, pb) in zip(m_fast.named_parameters(), m_slow.named_parameters()):
         assert na == nb and float((pa - pb).abs().max()) < 2e-2 * max(1.0, float(pb.abs().max())), na
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,d,m", [(1024, 64, 48), (1500, 40, 300), (640, 24, 5)])
+def test_split_k_gradient_path_matches_oracle_autograd(cuda_device, n, d, m):
+    """Few candidates against one large GP: the two triangular products of the forward-with-state / backward pair run with the long
+    half of their columns cut at K/2 (KR_LE_N_SPLIT / KR_GE_N_SPLIT, second parts added back by k_row_sumsq / k_make_C) and the dZ
+    product splits K over the batch axis.  n_pad = 1024 and 1536 take the split, 640 (an odd number of 128-tiles) does not."""
+    from hdbo_benchmark_b200 import _lib
+    from hdbo_benchmark_b200.engine import DeviceGP
+
+    X, y, ls, os_, nz, mu = O.synthetic_problem(n, d)
+    st = O.fit_state(X, y, ls, os_, nz, mu, O.MATERN52)
+    gp = DeviceGP(X.to(cuda_device), y.to(cuda_device), O.MATERN52)
+    gp.set_hyper(ls.to(cuda_device), os_, nz, mu)
+    gp.fit()
+    Z = O.sobol_candidates(m, d, seed=5)
+    Z[: min(3, m)] = X[: min(3, m)] + 1e-3                     # near training points: the variance term matters
+    best_f = float(y.max())
+    a_o, g_o = O.acquisition_value_and_grad_autograd(st, Z, O.ACQ_LOGEI, best_f)
+    bufs = {}
+    for _ in range(2):                                          # twice: the scratch of the split products is reused
+        a, g = gp.acq_value_grad(Z.to(cuda_device).contiguous(), _lib.ACQ_LOGEI, best_f, 1.0, bufs)
+    assert float((a.cpu() - a_o).abs().max()) < REL * max(1.0, float(a_o.abs().max()))
+    assert _rel(g, g_o) < REL
+    # the forward state V kept for joint covariances is whole (second parts folded in): variance from V equals the oracle's
+    mo, vo = O.posterior(st, Z)
+    assert float(((bufs["var"].cpu() - vo).abs() / vo.abs().clamp_min(1e-8)).max()) < REL
