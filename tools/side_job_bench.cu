@@ -1,7 +1,8 @@
 // A/B harness for the persistent rank-256 update kernel of the pipelined factorisation (k_side_updates, csrc/kernels_gemm.cu):
 // C(i, j) -= A(i, 0..255) B(j, 0..255)^T over a strided job list, one CTA per SM, with globaltimer / clock64 stamps of one CTA's
 // phases (C read, pipeline fill + mainloop, C write).  Variants: the CTA tile / k-block configuration, C added in the epilogue
-// instead of read into the accumulators, two independent 128x64 warp-group pipelines per CTA (staggered by half a job).
+// instead of read into the accumulators, an L2 prefetch of the next job's C tile, two independent 128x64 warp-group pipelines per
+// CTA (staggered by half a job).
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/side_job_bench tools/side_job_bench.cu
 #include <cstdio>
 #include <cstdlib>
@@ -19,7 +20,7 @@ struct Stamps { unsigned long long ns[64][4]; long long clk[64][4]; };
 // job q -> C tile (i, j) of a T x T tile matrix, all distinct inside one launch; operands = tile rows i, j of Lm (K = kblocks * 16)
 __device__ __forceinline__ void job_tiles(int q, int T, int& i, int& j) { i = q / T; j = q % T; }
 
-template <class G, int EPI_ADD>
+template <class G, int EPI_ADD, int PREFETCH = 0>
 __global__ void __launch_bounds__(G::THREADS, 1) k_side(const double* __restrict__ Lm, double* __restrict__ Cm, int ld, int T,
                                                         int njobs, int kblocks, Stamps* st) {
     extern __shared__ __align__(16) double smem[];
@@ -44,6 +45,15 @@ __global__ void __launch_bounds__(G::THREADS, 1) k_side(const double* __restrict
                 }
         }
         if (rec) { st->ns[n][1] = gtimer(); st->clk[n][1] = clock64(); }
+        if (PREFETCH && job + (int)gridDim.x < njobs) {          // the next job's C tile -> L2 (1024 lines of 128 B, 4 per thread)
+            int ni, nj; job_tiles(job + gridDim.x, T, ni, nj);
+            const double* Cn = Cm + (size_t)ni * 128 * lds + (size_t)nj * 128;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int l = threadIdx.x + u * 256;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(Cn + (size_t)(l >> 3) * lds + (l & 7) * 16));
+            }
+        }
         G::mainloop(A, ld, B, ld, 0, kblocks * 16 / G::BK, smem, acc);
         if (rec) { st->ns[n][2] = gtimer(); st->clk[n][2] = clock64(); }
 #pragma unroll
@@ -160,6 +170,9 @@ int main(int argc, char** argv) {
     report("g128_bk16_c_into_acc", ctas, njobs, kblocks, ms, st);
     ms = timeit([&] { k_side<G128, 1><<<ctas, 256, G128::SMEM_BYTES>>>(Lm, Cm, ld, T, njobs, kblocks, st); });
     report("g128_bk16_c_in_epilogue", ctas, njobs, kblocks, ms, st);
+    CK(cudaFuncSetAttribute(k_side<G128, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G128::SMEM_BYTES));
+    ms = timeit([&] { k_side<G128, 0, 1><<<ctas, 256, G128::SMEM_BYTES>>>(Lm, Cm, ld, T, njobs, kblocks, st); });
+    report("g128_bk16_c_into_acc_l2_prefetch_next_c", ctas, njobs, kblocks, ms, st);
     ms = timeit([&] { k_side<G128W, 0><<<ctas, 256, G128W::SMEM_BYTES>>>(Lm, Cm, ld, T, njobs, kblocks, st); });
     report("g128_bk32_c_into_acc", ctas, njobs, kblocks, ms, st);
     ms = timeit([&] { k_side_2g<<<ctas, 256, 2 * GH::SMEM_BYTES>>>(Lm, Cm, ld, T, njobs, kblocks, 0, st); });
