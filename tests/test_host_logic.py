@@ -210,3 +210,18 @@ def test_bench_workload_generator_matches_the_oracle_generator():
                         assert "world == 1" in guard and ("no_cpu_baseline" in guard or "cpu and" in guard), (fname, node.lineno, guard)
         top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
         assert not any("oracle" in ast.dump(n) for n in top), fname
+
+
+def test_bench_untimed_sampling_loop_contains_no_collective():
+    """bench.py keeps the GPU loaded after the timed region until the clock sampler has data; every rank leaves that loop at its own
+    time, so a collective inside it deadlocks multi-GPU runs (it did: an 8-GPU run hung on the arg-max all-gather).  Static guard."""
+    import ast
+    from pathlib import Path
+
+    src = (Path(__file__).resolve().parents[1] / "bench.py").read_text()
+    tree = ast.parse(src)
+    loops = [n for n in ast.walk(tree) if isinstance(n, ast.While) and "clocks.lines" in ast.unparse(n.test)]
+    assert len(loops) == 1, "the sampling loop of bench.py moved: update this guard"
+    body = ast.unparse(loops[0])
+    for forbidden in ("global_argmax", "dist.", "step_resident", "step_e2e", "timed(", "barrier("):
+        assert forbidden not in body, f"collective-bearing call `{forbidden}` inside the rank-local sampling loop"
